@@ -1,0 +1,212 @@
+/* tod.h — C ABI of libtod_b200.so, the B200-native (sm_100a) implementation of the per-frame
+ * perception hot path of icf3ver/tiny-object-detection.
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (file:line under /root/reference).  The reference has no FFI of its own for this path:
+ * the boundary is three crate-internal Rust signatures, so these are the symbols a
+ * thin `extern "C"` Rust crate binds (ffi/src/lib.rs shows that binding; INTEGRATION.md explains
+ * where it is spliced into src/yolact.rs and src/scene.rs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types;
+ *   - every function returns 0 (TOD_OK) or a negative tod_status; it never aborts.  The Rust shim
+ *     `.expect()`s the code to keep the reference's panic-on-error behaviour;
+ *   - tod_last_error() returns a thread-local human-readable message for the last failure;
+ *   - handles are NOT thread-safe (mirrors `&mut self`, yolact.rs:39): one handle per thread / GPU;
+ *   - buffers passed to the non-`_device` entry points are HOST memory owned by the caller (pinned
+ *     memory recommended); buffers passed to `_device` entry points are device pointers on the
+ *     handle's GPU and the call is asynchronous on the given CUDA stream (NULL = handle's stream);
+ *   - there is NO CPU fallback: without a CUDA device every create call fails with
+ *     TOD_ERR_NO_DEVICE.
+ */
+#ifndef TOD_H_
+#define TOD_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOD_ABI_VERSION 1
+
+typedef enum tod_status {
+  TOD_OK = 0,
+  TOD_ERR_INVALID_ARG = -1,
+  TOD_ERR_IO = -2,          /* model file unreadable */
+  TOD_ERR_MODEL = -3,       /* malformed / unsupported .tflite (e.g. edgetpu-custom-op) */
+  TOD_ERR_CUDA = -4,        /* CUDA runtime / driver error */
+  TOD_ERR_NO_DEVICE = -5,   /* no usable sm_100 device */
+  TOD_ERR_CAPACITY = -6,    /* batch larger than the handle was created for */
+  TOD_ERR_UNSUPPORTED = -7
+} tod_status;
+
+/* positive return: the call completed but the *reference* would not have (the literal
+ * flood fill of yolact.rs:60-77 never terminates when two class-3 cells touch). */
+#define TOD_WARN_REFERENCE_DIVERGES 1
+
+const char* tod_last_error(void);
+int tod_abi_version(void);
+int tod_device_count(int* count);
+
+/* ======================================================================================
+ * Scene: depth -> point cloud / height map / connection weights.
+ * Replaces the GPU half of `append_scene` (src/scene.rs:147-331): the Vulkan dispatch of
+ * shaders/pt_cloud.comp (scene.rs:238-247) and shaders/pt_cloud_weights.comp (scene.rs:249-260),
+ * the uploads (scene.rs:197-198) and the four read-backs (scene.rs:246,257-259).
+ * ====================================================================================== */
+typedef struct tod_scene tod_scene;
+
+typedef struct tod_scene_params {
+  int32_t width;                 /* pt_cloud.comp:23  (640; 320 for Carmine, README.md:18) */
+  int32_t height;                /* pt_cloud.comp:24  (480; 240) */
+  float max_depth_in;            /* pt_cloud.comp:25 */
+  float x_fov;                   /* pt_cloud.comp:28 */
+  float y_fov;                   /* pt_cloud.comp:27 */
+  float bot_avoidance_const;     /* pt_cloud.comp:32 */
+  int32_t bot_norm_const;        /* pt_cloud.comp:36 */
+  int32_t terrain_norm_const;    /* pt_cloud.comp:37 */
+  float bump_err;                /* pt_cloud.comp:39 */
+  int32_t sample_shift;          /* 0 = texelFetch(x,y) (default), 1 = what the Pi's V3D did */
+  int32_t weights_mode;          /* 0 = literal (pack()==0), 1 = intent (true neighbour distances) */
+  int32_t max_batch;             /* frames per call the handle is sized for */
+} tod_scene_params;
+
+/* fills the reference's constants (pt_cloud.comp:23-39) */
+void tod_scene_default_params(tod_scene_params* p);
+
+/* replaces the per-call Vulkan object creation of scene.rs:152-224 (hoisted: done once) */
+int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out);
+void tod_scene_destroy(tod_scene* s);
+
+/* One call = n independent frames through both shaders (scene.rs:274-282).
+ *   depth   u16[n][H][W]   (R16_UINT upload, scene.rs:197)
+ *   target  u16[n][H][W]   low byte = class, high byte = id (R8G8_UINT upload, scene.rs:198)
+ *   map     u32[n][H][W]   height map        (map_dest,          scene.rs:231,246)
+ *   world4  f32[n][H][W][4]                  (world_dest,        scene.rs:232,257)
+ *   conn0   f32[n][H][W][4]                  (connections0_dest, scene.rs:233,258)
+ *   conn1   f32[n][H][W][4]                  (connections1_dest, scene.rs:234,259)
+ *   balls4  f32[n][100][4]                   (ball_buffer,       scene.rs:211)
+ * Any output pointer may be NULL to skip that read-back. Blocks until the results are in place
+ * (scene.rs:282 `future.wait`). */
+int tod_scene_append_batch(tod_scene* s, const uint16_t* depth, const uint16_t* target, int n, uint32_t* map,
+                           float* world4, float* conn0, float* conn1, float* balls4);
+
+/* Same, device pointers, asynchronous on `stream` (a cudaStream_t; NULL = the handle's stream). */
+int tod_scene_append_batch_device(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n,
+                                  uint32_t* d_map, float* d_world4, float* d_conn0, float* d_conn1,
+                                  float* d_balls4, void* stream);
+
+/* `Scene` materialisation (scene.rs:312-327), fused on the device: from the device-resident results of
+ * the last append call for frame `frame`, fills host buffers
+ *   height f32[H*W], pos f32[H*W][3], balls i32[100][2], connections f32[H*W][8]. */
+int tod_scene_materialize(tod_scene* s, int frame, float* height, float* pos3, int32_t* balls2,
+                          float* connections8);
+
+/* average device time (ms) of the dominant kernel (pt_stamp) over the last append call */
+int tod_scene_last_kernel_ms(tod_scene* s, float* stamp_ms, float* weights_ms);
+
+/* ======================================================================================
+ * Yolact: int8 YOLACT inference + post-processing.
+ * Replaces `Yolact::init` (src/yolact.rs:17-37) and `Yolact::classify` (yolact.rs:39-41,192-234),
+ * i.e. interpreter.invoke() (yolact.rs:163) and everything around it.
+ * ====================================================================================== */
+typedef struct tod_yolact tod_yolact;
+
+typedef struct tod_yolact_options {
+  int32_t max_tiles;        /* 224x224 tiles per call the handle is sized for (2 per camera frame) */
+  int32_t id_mode;          /* 0 = literal terrible_id + `&` pack, 1 = intent (CCL + `|`) */
+  float conf_thresh;        /* 0.05  YOLACT detection score threshold */
+  float nms_thresh;         /* 0.5   Fast-NMS IoU threshold */
+  int32_t top_k;            /* 200   per-class candidates */
+  int32_t max_dets;         /* 100 */
+  int32_t use_cuda_graph;   /* 1 = capture the per-batch pipeline in a CUDA graph */
+  int32_t conv_impl;        /* 0 = tcgen05 int8 implicit GEMM wherever the layer shape allows (default),
+                               1 = CUDA-core direct convolution everywhere (on-device cross-check) */
+  int32_t fusion;           /* 0 = every TFLite tensor is materialised (each one can be fetched and compared),
+                               1 = PAD folded into the following convolution (default) */
+} tod_yolact_options;
+
+void tod_yolact_default_options(tod_yolact_options* o);
+
+/* <- Yolact::init (yolact.rs:17-37).  `tflite_path` replaces the hard-coded path of yolact.rs:19; a
+ * model holding the edgetpu custom op is rejected with TOD_ERR_MODEL (use the CPU model,
+ * data/FRC_model.tflite). */
+int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_options* opts, tod_yolact** out);
+void tod_yolact_destroy(tod_yolact* y);
+
+/* <- Yolact::classify (yolact.rs:39): in place on a caller-owned 640x480 frame, px in =
+ * r<<24|g<<16|b<<8 (scene.rs:86), px out = [resized class, 0, 0, 0] big-endian (yolact.rs:231-233). */
+int tod_yolact_classify(tod_yolact* y, uint32_t* frame, int width, int height);
+/* batched form: n frames, contiguous */
+int tod_yolact_classify_batch(tod_yolact* y, uint32_t* frames, int n, int width, int height);
+/* device-resident batched form: d_frames in/out on the GPU, optional d_target u16[n][H][W] receives the
+ * `(px & 0xFFFF) as u16` extraction of scene.rs:93 so the scene path can consume it without a host trip */
+int tod_yolact_classify_batch_device(tod_yolact* y, uint32_t* d_frames, int n, int width, int height,
+                                     uint16_t* d_target, void* stream);
+
+/* Parses a .tflite without touching a GPU (what FlatBufferModel::build_from_file + InterpreterBuilder check,
+ * yolact.rs:18-29): operator / tensor counts and the multiply-accumulates of one invoke. */
+int tod_model_inspect(const char* tflite_path, int32_t* num_ops, int32_t* num_tensors, int64_t* macs);
+
+/* Anchor priors f32[n][4] (cx,cy,w,h in [0,1]) for the detection head.  The handle computes the YOLACT priors
+ * for the FRC head (3147 = 3 x (28^2+14^2+7^2+4^2+2^2)) itself; any other head must be given its priors. */
+int tod_yolact_set_priors(tod_yolact* y, const float* priors, int n);
+
+/* 1 if some tile of the last classify / infer call would have hung the reference's flood fill (id_mode 0);
+ * synchronises the handle's stream. */
+int tod_yolact_last_diverged(tod_yolact* y, int* diverged);
+
+/* Model introspection (what interpreter.tensor_info gives the reference, yolact.rs:150,169-176) */
+int tod_yolact_num_outputs(const tod_yolact* y);
+int tod_yolact_output_info(const tod_yolact* y, int index, int32_t shape4[4], float* scale, int32_t* zero_point,
+                           int32_t* elems);
+int tod_yolact_num_tensors(const tod_yolact* y);
+int tod_yolact_num_ops(const tod_yolact* y);
+int tod_yolact_tensor_info(const tod_yolact* y, int tensor, int32_t shape4[4], int32_t* type, float* scale,
+                           int32_t* zero_point, int32_t* elems);
+
+typedef struct tod_detections {
+  int32_t max_dets;       /* capacity per tile of the arrays below */
+  int32_t* count;         /* [n]                       detections per tile */
+  float* boxes;           /* [n][max_dets][4]          x1,y1,x2,y2 in [0,1] */
+  float* scores;          /* [n][max_dets] */
+  int32_t* classes;       /* [n][max_dets]             0-based foreground class */
+  int32_t* priors;        /* [n][max_dets]             prior index == NMS keep index */
+  float* masks;           /* [n][max_dets][56][56]     sigmoid + crop, may be NULL */
+  uint8_t* masks_bin;     /* [n][max_dets][56][56]     > 0.5, may be NULL */
+} tod_detections;
+
+/* Runs the int8 graph on n RGB tiles u8[n][224][224][3] (== interpreter.invoke(), yolact.rs:161-163).
+ *   outputs_u8[k]  (k < num_outputs, may be NULL) receives output tensor k, u8[n][elems_k]
+ *   tile_classes   (may be NULL) u32[n][224][224]: the literal postprocess() result (yolact.rs:90-131)
+ *   dets           (may be NULL) YOLACT decode + Fast-NMS + mask assembly (north-star; not in the reference)
+ * Returns TOD_OK, or TOD_WARN_REFERENCE_DIVERGES if id_mode == 0 and some tile would hang the reference. */
+int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8,
+                           uint32_t* tile_classes, tod_detections* dets);
+
+/* Device-resident form used by the fused RGB-D pipeline and the benchmark: input tiles already on the GPU;
+ * results stay on the GPU (fetch with tod_yolact_fetch_*).  Asynchronous on `stream`. */
+int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int n, void* stream);
+int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out);
+int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t out_bytes);
+int tod_yolact_fetch_tile_classes(tod_yolact* y, int n, uint32_t* out);
+int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* dets);
+
+/* accounting for bench.py: kernels launched per infer call, MACs per tile, and per-kernel device time */
+int tod_yolact_stats(const tod_yolact* y, int64_t* macs_per_tile, int32_t* launches_per_call,
+                     int32_t* tc_conv_layers);
+/* times every op of the graph once with CUDA events for n resident tiles: fills up to `cap` entries of
+ * ms[] (per op, graph order) and returns the op count */
+int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int cap);
+
+/* ======================================================================================
+ * Micro-benchmark used as the int8 roofline denominator (MEASURED_PEAKS.json has no int8 peak,
+ * SURVEY §8d): a plain tcgen05 kind::i8 GEMM  C[M,N] s32 = A[M,K] s8 * B[N,K]^T s8.
+ * ====================================================================================== */
+int tod_i8_gemm_selftest(int device, int M, int N, int K, int iters, float* ms_per_iter, double* max_abs_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOD_H_ */

@@ -1,0 +1,75 @@
+"""CUDA int8 graph vs the CPU oracle's TFLite restatement: every tensor bit-exact (fusion off),
+outputs bit-exact (fusion on, CUDA graph on), batch order independence.  Calls go through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+OPS_WITH_DATA = None
+
+
+def _oracle_run(path, tile):
+    m = oracle.Model(path)
+    m.invoke(tile, threads=8)
+    return m
+
+
+@pytest.mark.parametrize("conv_impl", [1, 0])
+def test_small_model_every_tensor(tod, models, conv_impl):
+    _, small = models
+    tiles = synth.rgb_tiles(3, S=64, seed=31)
+    y = tod.Yolact.init(small, max_tiles=3, fusion=0, use_cuda_graph=0, conv_impl=conv_impl)
+    y.infer_tiles(tiles, detections=False)
+    for t in range(3):
+        m = _oracle_run(small, tiles[t])
+        for op in range(m.num_ops):
+            ti = m.op_output(op)
+            want = m.tensor(ti)
+            got = y.fetch_tensor(ti, 3)[t]
+            assert got.dtype == want.dtype
+            assert np.array_equal(got.reshape(-1), want.reshape(-1)), "tile %d op %d (code %d) tensor %d differs in %d of %d" % (
+                t, op, m.op_code(op), ti, (got.reshape(-1) != want.reshape(-1)).sum(), want.size)
+
+
+@pytest.mark.parametrize("conv_impl", [1, 0])
+def test_full_model_outputs(tod, models, conv_impl):
+    full, _ = models
+    tiles = synth.rgb_tiles(2, seed=32)
+    y = tod.Yolact.init(full, max_tiles=4, conv_impl=conv_impl)  # fusion + CUDA graph (defaults)
+    res = y.infer_tiles(tiles, detections=False)
+    for t in range(2):
+        m = _oracle_run(full, tiles[t])
+        for k, ti in enumerate(m.outputs):
+            want = m.tensor(ti)
+            assert np.array_equal(res["outputs"][k][t].reshape(-1), want.reshape(-1)), "tile %d output %d" % (t, k)
+    st = y.stats()
+    assert st["macs_per_tile"] == oracle.Model(full).macs() or st["macs_per_tile"] == 5618874112
+
+
+def test_fusion_and_graph_do_not_change_bytes(tod, models):
+    _, small = models
+    tiles = synth.rgb_tiles(5, S=64, seed=33)
+    a = tod.Yolact.init(small, max_tiles=5, fusion=0, use_cuda_graph=0).infer_tiles(tiles)
+    b = tod.Yolact.init(small, max_tiles=8, fusion=1, use_cuda_graph=1)
+    rb = b.infer_tiles(tiles)
+    rb2 = b.infer_tiles(tiles[::-1].copy())  # replayed graph, reversed batch
+    for k in range(5):
+        assert np.array_equal(a["outputs"][k], rb["outputs"][k])
+        assert np.array_equal(a["outputs"][k], rb2["outputs"][k][::-1])
+    assert np.array_equal(a["tile_classes"], rb["tile_classes"])
+
+
+def test_errors(tod, models, tmp_path):
+    _, small = models
+    with pytest.raises(tod.TodError):
+        tod.Yolact.init(str(tmp_path / "missing.tflite"))
+    bad = tmp_path / "bad.tflite"
+    bad.write_bytes(open(small, "rb").read()[:4000])
+    with pytest.raises(tod.TodError):
+        tod.Yolact.init(str(bad))
+    y = tod.Yolact.init(small, max_tiles=2)
+    with pytest.raises(tod.TodError):
+        y.infer_tiles(synth.rgb_tiles(3, S=64))

@@ -1,0 +1,66 @@
+// TFLite full-integer fixed-point arithmetic for the device epilogues and the host planner.
+//
+// The reference reaches this arithmetic through interpreter.invoke() (/root/reference/src/yolact.rs:163;
+// TensorFlow Lite C++ via crate tflite 0.9.0, Cargo.lock:1106-1108 — not vendored).  The rules are the
+// published gemmlowp ones: a Q31 multiplier applied with a rounding doubling
+// high multiply, then a rounding right shift (round half away from zero), both kept in integers so the
+// result is bit-identical to the CPU interpreter.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define TOD_HD __host__ __device__ __forceinline__
+#else
+#define TOD_HD inline
+#endif
+
+namespace tod {
+
+// (a*b*2 + 2^31 rounding) >> 32 with saturation of the single overflow case; the division by 2^31
+// truncates toward zero, hence the sign-dependent nudge.
+TOD_HD int32_t sat_round_doubling_high_mul(int32_t a, int32_t b) {
+  if (a == b && a == INT32_MIN) return INT32_MAX;
+  const int64_t prod = int64_t(a) * int64_t(b);
+  const int64_t nudged = prod + (prod >= 0 ? (int64_t(1) << 30) : (int64_t(1) - (int64_t(1) << 30)));
+  // truncating division by 2^31: add (2^31 - 1) to negatives before the arithmetic shift
+  const int64_t bias = (nudged >> 63) & ((int64_t(1) << 31) - 1);
+  return int32_t((nudged + bias) >> 31);
+}
+
+// x / 2^e rounded to nearest, ties away from zero
+TOD_HD int32_t round_divide_pot(int32_t x, int e) {
+  const int32_t mask = int32_t((int64_t(1) << e) - 1);
+  const int32_t rem = x & mask;
+  const int32_t thr = (mask >> 1) + (x < 0 ? 1 : 0);
+  return (x >> e) + (rem > thr ? 1 : 0);
+}
+
+// MultiplyByQuantizedMultiplier, double-rounding form (the TFLite default build)
+TOD_HD int32_t mul_by_quant_mult(int32_t x, int32_t q, int shift) {
+  const int left = shift > 0 ? shift : 0;
+  const int right = shift > 0 ? 0 : -shift;
+  return round_divide_pot(sat_round_doubling_high_mul(int32_t(uint32_t(x) << left), q), right);
+}
+
+// host only: real multiplier -> (Q31 mantissa, exponent)
+inline void quantize_multiplier(double m, int32_t* q, int* shift) {
+  if (m == 0.0) {
+    *q = 0;
+    *shift = 0;
+    return;
+  }
+  const double frac = std::frexp(m, shift);
+  int64_t fixed = int64_t(std::round(frac * double(int64_t(1) << 31)));
+  if (fixed == (int64_t(1) << 31)) {
+    fixed /= 2;
+    ++*shift;
+  }
+  if (*shift < -31) {
+    *shift = 0;
+    fixed = 0;
+  }
+  *q = int32_t(fixed);
+}
+
+}  // namespace tod

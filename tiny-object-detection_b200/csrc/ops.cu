@@ -1,0 +1,380 @@
+// CUDA-core kernels of the int8 graph: the layers that have no tensor-core mapping (depthwise,
+// element-wise, resampling) and a direct convolution used for the shapes the tcgen05 implicit-GEMM
+// path does not take (Cin = 3 stem, strided 3x3) and as its on-device cross-check.
+//
+// Arithmetic follows TFLite's integer kernels; the reference runs them inside
+// interpreter.invoke() (/root/reference/src/yolact.rs:163).
+#include "ops.h"
+
+#include "fixedpoint.cuh"
+
+namespace tod {
+namespace {
+
+__device__ __forceinline__ int8_t requant_store(int32_t acc, int32_t mult, int32_t shift, const Requant& rq) {
+  int32_t v = mul_by_quant_mult(acc, mult, shift) + rq.out_zp;
+  v = max(rq.act_min, min(rq.act_max, v));
+  return int8_t(v);
+}
+
+// ------------------------------------------------------------------ direct convolution
+// One thread: one output pixel x OCT output channels.  A warp covers 32 consecutive pixels of the
+// same channel group, so weight loads are warp-uniform (one transaction) and each lane streams its
+// own pixel's channels.  acc = sum in*w  +  (-zp) * sum_{valid taps} wsum[tap]  + bias.
+template <int OCT, bool VEC4>
+__global__ void __launch_bounds__(128) conv_direct_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                         const int8_t* __restrict__ w,
+                                                         const int32_t* __restrict__ bias,
+                                                         const int32_t* __restrict__ wsum, int32_t in_zp, ConvGeom g,
+                                                         Requant rq, int8_t* __restrict__ out, int64_t out_ts,
+                                                         int tiles) {
+  const int64_t pix = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = int64_t(tiles) * g.OH * g.OW;
+  if (pix >= total) return;
+  const int oc0 = blockIdx.y * OCT;
+  const int ox = int(pix % g.OW);
+  const int oy = int((pix / g.OW) % g.OH);
+  const int t = int(pix / (int64_t(g.OW) * g.OH));
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  const int taps = g.KH * g.KW;
+  const int64_t wstride = int64_t(taps) * g.IC;
+
+  int32_t acc[OCT];
+#pragma unroll
+  for (int j = 0; j < OCT; ++j) acc[j] = 0;
+
+  for (int fy = 0; fy < g.KH; ++fy) {
+    const int iy = oy * g.stride_h - g.pad_top + fy * g.dil_h;
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int fx = 0; fx < g.KW; ++fx) {
+      const int ix = ox * g.stride_w - g.pad_left + fx * g.dil_w;
+      if (ix < 0 || ix >= g.IW) continue;
+      const int tap = fy * g.KW + fx;
+      const int8_t* ip = tin + (int64_t(iy) * g.IW + ix) * g.IC;
+      const int8_t* wp = w + int64_t(oc0) * wstride + int64_t(tap) * g.IC;
+#pragma unroll
+      for (int j = 0; j < OCT; ++j)
+        if (oc0 + j < g.OC) acc[j] -= in_zp * __ldg(wsum + int64_t(oc0 + j) * taps + tap);
+      if (VEC4) {
+        for (int ic = 0; ic < g.IC; ic += 4) {
+          const int a = *reinterpret_cast<const int*>(ip + ic);
+#pragma unroll
+          for (int j = 0; j < OCT; ++j)
+            if (oc0 + j < g.OC) acc[j] = __dp4a(a, __ldg(reinterpret_cast<const int*>(wp + j * wstride + ic)), acc[j]);
+        }
+      } else {
+        for (int ic = 0; ic < g.IC; ++ic) {
+          const int a = ip[ic];
+#pragma unroll
+          for (int j = 0; j < OCT; ++j)
+            if (oc0 + j < g.OC) acc[j] += a * int(__ldg(wp + j * wstride + ic));
+        }
+      }
+    }
+  }
+  int8_t* op = out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + oc0;
+#pragma unroll
+  for (int j = 0; j < OCT; ++j) {
+    if (oc0 + j < g.OC) {
+      const int32_t a = acc[j] + (bias ? __ldg(bias + oc0 + j) : 0);
+      op[j] = requant_store(a, __ldg(rq.mult + oc0 + j), __ldg(rq.shift + oc0 + j), rq);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ depthwise 3x3 (any KHxKW)
+// One thread: one output pixel x 4 consecutive channels (int8x4 loads, coalesced along C).
+__global__ void __launch_bounds__(256) depthwise_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                       const int8_t* __restrict__ w,
+                                                       const int32_t* __restrict__ bias, int32_t in_zp, ConvGeom g,
+                                                       Requant rq, int8_t* __restrict__ out, int64_t out_ts,
+                                                       int tiles) {
+  const int c4n = g.OC >> 2;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = int64_t(tiles) * g.OH * g.OW * c4n;
+  if (idx >= total) return;
+  const int c = int(idx % c4n) * 4;
+  int64_t p = idx / c4n;
+  const int ox = int(p % g.OW);
+  p /= g.OW;
+  const int oy = int(p % g.OH);
+  const int t = int(p / g.OH);
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  int32_t acc[4] = {0, 0, 0, 0};
+  for (int fy = 0; fy < g.KH; ++fy) {
+    const int iy = oy * g.stride_h - g.pad_top + fy * g.dil_h;
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int fx = 0; fx < g.KW; ++fx) {
+      const int ix = ox * g.stride_w - g.pad_left + fx * g.dil_w;
+      if (ix < 0 || ix >= g.IW) continue;
+      const char4 a = *reinterpret_cast<const char4*>(tin + (int64_t(iy) * g.IW + ix) * g.IC + c);
+      const char4 k = __ldg(reinterpret_cast<const char4*>(w + (int64_t(fy) * g.KW + fx) * g.OC + c));
+      acc[0] += (int(a.x) - in_zp) * int(k.x);
+      acc[1] += (int(a.y) - in_zp) * int(k.y);
+      acc[2] += (int(a.z) - in_zp) * int(k.z);
+      acc[3] += (int(a.w) - in_zp) * int(k.w);
+    }
+  }
+  char4 o;
+  int8_t* ob = reinterpret_cast<int8_t*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int32_t a = acc[j] + (bias ? __ldg(bias + c + j) : 0);
+    ob[j] = requant_store(a, __ldg(rq.mult + c + j), __ldg(rq.shift + c + j), rq);
+  }
+  *reinterpret_cast<char4*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c) = o;
+}
+
+// scalar-channel variant for C % 4 != 0
+__global__ void __launch_bounds__(256) depthwise_scalar_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                              const int8_t* __restrict__ w,
+                                                              const int32_t* __restrict__ bias, int32_t in_zp,
+                                                              ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                              int64_t out_ts, int tiles) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = int64_t(tiles) * g.OH * g.OW * g.OC;
+  if (idx >= total) return;
+  const int c = int(idx % g.OC);
+  int64_t p = idx / g.OC;
+  const int ox = int(p % g.OW);
+  p /= g.OW;
+  const int oy = int(p % g.OH);
+  const int t = int(p / g.OH);
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  int32_t acc = 0;
+  for (int fy = 0; fy < g.KH; ++fy) {
+    const int iy = oy * g.stride_h - g.pad_top + fy * g.dil_h;
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int fx = 0; fx < g.KW; ++fx) {
+      const int ix = ox * g.stride_w - g.pad_left + fx * g.dil_w;
+      if (ix < 0 || ix >= g.IW) continue;
+      acc += (int(tin[(int64_t(iy) * g.IW + ix) * g.IC + c]) - in_zp) * int(__ldg(w + (int64_t(fy) * g.KW + fx) * g.OC + c));
+    }
+  }
+  acc += bias ? __ldg(bias + c) : 0;
+  out[int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c] = requant_store(acc, __ldg(rq.mult + c), __ldg(rq.shift + c), rq);
+}
+
+// ------------------------------------------------------------------ ADD (residual / FPN merge)
+__device__ __forceinline__ int8_t add_one(int a, int b, const AddParams& p) {
+  const int32_t xa = (a - p.zp_a) * (1 << 20);
+  const int32_t xb = (b - p.zp_b) * (1 << 20);
+  const int32_t ya = mul_by_quant_mult(xa, p.mult_a, p.shift_a);
+  const int32_t yb = mul_by_quant_mult(xb, p.mult_b, p.shift_b);
+  int32_t r = mul_by_quant_mult(ya + yb, p.mult_out, p.shift_out) + p.zp_out;
+  r = max(p.act_min, min(p.act_max, r));
+  return int8_t(r);
+}
+
+__global__ void __launch_bounds__(256) add_kernel(const int8_t* __restrict__ a, int64_t a_ts,
+                                                 const int8_t* __restrict__ b, int64_t b_ts, int8_t* __restrict__ out,
+                                                 int64_t out_ts, int64_t elems, int tiles, AddParams p, bool vec) {
+  const int t = blockIdx.y;
+  const int8_t* pa = a + int64_t(t) * a_ts;
+  const int8_t* pb = b + int64_t(t) * b_ts;
+  int8_t* po = out + int64_t(t) * out_ts;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (vec) {  // 16 bytes per thread-iteration
+    const int64_t n16 = elems >> 4;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const int4 va = reinterpret_cast<const int4*>(pa)[i];
+      const int4 vb = reinterpret_cast<const int4*>(pb)[i];
+      int4 vo;
+      const int8_t* ba = reinterpret_cast<const int8_t*>(&va);
+      const int8_t* bb = reinterpret_cast<const int8_t*>(&vb);
+      int8_t* bo = reinterpret_cast<int8_t*>(&vo);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bo[j] = add_one(ba[j], bb[j], p);
+      reinterpret_cast<int4*>(po)[i] = vo;
+    }
+    for (int64_t i = (n16 << 4) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride)
+      po[i] = add_one(pa[i], pb[i], p);
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) po[i] = add_one(pa[i], pb[i], p);
+  }
+}
+
+// ------------------------------------------------------------------ byte LUT (QUANTIZE / RELU / TANH)
+__global__ void __launch_bounds__(256) lut_kernel(const uint8_t* __restrict__ in, int64_t in_ts,
+                                                 uint8_t* __restrict__ out, int64_t out_ts, int64_t elems,
+                                                 const uint8_t* __restrict__ lut, bool vec) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.y;
+  const uint8_t* pi = in + int64_t(t) * in_ts;
+  uint8_t* po = out + int64_t(t) * out_ts;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (vec) {
+    const int64_t n16 = elems >> 4;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const uint4 v = reinterpret_cast<const uint4*>(pi)[i];
+      uint4 o;
+      const uint8_t* bv = reinterpret_cast<const uint8_t*>(&v);
+      uint8_t* bo = reinterpret_cast<uint8_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bo[j] = s_lut[bv[j]];
+      reinterpret_cast<uint4*>(po)[i] = o;
+    }
+    for (int64_t i = (n16 << 4) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride)
+      po[i] = s_lut[pi[i]];
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) po[i] = s_lut[pi[i]];
+  }
+}
+
+// ------------------------------------------------------------------ PAD
+__global__ void __launch_bounds__(256) pad_kernel(const int8_t* __restrict__ in, int64_t in_ts, int H, int W, int C,
+                                                 int pt, int pl, int OH, int OW, int8_t fill, int8_t* __restrict__ out,
+                                                 int64_t out_ts) {
+  const int t = blockIdx.y;
+  const int64_t total = int64_t(OH) * OW * C;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = int(i % C);
+    const int x = int((i / C) % OW) - pl;
+    const int y = int(i / (int64_t(C) * OW)) - pt;
+    int8_t v = fill;
+    if (x >= 0 && x < W && y >= 0 && y < H) v = in[int64_t(t) * in_ts + (int64_t(y) * W + x) * C + c];
+    out[int64_t(t) * out_ts + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ RESIZE_BILINEAR (integer, 10-bit weights)
+__device__ __forceinline__ void resize_axis(int o, int scale10, int in_size, bool half_pixel, int* v, int* lo, int* hi) {
+  int sv = o * scale10;
+  if (half_pixel) sv += scale10 / 2 - (1 << 9);
+  *v = sv;
+  *lo = max(sv / (1 << 10), 0);
+  *hi = min((sv + (1 << 10) - 1) / (1 << 10), in_size - 1);
+}
+
+__global__ void __launch_bounds__(256) resize_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
+                                                    int C, int8_t* __restrict__ out, int64_t out_ts, int OH, int OW,
+                                                    int hs, int ws, bool half_pixel) {
+  const int t = blockIdx.y;
+  const int c4n = C >> 2;
+  const int64_t total = int64_t(OH) * OW * c4n;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = int(i % c4n) * 4;
+    const int x = int((i / c4n) % OW);
+    const int y = int(i / (int64_t(c4n) * OW));
+    int iy, y0, y1, ix, x0, x1;
+    resize_axis(y, hs, IH, half_pixel, &iy, &y0, &y1);
+    resize_axis(x, ws, IW, half_pixel, &ix, &x0, &x1);
+    const int64_t wy1 = iy - (1 << 10) * y0, wy0 = (1 << 10) - wy1;
+    const int64_t wx1 = ix - (1 << 10) * x0, wx0 = (1 << 10) - wx1;
+    const char4 p00 = *reinterpret_cast<const char4*>(tin + (int64_t(y0) * IW + x0) * C + c);
+    const char4 p10 = *reinterpret_cast<const char4*>(tin + (int64_t(y1) * IW + x0) * C + c);
+    const char4 p01 = *reinterpret_cast<const char4*>(tin + (int64_t(y0) * IW + x1) * C + c);
+    const char4 p11 = *reinterpret_cast<const char4*>(tin + (int64_t(y1) * IW + x1) * C + c);
+    const int8_t* a = reinterpret_cast<const int8_t*>(&p00);
+    const int8_t* b = reinterpret_cast<const int8_t*>(&p10);
+    const int8_t* d = reinterpret_cast<const int8_t*>(&p01);
+    const int8_t* e = reinterpret_cast<const int8_t*>(&p11);
+    char4 o;
+    int8_t* ob = reinterpret_cast<int8_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t o20 = int64_t(a[j]) * wy0 * wx0 + int64_t(b[j]) * wy1 * wx0 + int64_t(d[j]) * wy0 * wx1 + int64_t(e[j]) * wy1 * wx1;
+      const int64_t rnd = o20 > 0 ? (1 << 19) : -(1 << 19);
+      ob[j] = int8_t((o20 + rnd) / (1 << 20));
+    }
+    *reinterpret_cast<char4*>(out + int64_t(t) * out_ts + (int64_t(y) * OW + x) * C + c) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const uint8_t* __restrict__ in, int64_t in_ts,
+                                                  uint8_t* __restrict__ out, int64_t out_ts, int64_t bytes, bool vec) {
+  const int t = blockIdx.y;
+  const uint8_t* pi = in + int64_t(t) * in_ts;
+  uint8_t* po = out + int64_t(t) * out_ts;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (vec) {
+    const int64_t n16 = bytes >> 4;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+      reinterpret_cast<uint4*>(po)[i] = reinterpret_cast<const uint4*>(pi)[i];
+    for (int64_t i = (n16 << 4) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < bytes; i += stride) po[i] = pi[i];
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < bytes; i += stride) po[i] = pi[i];
+  }
+}
+
+inline bool aligned16(const void* p, int64_t stride) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (stride & 15) == 0; }
+inline int grid_for(int64_t work_items, int threads, int tiles) {
+  // enough CTAs to fill 148 SMs a few times over, never more than the work needs
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (148 * 8 + tiles - 1) / tiles;
+  if (blocks > cap) blocks = cap;
+  return int(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const int32_t* bias, const int32_t* wsum,
+                        int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles,
+                        cudaStream_t s) {
+  constexpr int OCT = 8;
+  const int64_t pixels = int64_t(tiles) * g.OH * g.OW;
+  dim3 grid(unsigned((pixels + 127) / 128), unsigned((g.OC + OCT - 1) / OCT));
+  const bool vec = (g.IC % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0) && (in_ts % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(w) & 3) == 0);
+  if (vec)
+    conv_direct_kernel<OCT, true><<<grid, 128, 0, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+  else
+    conv_direct_kernel<OCT, false><<<grid, 128, 0, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+}
+
+void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const int32_t* bias, int32_t in_zp,
+                      const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles, cudaStream_t s) {
+  const bool vec = (g.OC % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0) && (in_ts % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (out_ts % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(w) & 3) == 0);
+  if (vec) {
+    const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / 4);
+    depthwise_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+  } else {
+    const int64_t total = int64_t(tiles) * g.OH * g.OW * g.OC;
+    depthwise_scalar_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+  }
+}
+
+void launch_add(const int8_t* a, int64_t a_ts, const int8_t* b, int64_t b_ts, int8_t* out, int64_t out_ts,
+                int64_t elems, int tiles, const AddParams& p, cudaStream_t s) {
+  const bool vec = aligned16(a, a_ts) && aligned16(b, b_ts) && aligned16(out, out_ts);
+  dim3 grid(grid_for(vec ? elems / 16 + 1 : elems, 256, tiles), tiles);
+  add_kernel<<<grid, 256, 0, s>>>(a, a_ts, b, b_ts, out, out_ts, elems, tiles, p, vec);
+}
+
+void launch_lut(const uint8_t* in, int64_t in_ts, uint8_t* out, int64_t out_ts, int64_t elems, int tiles,
+                const uint8_t* lut256, cudaStream_t s) {
+  const bool vec = aligned16(in, in_ts) && aligned16(out, out_ts);
+  dim3 grid(grid_for(vec ? elems / 16 + 1 : elems, 256, tiles), tiles);
+  lut_kernel<<<grid, 256, 0, s>>>(in, in_ts, out, out_ts, elems, lut256, vec);
+}
+
+void launch_pad(const int8_t* in, int64_t in_ts, int H, int W, int C, int pt, int pl, int OH, int OW, int8_t fill,
+                int8_t* out, int64_t out_ts, int tiles, cudaStream_t s) {
+  dim3 grid(grid_for(int64_t(OH) * OW * C, 256, tiles), tiles);
+  pad_kernel<<<grid, 256, 0, s>>>(in, in_ts, H, W, C, pt, pl, OH, OW, fill, out, out_ts);
+}
+
+void launch_resize_bilinear(const int8_t* in, int64_t in_ts, int IH, int IW, int C, int8_t* out, int64_t out_ts,
+                            int OH, int OW, bool align_corners, bool half_pixel, int tiles, cudaStream_t s) {
+  int hs = ((1 << 10) * IH + OH / 2) / OH, ws = ((1 << 10) * IW + OW / 2) / OW;
+  if (align_corners && OH > 1) hs = ((1 << 10) * (IH - 1) + (OH - 1) / 2) / (OH - 1);
+  if (align_corners && OW > 1) ws = ((1 << 10) * (IW - 1) + (OW - 1) / 2) / (OW - 1);
+  dim3 grid(grid_for(int64_t(OH) * OW * (C / 4), 256, tiles), tiles);
+  resize_kernel<<<grid, 256, 0, s>>>(in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
+}
+
+void launch_copy(const uint8_t* in, int64_t in_ts, uint8_t* out, int64_t out_ts, int64_t bytes, int tiles,
+                 cudaStream_t s) {
+  const bool vec = aligned16(in, in_ts) && aligned16(out, out_ts);
+  dim3 grid(grid_for(vec ? bytes / 16 + 1 : bytes, 256, tiles), tiles);
+  copy_kernel<<<grid, 256, 0, s>>>(in, in_ts, out, out_ts, bytes, vec);
+}
+
+}  // namespace tod

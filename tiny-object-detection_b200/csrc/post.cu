@@ -1,0 +1,474 @@
+// Kernels around the int8 graph.  See post.h.
+//
+// Float arithmetic that must match the CPU reference bit for bit is written with the explicit
+// round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...) so that no FMA contraction can change a
+// result (Rust never fuses a*b+c).
+#include "post.h"
+
+#include "common.h"
+
+namespace tod {
+namespace {
+
+// ================================================================= literal post-processing
+// One CTA per tile, one thread per seg-grid cell.
+//   yolact.rs:108-118  running-max classification over channels 0..3
+//   yolact.rs:52-88    terrible_id   (literal: no visited set -> either every id stays -1 or the
+//                                     reference never returns; intent: 4-connected components)
+//   yolact.rs:127-128  pack + 8x nearest replicate
+__global__ void __launch_bounds__(1024) seg_post_kernel(const uint8_t* __restrict__ seg, int64_t ts, SegPost P,
+                                                       uint32_t* __restrict__ out, int* __restrict__ diverges) {
+  __shared__ uint8_t s_cls[1024];
+  __shared__ int s_label[1024];
+  __shared__ uint32_t s_val[1024];
+  __shared__ int s_warp_roots[32];
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int cells = P.gh * P.gw;
+  const uint8_t* q = seg + int64_t(t) * ts;
+
+  int cls = 0;
+  if (tid < cells) {
+    const uint8_t* chunk = q + int64_t(tid) * P.ch;
+    float mx = 0.0f;  // :109
+    bool f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bool hit = false;
+      if (i < P.ch) {
+        const float v = __fmul_rn(P.scale, float(int(chunk[i]) - P.zp));  // yolact.rs:177
+        hit = v > mx;                                                      // :110
+        if (hit) mx = v;
+      }
+      f[i] = hit;
+    }
+    if (!f[0] && f[1] && !f[2] && !f[3]) cls = 1;  // :112-117
+    else if (!f[0] && f[2] && !f[3]) cls = 2;
+    else if (!f[0] && f[3]) cls = 3;
+    else cls = 0;
+  }
+  s_cls[tid] = uint8_t(cls);
+  __syncthreads();
+
+  int id = -1;
+  if (P.id_mode == 0) {
+    // literal: neighbours by flat index +-1 / +-gw (wrapping across row ends)
+    bool bad = false;
+    if (tid < cells && cls == 3) {
+      const int nb[4] = {tid - 1, tid + 1, tid - P.gw, tid + P.gw};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (nb[k] >= 0 && nb[k] < cells && s_cls[nb[k]] == 3) bad = true;
+    }
+    if (__syncthreads_or(bad) && tid == 0) diverges[t] = 1;
+  } else {
+    // intent: connected components by iterated min-label propagation + pointer jumping
+    const int x = tid % P.gw, y = tid / P.gw;
+    const bool ball = tid < cells && cls == 3;
+    s_label[tid] = ball ? tid : -1;
+    __syncthreads();
+    bool changed = true;
+    while (changed) {
+      int l = s_label[tid];
+      bool ch = false;
+      if (ball) {
+        int m = l;
+        if (x > 0 && s_label[tid - 1] >= 0) m = min(m, s_label[tid - 1]);
+        if (x < P.gw - 1 && s_label[tid + 1] >= 0) m = min(m, s_label[tid + 1]);
+        if (y > 0 && s_label[tid - P.gw] >= 0) m = min(m, s_label[tid - P.gw]);
+        if (y < P.gh - 1 && s_label[tid + P.gw] >= 0) m = min(m, s_label[tid + P.gw]);
+        m = min(m, s_label[m]);  // jump
+        ch = m < l;
+        l = m;
+      }
+      __syncthreads();
+      if (ball) s_label[tid] = l;
+      changed = __syncthreads_or(ch);
+    }
+    // component id = raster-order rank of its first (minimum-index) cell
+    const bool root = ball && s_label[tid] == tid;
+    const unsigned bal = __ballot_sync(0xffffffffu, root);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) s_warp_roots[warp] = __popc(bal);
+    __syncthreads();
+    if (ball) {
+      const int r = s_label[tid];
+      int rank = 0;
+      for (int w = 0; w < (r >> 5); ++w) rank += s_warp_roots[w];
+      // roots below r inside r's warp: recount from labels (r's warp may differ from mine)
+      const int base = r & ~31;
+      for (int j = base; j < r; ++j) rank += (s_cls[j] == 3 && s_label[j] == j) ? 1 : 0;
+      id = rank & 0x7F;
+    }
+  }
+
+  uint32_t v = 0;
+  if (tid < cells) {
+    const uint32_t idu = uint32_t(int32_t(id));  // `id as u32` sign-extends
+    if (P.id_mode == 0) v = (uint32_t(cls) << 24) & (idu << 16);  // literal `&`
+    else v = (uint32_t(cls) << 24) | ((idu & 0xFFu) << 16);
+  }
+  s_val[tid] = v;
+  __syncthreads();
+  const int OW = P.gw * P.up, OH = P.gh * P.up;
+  uint32_t* o = out + int64_t(t) * OW * OH;
+  for (int i = tid; i < OW * OH; i += blockDim.x) {
+    const int ox = i % OW, oy = i / OW;
+    o[i] = s_val[(oy / P.up) * P.gw + ox / P.up];
+  }
+}
+
+// ================================================================= Triangle resampling (image 0.24.1)
+// vertical_sample: u8 source -> f32 rows; horizontal_sample: f32 -> u8 with clamp + round.
+// Source pixel fetchers differ between the pre (u32 frame) and post (two stitched u32 tiles) use.
+struct FrameSrc {
+  const uint32_t* frames;
+  int W, H;
+  __device__ __forceinline__ uint32_t px(int f, int x, int y) const { return frames[(int64_t(f) * H + y) * W + x]; }
+};
+struct TilePairSrc {
+  const uint32_t* tiles;
+  int tw, th;
+  __device__ __forceinline__ uint32_t px(int f, int x, int y) const {  // yolact.rs:219-220 row interleave
+    const int t = x / tw;
+    return tiles[((int64_t(f) * 2 + t) * th + y) * tw + (x - t * tw)];
+  }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(256) vertical_kernel(Src src, int n, int sw, ResampleAxis A, float* __restrict__ tmp) {
+  const int64_t total = int64_t(n) * A.out_size * sw;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = int(idx % sw);
+  const int oy = int((idx / sw) % A.out_size);
+  const int f = int(idx / (int64_t(sw) * A.out_size));
+  const int left = A.left[oy], cnt = A.count[oy];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int i = 0; i < cnt; ++i) {
+    const float w = A.weight[oy * kMaxTaps + i];
+    const uint32_t p = src.px(f, x, left + i);
+    a0 = __fadd_rn(a0, __fmul_rn(float(p >> 24), w));
+    a1 = __fadd_rn(a1, __fmul_rn(float((p >> 16) & 0xFF), w));
+    a2 = __fadd_rn(a2, __fmul_rn(float((p >> 8) & 0xFF), w));
+  }
+  float* o = tmp + idx * 3;
+  o[0] = a0;
+  o[1] = a1;
+  o[2] = a2;
+}
+
+__device__ __forceinline__ uint32_t clamp_round_u8(float v) {
+  v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+  return uint32_t(roundf(v));
+}
+
+// mode 0: write RGB8 tiles (yolact.rs:213-214 crops); mode 1: write u32 frame (+ target)
+__global__ void __launch_bounds__(256) horizontal_kernel(const float* __restrict__ tmp, int n, int sw, int rows,
+                                                        ResampleAxis A, int mode, uint8_t* __restrict__ tiles, int tw,
+                                                        uint32_t* __restrict__ frames, uint16_t* __restrict__ target) {
+  const int64_t total = int64_t(n) * rows * A.out_size;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = int(idx % A.out_size);
+  const int y = int((idx / A.out_size) % rows);
+  const int f = int(idx / (int64_t(A.out_size) * rows));
+  const int left = A.left[ox], cnt = A.count[ox];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const float* row = tmp + (int64_t(f) * rows + y) * sw * 3;
+  for (int i = 0; i < cnt; ++i) {
+    const float w = A.weight[ox * kMaxTaps + i];
+    const float* p = row + int64_t(left + i) * 3;
+    a0 = __fadd_rn(a0, __fmul_rn(p[0], w));
+    a1 = __fadd_rn(a1, __fmul_rn(p[1], w));
+    a2 = __fadd_rn(a2, __fmul_rn(p[2], w));
+  }
+  const uint32_t r = clamp_round_u8(a0), g = clamp_round_u8(a1), b = clamp_round_u8(a2);
+  if (mode == 0) {
+    const int t = ox / tw;
+    uint8_t* o = tiles + (((int64_t(f) * 2 + t) * rows + y) * tw + (ox - t * tw)) * 3;
+    o[0] = uint8_t(r);
+    o[1] = uint8_t(g);
+    o[2] = uint8_t(b);
+  } else {
+    const uint32_t px = (r << 24) | (g << 16) | (b << 8);  // yolact.rs:231-232 from_be_bytes([r,g,b,0])
+    frames[idx] = px;
+    if (target) target[idx] = uint16_t(px & 0xFFFFu);  // scene.rs:93
+  }
+}
+
+// ================================================================= detection
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* k, int n) {  // n = power of two
+  for (int size = 2; size <= n; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int pos = 2 * i - (i & (stride - 1));
+        const unsigned long long a = k[pos], b = k[pos + stride];
+        const bool desc = (pos & size) == 0;
+        if ((a < b) == desc) {
+          k[pos] = b;
+          k[pos + stride] = a;
+        }
+      }
+    }
+  __syncthreads();
+}
+
+// decode + softmax + per-class candidate lists.  One thread per prior; the class bytes of the CTA's
+// priors are staged through shared memory so the global read is coalesced.
+constexpr int kDecodeThreads = 128;
+__global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, DetectBuffers b, const uint8_t* __restrict__ cls,
+                                                               int64_t cls_ts, const uint8_t* __restrict__ box, int64_t box_ts) {
+  extern __shared__ uint8_t s_q[];  // [kDecodeThreads][C]
+  __shared__ float s_exp[256];
+  const int t = blockIdx.y;
+  const int p0 = blockIdx.x * kDecodeThreads;
+  const int np = min(kDecodeThreads, c.P - p0);
+  for (int i = threadIdx.x; i < 256; i += kDecodeThreads) s_exp[i] = b.exp_diff[i];
+  const uint8_t* src = cls + int64_t(t) * cls_ts + int64_t(p0) * c.C;
+  for (int i = threadIdx.x; i < np * c.C; i += kDecodeThreads) s_q[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x >= np) return;
+  const int p = p0 + threadIdx.x;
+  // box_utils.decode, variances 0.1 / 0.2
+  const float4 pr = reinterpret_cast<const float4*>(b.priors)[p];
+  const uint8_t* l = box + int64_t(t) * box_ts + int64_t(p) * 4;
+  const float cx = __fadd_rn(pr.x, __fmul_rn(__fmul_rn(b.box_deq[l[0]], 0.1f), pr.z));
+  const float cy = __fadd_rn(pr.y, __fmul_rn(__fmul_rn(b.box_deq[l[1]], 0.1f), pr.w));
+  const float w = __fmul_rn(pr.z, b.box_exp[l[2]]);
+  const float h = __fmul_rn(pr.w, b.box_exp[l[3]]);
+  const float x1 = __fsub_rn(cx, __fdiv_rn(w, 2.0f)), y1 = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+  reinterpret_cast<float4*>(b.boxes)[int64_t(t) * c.P + p] = make_float4(x1, y1, __fadd_rn(w, x1), __fadd_rn(h, y1));
+  // softmax over the u8 codes: exp(scale*(q - qmax)) from a 256-entry table, summed class 0..C-1 in order
+  const uint8_t* q = s_q + threadIdx.x * c.C;
+  int qmax = 0;
+  for (int k = 0; k < c.C; ++k) qmax = max(qmax, int(q[k]));
+  float sum = 0.f;
+  for (int k = 0; k < c.C; ++k) sum = __fadd_rn(sum, s_exp[int(q[k]) - qmax + 255]);
+  for (int k = 1; k < c.C; ++k) {
+    const float sc = __fdiv_rn(s_exp[int(q[k]) - qmax + 255], sum);
+    if (sc > c.conf_thresh) {
+      const int slot = atomicAdd(b.cand_count + int64_t(t) * (c.C - 1) + (k - 1), 1);
+      b.cand[(int64_t(t) * (c.C - 1) + (k - 1)) * c.P + slot] =
+          (static_cast<unsigned long long>(__float_as_uint(sc)) << 32) | (0xFFFFFFFFu - unsigned(p));
+    }
+  }
+}
+
+__device__ __forceinline__ float iou_rn(const float4 a, const float4 b) {
+  const float ix = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float iy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  const float inter = __fmul_rn(ix > 0.f ? ix : 0.f, iy > 0.f ? iy : 0.f);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  return uni > 0.f ? __fdiv_rn(inter, uni) : 0.f;
+}
+
+// Fast-NMS for one (class, tile): sort the class' candidates, keep top_k, then each warp lane owns a
+// column j of the IoU matrix and scans the rows i < j (upper triangle); survivors are compacted with
+// ballot/popc and appended to the tile's survivor list.
+constexpr int kNmsThreads = 256;
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap) {
+  extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k]
+  float4* s_box = reinterpret_cast<float4*>(s_keys + sort_cap);
+  __shared__ int s_base;
+  const int k = blockIdx.x;  // foreground class
+  const int t = blockIdx.y;
+  const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
+  if (n == 0) return;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const unsigned long long* src = b.cand + (int64_t(t) * (c.C - 1) + k) * c.P;
+  for (int i = threadIdx.x; i < np2; i += kNmsThreads) s_keys[i] = i < n ? src[i] : 0ull;
+  bitonic_sort_desc(s_keys, np2);
+  const int m = min(n, c.top_k);
+  for (int i = threadIdx.x; i < m; i += kNmsThreads) {
+    const int prior = int(0xFFFFFFFFu - unsigned(s_keys[i] & 0xFFFFFFFFull));
+    s_box[i] = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int j0 = (threadIdx.x >> 5) * 32; j0 < m; j0 += kNmsThreads) {
+    const int j = j0 + lane;
+    bool keep = false;
+    if (j < m) {
+      const float4 bj = s_box[j];
+      float mx = 0.f;
+      for (int i = 0; i < j; ++i) mx = fmaxf(mx, iou_rn(s_box[i], bj));
+      keep = mx <= c.nms_thresh;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(b.surv_count + t, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const unsigned long long key = s_keys[j];
+      const unsigned prior = 0xFFFFFFFFu - unsigned(key & 0xFFFFFFFFull);
+      const unsigned order = 0xFFFFu - unsigned((k << 8) | j);  // ties: class asc, then rank asc
+      b.surv[int64_t(t) * (c.C - 1) * c.top_k + base + __popc(bal & ((1u << lane) - 1))] =
+          (key & 0xFFFFFFFF00000000ull) | (static_cast<unsigned long long>(order) << 16) | prior;
+    }
+  }
+  (void)s_base;
+}
+
+// merge the classes of one tile: sort survivors by score, keep max_dets
+__global__ void __launch_bounds__(1024) select_kernel(DetectCfg c, DetectBuffers b) {
+  extern __shared__ unsigned long long s_keys[];
+  const int t = blockIdx.x;
+  const int n = b.surv_count[t];
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const unsigned long long* src = b.surv + int64_t(t) * (c.C - 1) * c.top_k;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < n ? src[i] : 0ull;
+  if (n > 1) bitonic_sort_desc(s_keys, np2);
+  else __syncthreads();
+  const int nd = min(n, c.max_dets);
+  if (threadIdx.x == 0) b.det_count[t] = nd;
+  for (int d = threadIdx.x; d < nd; d += blockDim.x) {
+    const unsigned long long key = s_keys[d];
+    const int prior = int(key & 0xFFFFull);
+    const unsigned order = 0xFFFFu - unsigned((key >> 16) & 0xFFFFull);
+    const int64_t o = int64_t(t) * c.max_dets + d;
+    b.det_score[o] = __uint_as_float(unsigned(key >> 32));
+    b.det_class[o] = int(order >> 8);
+    b.det_prior[o] = prior;
+    reinterpret_cast<float4*>(b.det_box)[o] = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
+  }
+}
+
+// prototype-mask assembly: logits = P[ph*pw, K] . C^T[K, nd] in exact int32 (u8 x u8 dp4a with the
+// zero points folded algebraically), then sigmoid, crop to the box (+1 px), threshold.
+// One thread per prototype pixel keeps its K bytes in registers and sweeps the tile's detections.
+constexpr int kMaskThreads = 128;
+template <int K>
+__global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectBuffers b, const uint8_t* __restrict__ coef,
+                                                           int64_t coef_ts, const uint8_t* __restrict__ proto,
+                                                           int64_t proto_ts) {
+  extern __shared__ float4 s_crop[];  // [max_dets] crop windows, then coefficients [max_dets][K/4], then sums
+  unsigned int* s_coef = reinterpret_cast<unsigned int*>(s_crop + c.max_dets);
+  int* s_csum = reinterpret_cast<int*>(s_coef + c.max_dets * (K / 4));
+  const int t = blockIdx.y;
+  const int nd = b.det_count[t];
+  if (nd == 0) return;
+  for (int i = threadIdx.x; i < nd * (K / 4); i += kMaskThreads) {
+    const int d = i / (K / 4), w = i - d * (K / 4);
+    const int prior = b.det_prior[int64_t(t) * c.max_dets + d];
+    const uint8_t* cq = coef + int64_t(t) * coef_ts + int64_t(prior) * K + w * 4;
+    s_coef[i] = unsigned(cq[0]) | (unsigned(cq[1]) << 8) | (unsigned(cq[2]) << 16) | (unsigned(cq[3]) << 24);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < nd; d += kMaskThreads) {
+    unsigned int sum = 0;
+    for (int w = 0; w < K / 4; ++w) sum = __dp4a(s_coef[d * (K / 4) + w], 0x01010101u, sum);
+    s_csum[d] = int(sum);
+    // output_utils.crop / sanitize_coordinates(padding = 1)
+    const float4 bx = reinterpret_cast<const float4*>(b.det_box)[int64_t(t) * c.max_dets + d];
+    const float x1 = __fmul_rn(bx.x, float(c.pw)), x2 = __fmul_rn(bx.z, float(c.pw));
+    const float y1 = __fmul_rn(bx.y, float(c.ph)), y2 = __fmul_rn(bx.w, float(c.ph));
+    float xa = __fsub_rn(fminf(x1, x2), 1.0f), xb = __fadd_rn(fmaxf(x1, x2), 1.0f);
+    float ya = __fsub_rn(fminf(y1, y2), 1.0f), yb = __fadd_rn(fmaxf(y1, y2), 1.0f);
+    xa = fmaxf(xa, 0.f);
+    xb = fminf(xb, float(c.pw));
+    ya = fmaxf(ya, 0.f);
+    yb = fminf(yb, float(c.ph));
+    s_crop[d] = make_float4(xa, xb, ya, yb);
+  }
+  __syncthreads();
+  const int npx = c.ph * c.pw;
+  const int px = blockIdx.x * kMaskThreads + threadIdx.x;
+  if (px >= npx) return;
+  unsigned int pw_[K / 4];
+  const uint8_t* pq = proto + int64_t(t) * proto_ts + int64_t(px) * K;
+  unsigned int upsum = 0;
+#pragma unroll
+  for (int w = 0; w < K / 4; ++w) {
+    pw_[w] = *reinterpret_cast<const unsigned int*>(pq + 4 * w);
+    upsum = __dp4a(pw_[w], 0x01010101u, upsum);
+  }
+  const int psum = int(upsum);
+  const float fx = float(px % c.pw), fy = float(px / c.pw);
+  const int kzz = K * c.proto_zp * c.coef_zp;
+  for (int d = 0; d < nd; ++d) {
+    unsigned int dot = 0;
+#pragma unroll
+    for (int w = 0; w < K / 4; ++w) dot = __dp4a(pw_[w], s_coef[d * (K / 4) + w], dot);
+    const int idot = int(dot) - c.coef_zp * psum - c.proto_zp * s_csum[d] + kzz;
+    const float logit = __fmul_rn(float(idot), c.mask_scale);
+    float mval = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
+    const float4 cr = s_crop[d];
+    if (!(fx >= cr.x && fx < cr.y && fy >= cr.z && fy < cr.w)) mval = 0.f;
+    const int64_t o = (int64_t(t) * c.max_dets + d) * npx + px;
+    if (b.masks) b.masks[o] = mval;
+    if (b.masks_bin) b.masks_bin[o] = mval > 0.5f ? 1 : 0;
+  }
+}
+
+inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+void launch_seg_postprocess(const uint8_t* seg, int64_t ts, int tiles, const SegPost& p, uint32_t* out, int* diverges,
+                            cudaStream_t s) {
+  cudaMemsetAsync(diverges, 0, sizeof(int) * tiles, s);
+  seg_post_kernel<<<tiles, 1024, 0, s>>>(seg, ts, p, out, diverges);
+}
+
+void launch_classify_pre(const uint32_t* frames, int n, int W, int H, const ResampleAxis& vert, const ResampleAxis& horz,
+                         float* tmp, uint8_t* tiles, int tw, int th, cudaStream_t s) {
+  // image 0.24.1 resize: vertical_sample first (W x H -> W x th), then horizontal_sample (-> 2tw x th)
+  const int64_t tv = int64_t(n) * th * W;
+  vertical_kernel<FrameSrc><<<unsigned((tv + 255) / 256), 256, 0, s>>>(FrameSrc{frames, W, H}, n, W, vert, tmp);
+  const int64_t thz = int64_t(n) * th * 2 * tw;
+  horizontal_kernel<<<unsigned((thz + 255) / 256), 256, 0, s>>>(tmp, n, W, th, horz, 0, tiles, tw, nullptr, nullptr);
+}
+
+void launch_classify_post(const uint32_t* tile_px, int n, int W, int H, const ResampleAxis& vert, const ResampleAxis& horz,
+                          float* tmp, uint32_t* frames, uint16_t* target, int tw, int th, cudaStream_t s) {
+  const int sw = 2 * tw;
+  const int64_t tv = int64_t(n) * H * sw;
+  vertical_kernel<TilePairSrc><<<unsigned((tv + 255) / 256), 256, 0, s>>>(TilePairSrc{tile_px, tw, th}, n, sw, vert, tmp);
+  const int64_t thz = int64_t(n) * H * W;
+  horizontal_kernel<<<unsigned((thz + 255) / 256), 256, 0, s>>>(tmp, n, sw, H, horz, 1, nullptr, tw, frames, target);
+}
+
+size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8; }
+static size_t nms_smem(const DetectCfg& c) { return size_t(next_pow2(c.P)) * 8 + size_t(c.top_k) * 16; }
+static size_t mask_smem(const DetectCfg& c) { return size_t(c.max_dets) * (c.K + 4 + 16); }
+
+int detect_setup_kernels(const DetectCfg& c) {
+  if (c.P >= 65536 || (c.C - 1) > 255 || c.top_k > 256)
+    return fail(TOD_ERR_UNSUPPORTED, "detection head too large (P=%d, C=%d, top_k=%d)", c.P, c.C, c.top_k);
+  if (c.K != 32) return fail(TOD_ERR_UNSUPPORTED, "mask assembly is built for 32 coefficients, model has %d", c.K);
+  if (detect_select_smem(c) > 200 * 1024 || nms_smem(c) > 200 * 1024)
+    return fail(TOD_ERR_UNSUPPORTED, "detection head does not fit shared memory (P=%d, C=%d, top_k=%d)", c.P, c.C, c.top_k);
+  TOD_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(detect_select_smem(c))));
+  TOD_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(nms_smem(c))));
+  return TOD_OK;
+}
+
+int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
+                  int64_t box_ts, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto, int64_t proto_ts, int tiles,
+                  bool want_masks, cudaStream_t s) {
+  TOD_CUDA(cudaMemsetAsync(b.cand_count, 0, sizeof(int) * size_t(tiles) * (c.C - 1), s));
+  TOD_CUDA(cudaMemsetAsync(b.surv_count, 0, sizeof(int) * size_t(tiles), s));
+  dim3 g1((c.P + kDecodeThreads - 1) / kDecodeThreads, tiles);
+  decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
+  dim3 g2(c.C - 1, tiles);
+  nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P));
+  select_kernel<<<tiles, 1024, detect_select_smem(c), s>>>(c, b);
+  if (want_masks) {
+    dim3 g4((c.ph * c.pw + kMaskThreads - 1) / kMaskThreads, tiles);
+    mask_kernel<32><<<g4, kMaskThreads, mask_smem(c), s>>>(c, b, coef, coef_ts, proto, proto_ts);
+  }
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+}  // namespace tod

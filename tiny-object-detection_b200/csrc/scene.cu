@@ -1,0 +1,519 @@
+// Scene path: depth -> bird's-eye height map ("point cloud") -> world positions + 8-neighbour
+// connection weights.  B200-native replacement of the two Vulkan compute shaders the reference
+// dispatches from append_scene (/root/reference/src/scene.rs:238-260):
+//   shaders/pt_cloud.comp          -> land_kernel + stamp_kernel + balls_kernel
+//   shaders/pt_cloud_weights.comp  -> weights_kernel
+//
+// Design (not a port of the shaders):
+//  * The shader issues 400 (terrain) / 1600 (robot) imageAtomicMax per source pixel.  A stamp never
+//    changes a pixel's column (new_pos.x = img_pos.x, pt_cloud.comp:114), so the map is cut into
+//    32-column strips; one warp owns a strip, keeps it in shared memory as u16 and is the only
+//    writer of those columns: lane l owns column l.  The stamps become plain shared-memory
+//    read-max-write with no atomics, no races, and `map` is written to HBM exactly once, coalesced.
+//  * Every transcendental of the shader (pow/sqrt of the sigmoid bump, cos(atan(tan))) depends only
+//    on small integers (row, stamp offset, column), so it is tabulated once on the host at handle
+//    creation; the device arithmetic is integer + IEEE mul/div and the map is bit-exact by
+//    construction.
+//  * Under-specified GLSL behaviour follows the deterministic rules of SURVEY.md §9
+//    (zero-initialised map, integer ball sums, three ordered passes for the weights).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+
+namespace tod {
+namespace {
+
+constexpr int kStripW = 32;
+constexpr int kKindTerrain = 0, kKindRobot = 1, kKindBall = 2, kKindNone = 3;
+constexpr int kMaxBalls = 100;  // pt_cloud.comp:17
+
+struct SceneDev {
+  int W, H, s_t, s_b, py_bias, pad_rows;
+  float max_depth;
+  int sample_shift, weights_mode;
+};
+
+// ------------------------------------------------------------------ land: where does each pixel stamp?
+// pt_cloud.comp:84-114.  Output: land u16 = kind<<14 | (py + py_bias), plus ball sums and a per-row
+// "row holds a robot pixel" flag so the stamp kernel can skip the 40x40 pass on robot-free rows.
+__global__ void __launch_bounds__(256) land_kernel(const uint16_t* __restrict__ depth,
+                                                  const uint16_t* __restrict__ target, const float* __restrict__ cy_tab,
+                                                  const float* __restrict__ cx_tab, SceneDev P,
+                                                  uint16_t* __restrict__ land, unsigned int* __restrict__ row_robot,
+                                                  unsigned long long* __restrict__ ball_sums, int frames) {
+  const int64_t npx = int64_t(P.W) * P.H;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= npx * frames) return;
+  const int f = int(idx / npx);
+  const int p = int(idx - int64_t(f) * npx);
+  const int y = p / P.W, x = p - y * P.W;
+  // nearest texture() fetch; SURVEY §9.4: texel (x - shift, y - shift) with Repeat addressing
+  int sx = x - P.sample_shift, sy = y - P.sample_shift;
+  if (sx < 0) sx += P.W;
+  if (sy < 0) sy += P.H;
+  const int64_t src = int64_t(f) * npx + int64_t(sy) * P.W + sx;
+  const unsigned d = depth[src];
+  const unsigned tg = target[src];
+  const int cls = tg & 0xFF, id = tg >> 8;  // R8G8 little-endian upload (scene.rs:198)
+  // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
+  const float de = __fmul_rn(__fmul_rn(float(d), cy_tab[y]), cx_tab[x]);
+  // :98  int(float(height) * depth / max_depth_in)
+  const int dz = int(__fdiv_rn(__fmul_rn(float(P.H), de), P.max_depth));
+  const int py = P.H - dz;  // :114
+  int action = cls;
+  if (action > 1) action -= 1;  // :108-111
+  int kind;
+  if (action == 0) kind = kKindTerrain;
+  else if (action == 2) kind = kKindBall;
+  else kind = kKindRobot;
+  if (kind == kKindBall) {
+    if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
+      unsigned long long* b = ball_sums + (int64_t(f) * kMaxBalls + id) * 3;
+      atomicAdd(b + 0, (unsigned long long)(long long)x);
+      atomicAdd(b + 1, (unsigned long long)(long long)py);
+      atomicAdd(b + 2, 1ull);
+    }
+  } else {
+    const int s = kind == kKindTerrain ? P.s_t : P.s_b;
+    // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
+    if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
+    else if (kind == kKindRobot) atomicOr(row_robot + int64_t(f) * P.H + y, 1u);
+  }
+  int enc = py + P.py_bias;
+  enc = max(0, min(enc, 0x3FFF));
+  land[idx] = uint16_t((kind << 14) | enc);
+}
+
+__global__ void balls_kernel(const unsigned long long* __restrict__ sums, float* __restrict__ balls4, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long sx = (long long)sums[3 * i + 0], sy = (long long)sums[3 * i + 1], sn = (long long)sums[3 * i + 2];
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sn > 0) {
+    o.x = float(double(sx) / double(sn));
+    o.y = float(double(sy) / double(sn));
+    o.z = float(sn);
+  }
+  reinterpret_cast<float4*>(balls4)[i] = o;
+}
+
+// ------------------------------------------------------------------ stamp
+// grid = (strips, frames), block = one warp.  tile rows are padded by pad_rows above and below so a
+// stamp that hangs over the top/bottom edge needs no per-row test; the padding is dropped on output.
+__device__ __forceinline__ void stamp_rows(uint16_t* col, const uint16_t* __restrict__ lut_row, int lo, int hi,
+                                           bool active) {
+  // col points at tile[(py - s + pad) * 32 + lane]; lut_row is warp-uniform
+  for (int oy = lo; oy < hi; ++oy) {
+    const uint16_t v = __ldg(lut_row + oy);
+    if (active) {
+      uint16_t* q = col + oy * kStripW;
+      const uint16_t cur = *q;
+      if (v > cur) *q = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) stamp_kernel(const uint16_t* __restrict__ land,
+                                                  const unsigned int* __restrict__ row_robot,
+                                                  const uint16_t* __restrict__ lut_t,   // [H][2s_t][2s_t]
+                                                  const uint8_t* __restrict__ span_t,   // [H][2s_t][2] non-zero oy range
+                                                  const uint16_t* __restrict__ lut_b,   // [2s_b][2s_b]
+                                                  const uint8_t* __restrict__ span_b,   // [2s_b][2]
+                                                  SceneDev P, uint32_t* __restrict__ map) {
+  extern __shared__ uint16_t tile[];
+  const int lane = threadIdx.x;
+  const int f = blockIdx.y;
+  const int x0 = blockIdx.x * kStripW;
+  const int lx = x0 + lane;
+  const int rows = P.H + 2 * P.pad_rows;
+  for (int i = lane; i < rows * kStripW / 2; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+  __syncwarp();
+  const uint16_t* L = land + int64_t(f) * P.W * P.H;
+  const unsigned int* RR = row_robot + int64_t(f) * P.H;
+  const int d_t = 2 * P.s_t, d_b = 2 * P.s_b;
+  for (int y = 0; y < P.H; ++y) {
+    const uint16_t* Lr = L + int64_t(y) * P.W;
+    // terrain: loc.x = x - s + ox  =>  source column x = lx + s - ox
+    for (int ox = 0; ox < d_t; ++ox) {
+      const int x = lx + P.s_t - ox;
+      unsigned v = kKindNone << 14;
+      if (x >= 0 && x < P.W) v = Lr[x];
+      const bool active = (v >> 14) == kKindTerrain && lx < P.W;
+      if (!__any_sync(0xffffffffu, active)) continue;
+      const int py = int(v & 0x3FFF) - P.py_bias;
+      const int e = y * d_t + ox;
+      const int lo = span_t[2 * e], hi = span_t[2 * e + 1];
+      stamp_rows(tile + (py - P.s_t + P.pad_rows) * kStripW + lane, lut_t + int64_t(e) * d_t, lo, hi, active);
+    }
+    if (RR[y]) {
+      for (int ox = 0; ox < d_b; ++ox) {
+        const int x = lx + P.s_b - ox;
+        unsigned v = kKindNone << 14;
+        if (x >= 0 && x < P.W) v = Lr[x];
+        const bool active = (v >> 14) == kKindRobot && lx < P.W;
+        if (!__any_sync(0xffffffffu, active)) continue;
+        const int py = int(v & 0x3FFF) - P.py_bias;
+        stamp_rows(tile + (py - P.s_b + P.pad_rows) * kStripW + lane, lut_b + ox * d_b, span_b[2 * ox], span_b[2 * ox + 1], active);
+      }
+    }
+  }
+  __syncwarp();
+  if (lx < P.W) {
+    uint32_t* M = map + int64_t(f) * P.W * P.H;
+    const bool col_ok = lx > 0 && lx < P.W - 1;  // pt_cloud.comp:67
+    for (int r = 0; r < P.H; ++r) {
+      const bool ok = col_ok && r > 0 && r < P.H - 1;
+      M[int64_t(r) * P.W + lx] = ok ? uint32_t(tile[(r + P.pad_rows) * kStripW + lane]) : 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weights
+// pt_cloud_weights.comp:49-123 as one streaming pass: every thread recomputes the (at most 8)
+// distances it needs from the 3x3 map neighbourhood instead of exchanging them through images, which
+// is what the shader's 3 stages + barriers do (and what SURVEY §9.6 orders globally).
+__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+__global__ void __launch_bounds__(256) weights_kernel(const uint32_t* __restrict__ map, SceneDev P,
+                                                     float4* __restrict__ world, float4* __restrict__ conn0,
+                                                     float4* __restrict__ conn1, int frames) {
+  const int64_t npx = int64_t(P.W) * P.H;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= npx * frames) return;
+  const int f = int(idx / npx);
+  const int p = int(idx - int64_t(f) * npx);
+  const int y = p / P.W, x = p - y * P.W;
+  const uint32_t* M = map + int64_t(f) * npx;
+  const bool literal = P.weights_mode == 0;
+  auto h = [&](int xx, int yy) { return float(M[int64_t(yy) * P.W + xx]); };
+  const float h00 = literal ? float(M[0]) : 0.f;
+  // distance between pixel a (the "pos" of the shader invocation) and its neighbour b
+  auto link = [&](int ax, int ay, int bx, int by) {
+    const float wx = float(ax), wy = h(ax, ay), wz = float(ay);
+    if (literal) return dist3(wx, wy, wz, 0.f, h00, 0.f);  // pack() == 0 -> unpack loads world[0,0]
+    return dist3(wx, wy, wz, float(bx), h(bx, by), float(by));
+  };
+  const bool nxmin = x > 0, nxmax = x < P.W - 1, nymin = y > 0, nymax = y < P.H - 1;
+  if (world) world[idx] = make_float4(float(x), h(x, y), float(y), 0.f);  // :59-69
+  if (conn1) {  // :86-107  (below, below-left, left, above-left)
+    float4 c;
+    c.x = nymax ? link(x, y, x, y + 1) : -1.f;
+    c.y = (nxmin && nymax) ? link(x, y, x - 1, y + 1) : -1.f;
+    c.z = nxmin ? link(x, y, x - 1, y) : -1.f;
+    c.w = (nxmin && nymin) ? link(x, y, x - 1, y - 1) : -1.f;
+    conn1[idx] = c;
+  }
+  if (conn0) {  // :112-122  conn1[up].r, conn1[up-right].g, conn1[right].b, conn1[down-right].a
+    float4 c;
+    c.x = nymin ? link(x, y - 1, x, y) : -1.f;
+    c.y = (nxmax && nymin) ? link(x + 1, y - 1, x, y) : -1.f;
+    c.z = nxmax ? link(x + 1, y, x, y) : -1.f;
+    c.w = (nxmax && nymax) ? link(x + 1, y + 1, x, y) : -1.f;
+    conn0[idx] = c;
+  }
+}
+
+// ------------------------------------------------------------------ Scene materialisation (scene.rs:312-327)
+__device__ __forceinline__ int f32_as_i32_sat(float f) {  // Rust `as i32`
+  if (!(f == f)) return 0;
+  if (f >= 2147483648.0f) return 2147483647;
+  if (f <= -2147483648.0f) return -2147483647 - 1;
+  return int(f);
+}
+
+__global__ void __launch_bounds__(256) materialize_kernel(const uint32_t* __restrict__ map, const float4* __restrict__ world,
+                                                         const float4* __restrict__ conn0, const float4* __restrict__ conn1,
+                                                         const float4* __restrict__ balls4, int npx,
+                                                         float* __restrict__ height, float* __restrict__ pos3,
+                                                         float4* __restrict__ conn8, int* __restrict__ balls2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kMaxBalls) {
+    const float4 b = balls4[i];
+    balls2[2 * i] = f32_as_i32_sat(b.x);
+    balls2[2 * i + 1] = f32_as_i32_sat(b.y);
+  }
+  if (i >= npx) return;
+  height[i] = float(map[i]);
+  const float4 w = world[i];
+  pos3[3 * i + 0] = w.x;
+  pos3[3 * i + 1] = w.y;
+  pos3[3 * i + 2] = w.z;
+  conn8[2 * i] = conn0[i];
+  conn8[2 * i + 1] = conn1[i];
+}
+
+// ------------------------------------------------------------------ host: tables
+inline uint32_t float_to_uint_rz(float f) {  // uint(y_add); NaN -> 0
+  if (!(f == f) || f <= 0.0f) return 0u;
+  if (f >= 4294967296.0f) return 0xFFFFFFFFu;
+  return uint32_t(f);
+}
+
+// pt_cloud.comp:59-72 for one (val, bump_size): out[ox][oy] = uint(y_add)
+void bump_table(float val, int s, float bump_err, std::vector<uint32_t>* out) {
+  out->assign(size_t(4) * s * s, 0u);
+  const float c1 = val / bump_err - 1.0f;
+  const float c2 = 2.0f / float(s);
+  for (int ox = 0; ox < 2 * s; ++ox)
+    for (int oy = 0; oy < 2 * s; ++oy) {
+      const float dx = float(s - ox), dy = float(s - oy);  // pos - loc
+      const float prox = std::sqrt(dx * dx + dy * dy);      // pow(a,2) := a*a
+      const float e = c2 * prox - 1.0f;
+      const float y_add = val / (1.0f + std::pow(c1, e));
+      (*out)[size_t(ox) * 2 * s + oy] = float_to_uint_rz(y_add);
+    }
+}
+
+void spans_of(const uint16_t* lut, int d, uint8_t* span) {  // per ox: [lo, hi) of non-zero entries
+  for (int ox = 0; ox < d; ++ox) {
+    int lo = d, hi = 0;
+    for (int oy = 0; oy < d; ++oy)
+      if (lut[ox * d + oy]) {
+        lo = oy < lo ? oy : lo;
+        hi = oy + 1;
+      }
+    if (hi == 0) lo = 0;
+    span[2 * ox] = uint8_t(lo);
+    span[2 * ox + 1] = uint8_t(hi);
+  }
+}
+
+}  // namespace
+}  // namespace tod
+
+using namespace tod;
+
+struct tod_scene {
+  int device = 0;
+  tod_scene_params prm{};
+  SceneDev dev{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // tables
+  float *cy = nullptr, *cx = nullptr;
+  uint16_t *lut_t = nullptr, *lut_b = nullptr;
+  uint8_t *span_t = nullptr, *span_b = nullptr;
+  // per-batch buffers
+  uint16_t *depth = nullptr, *target = nullptr, *land = nullptr;
+  unsigned int* row_robot = nullptr;
+  unsigned long long* ball_sums = nullptr;
+  uint32_t* map = nullptr;
+  float *world = nullptr, *conn0 = nullptr, *conn1 = nullptr, *balls = nullptr;
+  // materialisation scratch (one frame)
+  float *m_height = nullptr, *m_pos = nullptr, *m_conn = nullptr;
+  int* m_balls = nullptr;
+  size_t stamp_smem = 0;
+  int last_n = 0;
+  bool timed = false;
+};
+
+extern "C" {
+
+void tod_scene_default_params(tod_scene_params* p) {
+  if (!p) return;
+  p->width = 640;                  // pt_cloud.comp:23
+  p->height = 480;                 // :24
+  p->max_depth_in = 4000.0f;       // :25
+  p->y_fov = 1.01229096616f;       // :27
+  p->x_fov = 1.51843644924f;       // :28
+  p->bot_avoidance_const = 100.0f; // :32
+  p->bot_norm_const = 20;          // :36
+  p->terrain_norm_const = 10;      // :37
+  p->bump_err = 0.1f;              // :39
+  p->sample_shift = 0;
+  p->weights_mode = 0;
+  p->max_batch = 1;
+}
+
+void tod_scene_destroy(tod_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  void* ptrs[] = {s->cy, s->cx, s->lut_t, s->lut_b, s->span_t, s->span_b, s->depth, s->target, s->land, s->row_robot,
+                  s->ball_sums, s->map, s->world, s->conn0, s->conn1, s->balls, s->m_height, s->m_pos, s->m_conn, s->m_balls};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : s->ev)
+    if (e) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out) {
+  if (!params || !out) return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: null argument");
+  *out = nullptr;
+  const tod_scene_params& p = *params;
+  if (p.width < 3 || p.height < 3 || p.width > 8192 || p.height > 8192)
+    return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: unsupported image size %dx%d", p.width, p.height);
+  if (p.terrain_norm_const < 1 || p.terrain_norm_const > 64 || p.bot_norm_const < 1 || p.bot_norm_const > 64)
+    return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: bump sizes must be in [1,64]");
+  if (p.max_batch < 1) return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: max_batch must be >= 1");
+  if (p.sample_shift != 0 && p.sample_shift != 1) return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: sample_shift must be 0 or 1");
+  if (p.weights_mode != 0 && p.weights_mode != 1) return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: weights_mode must be 0 or 1");
+  if (!(p.max_depth_in > 0.f) || !(p.bump_err > 0.f)) return fail(TOD_ERR_INVALID_ARG, "tod_scene_create: max_depth_in and bump_err must be positive");
+  // stamp values are stored as u16 in shared memory: y_add <= val <= max(H-1, bot_avoidance_const)
+  if (!(p.bot_avoidance_const >= 0.f && p.bot_avoidance_const < 65535.f))
+    return fail(TOD_ERR_UNSUPPORTED, "tod_scene_create: bot_avoidance_const must be in [0, 65535)");
+  TOD_TRY(select_device(device));
+
+  tod_scene* s = new tod_scene();
+  s->device = device;
+  s->prm = p;
+  const int W = p.width, H = p.height, st = p.terrain_norm_const, sb = p.bot_norm_const;
+  const int smax = st > sb ? st : sb;
+  s->dev = SceneDev{W, H, st, sb, 2 * smax + 2, 2 * smax, p.max_depth_in, p.sample_shift, p.weights_mode};
+  s->stamp_smem = size_t(H + 2 * s->dev.pad_rows) * kStripW * sizeof(uint16_t);
+
+  // host tables: the shader's transcendentals as functions of small integers
+  std::vector<float> cy(H), cx(W);
+  const float ty = std::tan(p.y_fov / 2.0f), tx = std::tan(p.x_fov / 2.0f);
+  for (int y = 0; y < H; ++y) cy[y] = std::cos(std::atan(ty * float(y) * 2.0f / float(H)));  // pt_cloud.comp:94
+  for (int x = 0; x < W; ++x) cx[x] = std::cos(std::atan(tx * float(x) * 2.0f / float(W)));  // :95
+  const int dt = 2 * st, db = 2 * sb;
+  std::vector<uint16_t> lut_t(size_t(H) * dt * dt), lut_b(size_t(db) * db);
+  std::vector<uint8_t> span_t(size_t(H) * dt * 2), span_b(size_t(db) * 2);
+  std::vector<uint32_t> slab;
+  for (int y = 0; y < H; ++y) {  // terrain: val = float(img_pos.y) (:116-117)
+    bump_table(float(y), st, p.bump_err, &slab);
+    for (size_t i = 0; i < slab.size(); ++i) lut_t[size_t(y) * dt * dt + i] = uint16_t(slab[i] > 65535u ? 65535u : slab[i]);
+    spans_of(&lut_t[size_t(y) * dt * dt], dt, &span_t[size_t(y) * dt * 2]);
+  }
+  bump_table(p.bot_avoidance_const, sb, p.bump_err, &slab);  // robot (:121-122)
+  for (size_t i = 0; i < slab.size(); ++i) lut_b[i] = uint16_t(slab[i] > 65535u ? 65535u : slab[i]);
+  spans_of(lut_b.data(), db, span_b.data());
+
+  const size_t npx = size_t(W) * H, nb = size_t(p.max_batch);
+  auto cleanup_fail = [&](int rc) {
+    tod_scene_destroy(s);
+    return rc;
+  };
+#define SC_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return cleanup_fail(fail(TOD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+  } while (0)
+  SC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : s->ev) SC_CUDA(cudaEventCreate(&e));
+  SC_CUDA(cudaMalloc(&s->cy, H * sizeof(float)));
+  SC_CUDA(cudaMalloc(&s->cx, W * sizeof(float)));
+  SC_CUDA(cudaMalloc(&s->lut_t, lut_t.size() * 2));
+  SC_CUDA(cudaMalloc(&s->lut_b, lut_b.size() * 2));
+  SC_CUDA(cudaMalloc(&s->span_t, span_t.size()));
+  SC_CUDA(cudaMalloc(&s->span_b, span_b.size()));
+  SC_CUDA(cudaMemcpy(s->cy, cy.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMemcpy(s->cx, cx.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMemcpy(s->lut_t, lut_t.data(), lut_t.size() * 2, cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMemcpy(s->lut_b, lut_b.data(), lut_b.size() * 2, cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMemcpy(s->span_t, span_t.data(), span_t.size(), cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMemcpy(s->span_b, span_b.data(), span_b.size(), cudaMemcpyHostToDevice));
+  SC_CUDA(cudaMalloc(&s->depth, nb * npx * 2));
+  SC_CUDA(cudaMalloc(&s->target, nb * npx * 2));
+  SC_CUDA(cudaMalloc(&s->land, nb * npx * 2));
+  SC_CUDA(cudaMalloc(&s->row_robot, nb * H * sizeof(unsigned int)));
+  SC_CUDA(cudaMalloc(&s->ball_sums, nb * kMaxBalls * 3 * sizeof(unsigned long long)));
+  SC_CUDA(cudaMalloc(&s->map, nb * npx * 4));
+  SC_CUDA(cudaMalloc(&s->world, nb * npx * 16));
+  SC_CUDA(cudaMalloc(&s->conn0, nb * npx * 16));
+  SC_CUDA(cudaMalloc(&s->conn1, nb * npx * 16));
+  SC_CUDA(cudaMalloc(&s->balls, nb * kMaxBalls * 16));
+  SC_CUDA(cudaMalloc(&s->m_height, npx * 4));
+  SC_CUDA(cudaMalloc(&s->m_pos, npx * 12));
+  SC_CUDA(cudaMalloc(&s->m_conn, npx * 32));
+  SC_CUDA(cudaMalloc(&s->m_balls, kMaxBalls * 8));
+  SC_CUDA(cudaFuncSetAttribute(stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->stamp_smem)));
+#undef SC_CUDA
+  *out = s;
+  return TOD_OK;
+}
+
+// kernels only; all pointers on the device
+static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n, uint32_t* d_map,
+                     float* d_world, float* d_conn0, float* d_conn1, float* d_balls, cudaStream_t st, bool timed) {
+  const SceneDev& P = s->dev;
+  const int64_t npx = int64_t(P.W) * P.H;
+  TOD_CUDA(cudaMemsetAsync(s->row_robot, 0, size_t(n) * P.H * sizeof(unsigned int), st));
+  TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(n) * kMaxBalls * 3 * sizeof(unsigned long long), st));
+  const unsigned blocks = unsigned((npx * n + 255) / 256);
+  land_kernel<<<blocks, 256, 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums, n);
+  if (timed) TOD_CUDA(cudaEventRecord(s->ev[0], st));
+  dim3 grid((P.W + kStripW - 1) / kStripW, n);
+  stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
+  if (timed) TOD_CUDA(cudaEventRecord(s->ev[1], st));
+  if (d_world || d_conn0 || d_conn1)
+    weights_kernel<<<blocks, 256, 0, st>>>(d_map, P, reinterpret_cast<float4*>(d_world), reinterpret_cast<float4*>(d_conn0),
+                                           reinterpret_cast<float4*>(d_conn1), n);
+  if (timed) TOD_CUDA(cudaEventRecord(s->ev[2], st));
+  if (d_balls) balls_kernel<<<(n * kMaxBalls + 127) / 128, 128, 0, st>>>(s->ball_sums, d_balls, n * kMaxBalls);
+  TOD_CUDA(cudaGetLastError());
+  s->timed = timed;
+  return TOD_OK;
+}
+
+int tod_scene_append_batch_device(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n,
+                                  uint32_t* d_map, float* d_world4, float* d_conn0, float* d_conn1, float* d_balls4,
+                                  void* stream) {
+  if (!s || !d_depth || !d_target) return fail(TOD_ERR_INVALID_ARG, "tod_scene_append_batch_device: null argument");
+  if (n < 1 || n > s->prm.max_batch) return fail(TOD_ERR_CAPACITY, "tod_scene_append_batch_device: n=%d outside [1,%d]", n, s->prm.max_batch);
+  TOD_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->stream;
+  s->last_n = n;
+  return scene_run(s, d_depth, d_target, n, d_map ? d_map : s->map, d_world4, d_conn0, d_conn1, d_balls4, st, stream == nullptr);
+}
+
+int tod_scene_append_batch(tod_scene* s, const uint16_t* depth, const uint16_t* target, int n, uint32_t* map,
+                           float* world4, float* conn0, float* conn1, float* balls4) {
+  if (!s || !depth || !target) return fail(TOD_ERR_INVALID_ARG, "tod_scene_append_batch: null argument");
+  if (n < 1 || n > s->prm.max_batch) return fail(TOD_ERR_CAPACITY, "tod_scene_append_batch: n=%d outside [1,%d]", n, s->prm.max_batch);
+  TOD_CUDA(cudaSetDevice(s->device));
+  const size_t npx = size_t(s->dev.W) * s->dev.H;
+  cudaStream_t st = s->stream;
+  TOD_CUDA(cudaMemcpyAsync(s->depth, depth, n * npx * 2, cudaMemcpyHostToDevice, st));   // scene.rs:197
+  TOD_CUDA(cudaMemcpyAsync(s->target, target, n * npx * 2, cudaMemcpyHostToDevice, st)); // scene.rs:198
+  // Scene materialisation reads all four images, so they are always produced on the device
+  TOD_TRY(scene_run(s, s->depth, s->target, n, s->map, s->world, s->conn0, s->conn1, s->balls, st, true));
+  if (map) TOD_CUDA(cudaMemcpyAsync(map, s->map, n * npx * 4, cudaMemcpyDeviceToHost, st));          // scene.rs:246
+  if (world4) TOD_CUDA(cudaMemcpyAsync(world4, s->world, n * npx * 16, cudaMemcpyDeviceToHost, st)); // :257
+  if (conn0) TOD_CUDA(cudaMemcpyAsync(conn0, s->conn0, n * npx * 16, cudaMemcpyDeviceToHost, st));   // :258
+  if (conn1) TOD_CUDA(cudaMemcpyAsync(conn1, s->conn1, n * npx * 16, cudaMemcpyDeviceToHost, st));   // :259
+  if (balls4) TOD_CUDA(cudaMemcpyAsync(balls4, s->balls, size_t(n) * kMaxBalls * 16, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));  // scene.rs:282 future.wait
+  s->last_n = n;
+  return TOD_OK;
+}
+
+int tod_scene_materialize(tod_scene* s, int frame, float* height, float* pos3, int32_t* balls2, float* connections8) {
+  if (!s) return fail(TOD_ERR_INVALID_ARG, "tod_scene_materialize: null handle");
+  if (frame < 0 || frame >= s->last_n) return fail(TOD_ERR_INVALID_ARG, "tod_scene_materialize: frame %d not in the last batch of %d", frame, s->last_n);
+  TOD_CUDA(cudaSetDevice(s->device));
+  const size_t npx = size_t(s->dev.W) * s->dev.H;
+  cudaStream_t st = s->stream;
+  materialize_kernel<<<unsigned((npx + 255) / 256), 256, 0, st>>>(
+      s->map + frame * npx, reinterpret_cast<const float4*>(s->world) + frame * npx,
+      reinterpret_cast<const float4*>(s->conn0) + frame * npx, reinterpret_cast<const float4*>(s->conn1) + frame * npx,
+      reinterpret_cast<const float4*>(s->balls) + size_t(frame) * kMaxBalls, int(npx), s->m_height, s->m_pos,
+      reinterpret_cast<float4*>(s->m_conn), s->m_balls);
+  TOD_CUDA(cudaGetLastError());
+  if (height) TOD_CUDA(cudaMemcpyAsync(height, s->m_height, npx * 4, cudaMemcpyDeviceToHost, st));
+  if (pos3) TOD_CUDA(cudaMemcpyAsync(pos3, s->m_pos, npx * 12, cudaMemcpyDeviceToHost, st));
+  if (connections8) TOD_CUDA(cudaMemcpyAsync(connections8, s->m_conn, npx * 32, cudaMemcpyDeviceToHost, st));
+  if (balls2) TOD_CUDA(cudaMemcpyAsync(balls2, s->m_balls, kMaxBalls * 8, cudaMemcpyDeviceToHost, st));
+  TOD_CUDA(cudaStreamSynchronize(st));
+  return TOD_OK;
+}
+
+int tod_scene_last_kernel_ms(tod_scene* s, float* stamp_ms, float* weights_ms) {
+  if (!s) return fail(TOD_ERR_INVALID_ARG, "tod_scene_last_kernel_ms: null handle");
+  if (!s->timed) return fail(TOD_ERR_INVALID_ARG, "tod_scene_last_kernel_ms: the last call ran on a caller stream and was not timed");
+  TOD_CUDA(cudaSetDevice(s->device));
+  TOD_CUDA(cudaEventSynchronize(s->ev[2]));
+  if (stamp_ms) TOD_CUDA(cudaEventElapsedTime(stamp_ms, s->ev[0], s->ev[1]));
+  if (weights_ms) TOD_CUDA(cudaEventElapsedTime(weights_ms, s->ev[1], s->ev[2]));
+  return TOD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1105 @@
+// Yolact handle: model load, execution plan, batched inference, the reference's classify() pipeline
+// and the YOLACT detection head.  Replaces Yolact::init / Yolact::classify
+// (/root/reference/src/yolact.rs:17-41) and everything below them (classify, classify_tile,
+// postprocess, terrible_id, interpreter.invoke()).
+//
+// Design: the TFLite graph is planned once at create time into a flat list of kernel launches over
+// [tile]-batched NHWC buffers.  RESHAPE is an alias, CONCATENATION inputs are produced directly inside
+// the concat buffer (tensors carry a byte stride between tiles), PAD is folded into the consuming
+// convolution, per-channel requantisation constants / byte LUTs are tabulated on the host with the exact
+// TFLite integer rules, and the whole per-batch launch sequence is replayed from a CUDA graph.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "conv_tc.h"
+#include "fixedpoint.cuh"
+#include "ops.h"
+#include "post.h"
+#include "tflite_reader.h"
+
+namespace tod {
+namespace {
+
+constexpr int64_t kAlign = 256;
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+enum StepKind { kStepConvDirect, kStepConvTc, kStepDepthwise, kStepAdd, kStepLut, kStepPad, kStepResize, kStepCopy };
+
+struct Place {   // where a tensor lives at run time
+  uint8_t* base = nullptr;   // tile 0
+  int64_t tile_stride = 0;   // bytes between tiles
+  int64_t bytes = 0;         // dense bytes per tile
+};
+
+struct Step {
+  StepKind kind;
+  int op = -1;             // index into Graph::ops
+  int in0 = -1, in1 = -1, out = -1;
+  ConvGeom g{};
+  int32_t in_zp = 0;
+  // offsets into the constant arena (-1 = absent)
+  int64_t w_off = -1, bias_off = -1, wsum_off = -1, mult_off = -1, shift_off = -1, lut_off = -1;
+  int32_t out_zp = 0, act_min = 0, act_max = 0;
+  AddParams add{};
+  int pad_top = 0, pad_left = 0;
+  int8_t fill = 0;
+  bool align_corners = false, half_pixel = false;
+  int64_t copy_dst_off = 0, copy_bytes = 0;
+  int64_t macs = 0;
+  ConvTc* tc = nullptr;
+};
+
+void conv_out_pad(int padding, int in, int k, int stride, int dil, int* out, int* pad) {
+  const int eff = (k - 1) * dil + 1;
+  *out = padding == kSame ? (in + stride - 1) / stride : (in + stride - eff) / stride;
+  const int total = std::max(0, (*out - 1) * stride + eff - in);
+  *pad = padding == kSame ? total / 2 : 0;
+}
+
+void activation_range(int act, const GTensor& out, int32_t* lo, int32_t* hi) {
+  const int32_t qmin = out.type == kU8 ? 0 : -128, qmax = out.type == kU8 ? 255 : 127;
+  const float scale = out.scale();
+  const int32_t zp = out.zp();
+  auto quant = [&](float f) { return zp + int32_t(std::round(f / scale)); };
+  *lo = qmin;
+  *hi = qmax;
+  if (act == kActRelu) *lo = std::max(qmin, quant(0.0f));
+  else if (act == kActRelu6) {
+    *lo = std::max(qmin, quant(0.0f));
+    *hi = std::min(qmax, quant(6.0f));
+  } else if (act == kActReluN1To1) {
+    *lo = std::max(qmin, quant(-1.0f));
+    *hi = std::min(qmax, quant(1.0f));
+  }
+}
+
+struct ConstArena {
+  std::vector<uint8_t> host;
+  int64_t add(const void* p, size_t bytes) {
+    const int64_t off = round_up(int64_t(host.size()), kAlign);
+    host.resize(size_t(off) + bytes);
+    if (bytes) std::memcpy(host.data() + off, p, bytes);
+    return off;
+  }
+};
+
+// image 0.24.1 imageops::resize sampling weights (Triangle filter, support 1.0); yolact.rs:208,231
+struct AxisTables {
+  std::vector<int> left, count;
+  std::vector<float> weight;
+  int in_size = 0, out_size = 0;
+  int *d_left = nullptr, *d_count = nullptr;
+  float* d_weight = nullptr;
+};
+
+int build_axis(int in_size, int out_size, AxisTables* t) {
+  t->in_size = in_size;
+  t->out_size = out_size;
+  t->left.assign(out_size, 0);
+  t->count.assign(out_size, 0);
+  t->weight.assign(size_t(out_size) * kMaxTaps, 0.f);
+  const float ratio = float(in_size) / float(out_size);
+  const float sratio = ratio < 1.0f ? 1.0f : ratio;
+  const float support = 1.0f * sratio;
+  for (int o = 0; o < out_size; ++o) {
+    float input = (float(o) + 0.5f) * ratio;
+    int64_t left = int64_t(std::floor(input - support));
+    left = std::min<int64_t>(std::max<int64_t>(left, 0), in_size - 1);
+    int64_t right = int64_t(std::ceil(input + support));
+    right = std::min<int64_t>(std::max<int64_t>(right, left + 1), in_size);
+    input = input - 0.5f;
+    const int n = int(right - left);
+    if (n > kMaxTaps) return fail(TOD_ERR_UNSUPPORTED, "resize %d -> %d needs %d taps (max %d)", in_size, out_size, n, kMaxTaps);
+    float sum = 0.f;
+    float* w = &t->weight[size_t(o) * kMaxTaps];
+    for (int i = 0; i < n; ++i) {
+      const float a = std::fabs((float(left + i) - input) / sratio);
+      w[i] = a < 1.0f ? 1.0f - a : 0.0f;
+      sum += w[i];
+    }
+    for (int i = 0; i < n; ++i) w[i] /= sum;
+    t->left[o] = int(left);
+    t->count[o] = n;
+  }
+  return TOD_OK;
+}
+
+}  // namespace
+}  // namespace tod
+
+using namespace tod;
+
+struct tod_yolact {
+  int device = 0;
+  tod_yolact_options opt{};
+  Graph graph;
+  std::vector<Step> steps;
+  std::vector<Place> place;   // per tensor
+  int64_t macs_per_tile = 0;
+  int tc_layers = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t* d_const = nullptr;
+  uint8_t* d_act = nullptr;
+  size_t act_bytes = 0;
+  // literal post-processing
+  int seg_out = -1;
+  uint32_t* d_tile_classes = nullptr;  // [max_tiles][th][tw]
+  int* d_diverges = nullptr;
+  int* h_diverges = nullptr;           // pinned
+  // detection
+  int o_box = -1, o_cls = -1, o_coef = -1, o_proto = -1;
+  bool det_ready = false, have_priors = false;
+  DetectCfg dcfg{};
+  DetectBuffers dbuf{};
+  std::vector<void*> det_allocs;
+  float* d_priors = nullptr;
+  // classify() pipeline
+  int cw = 0, chh = 0;  // frame size the tables below were built for
+  AxisTables pre_v, pre_h, post_v, post_h;
+  float* d_tmp = nullptr;
+  uint32_t* d_frames = nullptr;
+  uint8_t* d_tiles_rgb = nullptr;
+  // CUDA graphs, keyed by (tiles << 2 | dets << 1 | masks)
+  std::map<int, cudaGraphExec_t> graphs;
+  int last_tiles = 0;
+  int launches_per_call = 0;
+
+  const GTensor& T(int i) const { return graph.tensors[i]; }
+  int tile_w() const { return T(graph.inputs[0]).dims[2]; }
+  int tile_h() const { return T(graph.inputs[0]).dims[1]; }
+};
+
+namespace {
+
+// ------------------------------------------------------------------ planning
+int plan(tod_yolact* y, ConstArena* arena) {
+  const Graph& G = y->graph;
+  const int nt = int(G.tensors.size());
+  const bool fuse = y->opt.fusion != 0;
+
+  for (int t : G.outputs)
+    if (t < 0 || t >= nt) return fail(TOD_ERR_MODEL, "graph output %d out of range", t);
+  const GTensor& in0 = G.tensors[G.inputs[0]];
+  if (in0.type != kU8 || in0.dims[0] != 1 || in0.dims[3] != 3)
+    return fail(TOD_ERR_MODEL, "expected a uint8 [1,H,W,3] input (yolact.rs:143-153), got type %d [%d,%d,%d,%d]", in0.type, in0.dims[0],
+                in0.dims[1], in0.dims[2], in0.dims[3]);
+
+  std::vector<int> producer(nt, -1), consumers(nt, 0);
+  for (size_t i = 0; i < G.ops.size(); ++i) {
+    for (int t : G.ops[i].outputs) producer[t] = int(i);
+    for (int t : G.ops[i].inputs)
+      if (t >= 0) consumers[t]++;
+  }
+  for (int t : G.outputs) consumers[t]++;
+
+  // ---- storage: RESHAPE aliases its input; CONCATENATION inputs are placed inside the output
+  std::vector<int> alias_of(nt, -1);
+  struct Parent { int tensor = -1; int64_t off = 0; };
+  std::vector<Parent> parent(nt);
+  auto storage = [&](int t) {
+    while (alias_of[t] >= 0) t = alias_of[t];
+    return t;
+  };
+  for (const GOp& op : G.ops)
+    if (op.code == kReshape) {
+      const int a = op.inputs[0], o = op.outputs[0];
+      if (G.tensors[a].is_const()) return fail(TOD_ERR_UNSUPPORTED, "RESHAPE of a constant tensor");
+      if (G.tensors[a].elems() * G.tensors[a].elem_size() != G.tensors[o].elems() * G.tensors[o].elem_size())
+        return fail(TOD_ERR_MODEL, "RESHAPE changes the element count");
+      alias_of[o] = a;
+    }
+  struct CopyJob { int op, src, dst; int64_t off, bytes; };
+  std::vector<CopyJob> copies;
+  for (size_t i = 0; i < G.ops.size(); ++i) {
+    const GOp& op = G.ops[i];
+    if (op.code != kConcat) continue;
+    const GTensor& O = G.tensors[op.outputs[0]];
+    int axis = op.axis < 0 ? op.axis + O.rank : op.axis;
+    if (axis < 0 || axis >= O.rank) return fail(TOD_ERR_MODEL, "CONCATENATION axis out of range");
+    const int a4 = axis + 4 - O.rank;
+    int64_t outer = 1, inner = O.elem_size();
+    for (int d = 0; d < a4; ++d) outer *= O.dims[d];
+    for (int d = a4 + 1; d < 4; ++d) inner *= O.dims[d];
+    if (outer != 1) return fail(TOD_ERR_UNSUPPORTED, "CONCATENATION along an inner axis (outer size %lld) is not supported", (long long)outer);
+    int64_t off = 0;
+    for (int t : op.inputs) {
+      const GTensor& I = G.tensors[t];
+      if (I.scale() != O.scale() || I.zp() != O.zp() || I.type != O.type)
+        return fail(TOD_ERR_UNSUPPORTED, "CONCATENATION inputs must share the output quantisation");
+      const int64_t chunk = int64_t(I.dims[a4]) * inner;
+      const int s = storage(t);
+      const bool can_place = parent[s].tensor < 0 && !G.tensors[s].is_const() && s != G.inputs[0] && s != storage(op.outputs[0]);
+      if (can_place) parent[s] = Parent{op.outputs[0], off};
+      else copies.push_back(CopyJob{int(i), t, op.outputs[0], off, chunk});
+      off += chunk;
+    }
+  }
+
+  // ---- activation arena: one block per root storage, [max_tiles][stride]
+  std::vector<int64_t> root_off(nt, -1), root_stride(nt, 0);
+  int64_t total = 0;
+  const int64_t mt = y->opt.max_tiles;
+  for (int t = 0; t < nt; ++t) {
+    const GTensor& X = G.tensors[t];
+    if (X.is_const() || alias_of[t] >= 0 || parent[t].tensor >= 0) continue;
+    if (producer[t] < 0 && t != G.inputs[0]) continue;  // unused
+    if (X.dims[0] != 1) return fail(TOD_ERR_UNSUPPORTED, "tensor '%s' has batch %d; the model must be exported with batch 1", X.name.c_str(), X.dims[0]);
+    root_stride[t] = round_up(X.elems() * X.elem_size(), kAlign);
+    root_off[t] = total;
+    total += root_stride[t] * mt;
+  }
+  y->act_bytes = size_t(total);
+  TOD_CUDA(cudaMalloc(&y->d_act, y->act_bytes ? y->act_bytes : 256));
+  y->place.assign(nt, Place{});
+  for (int t = 0; t < nt; ++t) {
+    const GTensor& X = G.tensors[t];
+    if (X.is_const()) continue;
+    int s = storage(t);
+    int64_t off = 0;
+    int guard = 0;
+    while (parent[s].tensor >= 0 && guard++ < nt) {
+      off += parent[s].off;
+      s = storage(parent[s].tensor);
+    }
+    if (root_off[s] < 0) continue;
+    y->place[t] = Place{y->d_act + root_off[s] + off, root_stride[s], X.elems() * X.elem_size()};
+  }
+
+  // ---- steps
+  auto requant_tables = [&](const GTensor& I, const GTensor& Wt, const GTensor& O, int channels, Step* st) {
+    std::vector<int32_t> q(channels), sh(channels);
+    for (int c = 0; c < channels; ++c) {
+      const float ws = Wt.scales.size() > 1 ? Wt.scales[c] : Wt.scale();
+      const double eff = double(I.scale()) * double(ws) / double(O.scale());
+      int s = 0;
+      quantize_multiplier(eff, &q[c], &s);
+      sh[c] = s;
+    }
+    st->mult_off = arena->add(q.data(), q.size() * 4);
+    st->shift_off = arena->add(sh.data(), sh.size() * 4);
+  };
+
+  std::vector<bool> pad_folded(G.ops.size(), false);
+  for (size_t i = 0; i < G.ops.size(); ++i) {
+    const GOp& op = G.ops[i];
+    Step st{};
+    st.op = int(i);
+    switch (op.code) {
+      case kConv2D:
+      case kDepthwise: {
+        const bool dw = op.code == kDepthwise;
+        if (op.inputs.size() < 2) return fail(TOD_ERR_MODEL, "conv operator %zu has %zu inputs", i, op.inputs.size());
+        int src = op.inputs[0];
+        const GTensor& Wt = G.tensors[op.inputs[1]];
+        const int bias_t = op.inputs.size() > 2 ? op.inputs[2] : -1;
+        const GTensor& O = G.tensors[op.outputs[0]];
+        const GTensor* I = &G.tensors[src];
+        if (I->type != kI8 || Wt.type != kI8 || O.type != kI8 || !Wt.is_const())
+          return fail(TOD_ERR_UNSUPPORTED, "conv operator %zu: only int8 activations with constant int8 weights are supported", i);
+        if (dw && op.depth_multiplier != 1) return fail(TOD_ERR_UNSUPPORTED, "depthwise multiplier %d", op.depth_multiplier);
+        for (int64_t z : Wt.zero_points)
+          if (z != 0) return fail(TOD_ERR_UNSUPPORTED, "conv operator %zu: weight zero point must be 0", i);
+        ConvGeom g{};
+        g.KH = Wt.dims[1];
+        g.KW = Wt.dims[2];
+        g.OC = dw ? Wt.dims[3] : Wt.dims[0];
+        g.stride_h = op.stride_h; g.stride_w = op.stride_w; g.dil_h = op.dil_h; g.dil_w = op.dil_w;
+        int OH, OW, ph, pw;
+        conv_out_pad(op.padding, I->dims[1], g.KH, g.stride_h, g.dil_h, &OH, &ph);
+        conv_out_pad(op.padding, I->dims[2], g.KW, g.stride_w, g.dil_w, &OW, &pw);
+        if (O.dims[1] != OH || O.dims[2] != OW || O.dims[3] != g.OC || (!dw && Wt.dims[3] != I->dims[3]) || (dw && Wt.dims[3] != I->dims[3]))
+          return fail(TOD_ERR_MODEL, "conv operator %zu ('%s'): inconsistent shapes", i, O.name.c_str());
+        g.pad_top = ph;
+        g.pad_left = pw;
+        // PAD folding: a zero-point PAD feeding only this VALID convolution contributes nothing to the
+        // accumulators (in - zp == 0), which is exactly "tap skipped" on the unpadded tensor.
+        const int pp = producer[src];
+        if (fuse && op.padding == kValid && pp >= 0 && G.ops[pp].code == kPad && consumers[src] == 1) {
+          const GOp& P = G.ops[pp];
+          const GTensor& PI = G.tensors[P.inputs[0]];
+          const GTensor& PD = G.tensors[P.inputs[1]];
+          if (PD.is_const() && PD.type == kI32 && PD.elems() == 8 && PI.scale() == I->scale() && PI.zp() == I->zp()) {
+            int32_t pd[8];
+            std::memcpy(pd, PD.const_data, 32);
+            if (!pd[0] && !pd[1] && !pd[6] && !pd[7]) {
+              g.pad_top = pd[2];
+              g.pad_left = pd[4];
+              src = P.inputs[0];
+              I = &G.tensors[src];
+              pad_folded[pp] = true;
+            }
+          }
+        }
+        g.IH = I->dims[1]; g.IW = I->dims[2]; g.IC = I->dims[3];
+        g.OH = OH; g.OW = OW;
+        st.g = g;
+        st.in0 = src;
+        st.out = op.outputs[0];
+        st.in_zp = I->zp();
+        st.out_zp = O.zp();
+        activation_range(op.activation, O, &st.act_min, &st.act_max);
+        requant_tables(*I, Wt, O, g.OC, &st);
+        st.w_off = arena->add(Wt.const_data, Wt.const_bytes);
+        if (bias_t >= 0) {
+          const GTensor& B = G.tensors[bias_t];
+          if (!B.is_const() || B.type != kI32 || B.elems() != g.OC) return fail(TOD_ERR_UNSUPPORTED, "conv operator %zu: bias must be constant int32[OC]", i);
+          st.bias_off = arena->add(B.const_data, B.const_bytes);
+        }
+        if (dw) {
+          st.kind = kStepDepthwise;
+          st.macs = int64_t(OH) * OW * g.OC * g.KH * g.KW;
+        } else {
+          st.kind = kStepConvDirect;
+          const int taps = g.KH * g.KW;
+          std::vector<int32_t> wsum(size_t(g.OC) * taps, 0);
+          const int8_t* w = reinterpret_cast<const int8_t*>(Wt.const_data);
+          for (int oc = 0; oc < g.OC; ++oc)
+            for (int tp = 0; tp < taps; ++tp) {
+              int32_t s = 0;
+              for (int ic = 0; ic < g.IC; ++ic) s += w[(size_t(oc) * taps + tp) * g.IC + ic];
+              wsum[size_t(oc) * taps + tp] = s;
+            }
+          st.wsum_off = arena->add(wsum.data(), wsum.size() * 4);
+          st.macs = int64_t(OH) * OW * g.OC * taps * g.IC;
+        }
+        break;
+      }
+      case kAdd: {
+        const GTensor& A = G.tensors[op.inputs[0]];
+        const GTensor& B = G.tensors[op.inputs[1]];
+        const GTensor& O = G.tensors[op.outputs[0]];
+        if (A.elems() != B.elems() || A.elems() != O.elems() || A.type != kI8 || B.type != kI8 || O.type != kI8 || A.is_const() || B.is_const())
+          return fail(TOD_ERR_UNSUPPORTED, "ADD operator %zu: only same-shape int8 activations are supported", i);
+        st.kind = kStepAdd;
+        st.in0 = op.inputs[0]; st.in1 = op.inputs[1]; st.out = op.outputs[0];
+        const double twice_max = 2 * std::max(A.scale(), B.scale());  // tensorflow/lite/kernels/add.cc Prepare
+        int s;
+        quantize_multiplier(A.scale() / twice_max, &st.add.mult_a, &s); st.add.shift_a = s;
+        quantize_multiplier(B.scale() / twice_max, &st.add.mult_b, &s); st.add.shift_b = s;
+        quantize_multiplier(twice_max / ((1 << 20) * O.scale()), &st.add.mult_out, &s); st.add.shift_out = s;
+        st.add.zp_a = A.zp(); st.add.zp_b = B.zp(); st.add.zp_out = O.zp();
+        activation_range(op.activation, O, &st.add.act_min, &st.add.act_max);
+        break;
+      }
+      case kQuantize:
+      case kRelu:
+      case kTanh: {
+        const GTensor& I = G.tensors[op.inputs[0]];
+        const GTensor& O = G.tensors[op.outputs[0]];
+        const bool in8 = I.type == kI8 || I.type == kU8, out8 = O.type == kI8 || O.type == kU8;
+        if (!in8 || !out8 || I.is_const() || I.elems() != O.elems())
+          return fail(TOD_ERR_UNSUPPORTED, "operator %zu (code %d): only 8-bit -> 8-bit activations are supported", i, op.code);
+        uint8_t lut[256];
+        const int32_t imin = I.type == kU8 ? 0 : -128;
+        const int32_t omin = O.type == kU8 ? 0 : -128, omax = O.type == kU8 ? 255 : 127;
+        if (op.code == kTanh) {
+          if (I.type != O.type) return fail(TOD_ERR_UNSUPPORTED, "TANH operator %zu changes the tensor type", i);
+          const float inv = 1 / O.scale();  // activations.cc PopulateLookupTable
+          for (int k = 0; k < 256; ++k) {
+            const int32_t v = imin + k;
+            const float deq = I.scale() * (v - I.zp());
+            const float tr = std::tanh(deq);
+            const float resc = std::round(tr * inv);
+            const int32_t qv = int32_t(resc + O.zp());
+            lut[uint8_t(v)] = uint8_t(std::max(std::min(omax, qv), omin));
+          }
+        } else {
+          int32_t q; int sh;
+          quantize_multiplier(double(I.scale()) / double(O.scale()), &q, &sh);
+          int32_t lo = omin;
+          if (op.code == kRelu) lo = std::max(omin, O.zp() + int32_t(std::round(0.0f / O.scale())));
+          for (int k = 0; k < 256; ++k) {
+            const int32_t v = imin + k;
+            int32_t r = mul_by_quant_mult(v - I.zp(), q, sh) + O.zp();
+            r = std::min(std::max(r, lo), omax);
+            lut[uint8_t(v)] = uint8_t(r);
+          }
+        }
+        st.kind = kStepLut;
+        st.in0 = op.inputs[0]; st.out = op.outputs[0];
+        st.lut_off = arena->add(lut, 256);
+        break;
+      }
+      case kPad: {
+        const GTensor& I = G.tensors[op.inputs[0]];
+        const GTensor& PD = G.tensors[op.inputs[1]];
+        const GTensor& O = G.tensors[op.outputs[0]];
+        if (I.type != kI8 || !PD.is_const() || PD.type != kI32 || PD.elems() != 8) return fail(TOD_ERR_UNSUPPORTED, "PAD operator %zu: need int8 input and constant int32[4,2] paddings", i);
+        int32_t pd[8];
+        std::memcpy(pd, PD.const_data, 32);
+        if (pd[0] || pd[1] || pd[6] || pd[7]) return fail(TOD_ERR_UNSUPPORTED, "PAD operator %zu: batch / channel padding", i);
+        if (O.dims[1] != I.dims[1] + pd[2] + pd[3] || O.dims[2] != I.dims[2] + pd[4] + pd[5] || O.dims[3] != I.dims[3])
+          return fail(TOD_ERR_MODEL, "PAD operator %zu: inconsistent shapes", i);
+        st.kind = kStepPad;
+        st.in0 = op.inputs[0]; st.out = op.outputs[0];
+        st.pad_top = pd[2]; st.pad_left = pd[4];
+        st.fill = int8_t(O.zp());
+        break;
+      }
+      case kResizeBilinear: {
+        const GTensor& I = G.tensors[op.inputs[0]];
+        const GTensor& O = G.tensors[op.outputs[0]];
+        if (I.type != kI8 || O.type != kI8 || I.dims[3] != O.dims[3] || I.dims[3] % 4 != 0)
+          return fail(TOD_ERR_UNSUPPORTED, "RESIZE_BILINEAR operator %zu: need int8 with channels %% 4 == 0", i);
+        st.kind = kStepResize;
+        st.in0 = op.inputs[0]; st.out = op.outputs[0];
+        st.align_corners = op.align_corners; st.half_pixel = op.half_pixel_centers;
+        break;
+      }
+      case kReshape:
+      case kConcat:
+        continue;  // aliases; residual copies are appended below
+      default:
+        return fail(TOD_ERR_UNSUPPORTED, "operator code %d", op.code);
+    }
+    y->steps.push_back(st);
+    // copies for concat inputs that could not be placed run right after their concat's position
+    (void)copies;
+  }
+  // un-aliased concat inputs: a copy step after the producer has run (append in op order)
+  for (const CopyJob& c : copies) {
+    Step st{};
+    st.kind = kStepCopy;
+    st.op = c.op;
+    st.in0 = c.src; st.out = c.dst;
+    st.copy_dst_off = c.off; st.copy_bytes = c.bytes;
+    // insert after the last step whose op index < concat op index
+    auto it = std::find_if(y->steps.begin(), y->steps.end(), [&](const Step& s) { return s.op > c.op; });
+    y->steps.insert(it, st);
+  }
+  // drop folded PADs
+  y->steps.erase(std::remove_if(y->steps.begin(), y->steps.end(), [&](const Step& s) { return s.kind == kStepPad && pad_folded[s.op]; }),
+                 y->steps.end());
+  for (const Step& s : y->steps) {
+    y->macs_per_tile += s.macs;
+    if (s.in0 >= 0 && !y->place[s.in0].base) return fail(TOD_ERR_MODEL, "operator %d reads tensor %d which nothing produces", s.op, s.in0);
+  }
+  return TOD_OK;
+}
+
+int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
+  TOD_CUDA(cudaMalloc(&y->d_const, arena.host.size() ? arena.host.size() : 256));
+  TOD_CUDA(cudaMemcpy(y->d_const, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
+  for (Step& st : y->steps) {
+    if (st.kind != kStepConvDirect || y->opt.conv_impl != 0) continue;
+    const Place& pi = y->place[st.in0];
+    const Place& po = y->place[st.out];
+    const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
+    if (!conv_tc_supported(st.g, pi.tile_stride, pi.base, w)) continue;
+    ConvTcArgs a{};
+    a.g = st.g;
+    a.in = reinterpret_cast<const int8_t*>(pi.base);
+    a.in_tile_stride = pi.tile_stride;
+    a.w = w;
+    a.in_zp = st.in_zp;
+    a.rq = Requant{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
+                   st.out_zp, st.act_min, st.act_max};
+    a.out = reinterpret_cast<int8_t*>(po.base);
+    a.out_tile_stride = po.tile_stride;
+    a.max_tiles = y->opt.max_tiles;
+    a.h_bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(arena.host.data() + st.bias_off) : nullptr;
+    a.h_wsum = reinterpret_cast<const int32_t*>(arena.host.data() + st.wsum_off);
+    TOD_TRY(conv_tc_create(a, &st.tc));
+    st.kind = kStepConvTc;
+    y->tc_layers++;
+  }
+  return TOD_OK;
+}
+
+int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
+  const Place& pi = y->place[st.in0];
+  const Place& po = y->place[st.out];
+  switch (st.kind) {
+    case kStepConvTc:
+      return conv_tc_launch(st.tc, n, s);
+    case kStepConvDirect:
+    case kStepDepthwise: {
+      Requant rq{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
+                 st.out_zp, st.act_min, st.act_max};
+      const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
+      const int32_t* bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(y->d_const + st.bias_off) : nullptr;
+      if (st.kind == kStepDepthwise)
+        launch_depthwise(reinterpret_cast<const int8_t*>(pi.base), pi.tile_stride, w, bias, st.in_zp, st.g, rq,
+                         reinterpret_cast<int8_t*>(po.base), po.tile_stride, n, s);
+      else
+        launch_conv_direct(reinterpret_cast<const int8_t*>(pi.base), pi.tile_stride, w, bias,
+                           reinterpret_cast<const int32_t*>(y->d_const + st.wsum_off), st.in_zp, st.g, rq,
+                           reinterpret_cast<int8_t*>(po.base), po.tile_stride, n, s);
+      break;
+    }
+    case kStepAdd: {
+      const Place& pb = y->place[st.in1];
+      launch_add(reinterpret_cast<const int8_t*>(pi.base), pi.tile_stride, reinterpret_cast<const int8_t*>(pb.base), pb.tile_stride,
+                 reinterpret_cast<int8_t*>(po.base), po.tile_stride, po.bytes, n, st.add, s);
+      break;
+    }
+    case kStepLut:
+      launch_lut(pi.base, pi.tile_stride, po.base, po.tile_stride, po.bytes, n, y->d_const + st.lut_off, s);
+      break;
+    case kStepPad: {
+      const GTensor& I = y->T(st.in0);
+      const GTensor& O = y->T(st.out);
+      launch_pad(reinterpret_cast<const int8_t*>(pi.base), pi.tile_stride, I.dims[1], I.dims[2], I.dims[3], st.pad_top, st.pad_left,
+                 O.dims[1], O.dims[2], st.fill, reinterpret_cast<int8_t*>(po.base), po.tile_stride, n, s);
+      break;
+    }
+    case kStepResize: {
+      const GTensor& I = y->T(st.in0);
+      const GTensor& O = y->T(st.out);
+      launch_resize_bilinear(reinterpret_cast<const int8_t*>(pi.base), pi.tile_stride, I.dims[1], I.dims[2], I.dims[3],
+                             reinterpret_cast<int8_t*>(po.base), po.tile_stride, O.dims[1], O.dims[2], st.align_corners, st.half_pixel,
+                             n, s);
+      break;
+    }
+    case kStepCopy:
+      launch_copy(pi.base, pi.tile_stride, po.base + st.copy_dst_off, po.tile_stride, st.copy_bytes, n, s);
+      break;
+  }
+  return TOD_OK;
+}
+
+// default YOLACT priors of the FRC head (upstream make_priors order: level, row, column, aspect ratio)
+int default_priors(int P, std::vector<float>* out) {
+  static const int kSizes[5] = {28, 14, 7, 4, 2};
+  static const float kScales[5] = {12.0f, 24.0f, 48.0f, 96.0f, 192.0f};
+  static const float kAspect[3] = {1.0f, 0.5f, 2.0f};
+  int total = 0;
+  for (int s : kSizes) total += 3 * s * s;
+  if (total != P) return -1;
+  out->clear();
+  for (int l = 0; l < 5; ++l) {
+    const int s = kSizes[l];
+    for (int j = 0; j < s; ++j)
+      for (int i = 0; i < s; ++i) {
+        const float x = (float(i) + 0.5f) / float(s), yv = (float(j) + 0.5f) / float(s);
+        for (int a = 0; a < 3; ++a) {
+          const float ar = std::sqrt(kAspect[a]);
+          out->push_back(x);
+          out->push_back(yv);
+          out->push_back(kScales[l] * ar / 224.0f);
+          out->push_back(kScales[l] / ar / 224.0f);
+        }
+      }
+  }
+  return 0;
+}
+
+template <class T>
+int dev_alloc(tod_yolact* y, T** p, size_t count) {
+  void* v = nullptr;
+  TOD_CUDA(cudaMalloc(&v, count * sizeof(T) ? count * sizeof(T) : 256));
+  y->det_allocs.push_back(v);
+  *p = static_cast<T*>(v);
+  return TOD_OK;
+}
+
+int setup_detection(tod_yolact* y) {
+  const Graph& G = y->graph;
+  if (G.outputs.size() < 5) return TOD_OK;
+  // outputs: spatial tensors [1,h,w,c] (seg == outputs[4] as in yolact.rs:91, proto == the other one)
+  // and head tensors [1,P,c] (box: c == 4, coef: c == proto channels, cls: the remaining one)
+  std::vector<int> spatial, head;
+  for (size_t i = 0; i < G.outputs.size(); ++i) {
+    const GTensor& X = G.tensors[G.outputs[i]];
+    if (X.type != kU8) return TOD_OK;
+    if (X.dims[1] > 1) spatial.push_back(int(i));
+    else head.push_back(int(i));
+  }
+  if (spatial.size() != 2 || head.size() != 3) return TOD_OK;
+  const int seg_i = 4;
+  if (std::find(spatial.begin(), spatial.end(), seg_i) == spatial.end()) return TOD_OK;
+  const int proto_i = spatial[0] == seg_i ? spatial[1] : spatial[0];
+  const GTensor& PR = G.tensors[G.outputs[proto_i]];
+  int box_i = -1, coef_i = -1, cls_i = -1;
+  for (int h : head) {
+    const GTensor& X = G.tensors[G.outputs[h]];
+    if (X.dims[3] == 4 && box_i < 0) box_i = h;
+    else if (X.dims[3] == PR.dims[3] && coef_i < 0) coef_i = h;
+    else cls_i = h;
+  }
+  if (box_i < 0 || coef_i < 0 || cls_i < 0) return TOD_OK;
+  const GTensor& BX = G.tensors[G.outputs[box_i]];
+  const GTensor& CL = G.tensors[G.outputs[cls_i]];
+  const GTensor& CF = G.tensors[G.outputs[coef_i]];
+  if (BX.dims[2] != CL.dims[2] || BX.dims[2] != CF.dims[2]) return TOD_OK;
+  DetectCfg c{};
+  c.P = BX.dims[2];
+  c.C = CL.dims[3];
+  c.K = CF.dims[3];
+  c.ph = PR.dims[1];
+  c.pw = PR.dims[2];
+  c.conf_thresh = y->opt.conf_thresh;
+  c.nms_thresh = y->opt.nms_thresh;
+  c.top_k = y->opt.top_k;
+  c.max_dets = y->opt.max_dets;
+  c.box_zp = BX.zp();
+  c.coef_zp = CF.zp();
+  c.proto_zp = PR.zp();
+  c.mask_scale = PR.scale() * CF.scale();
+  if (c.C < 2 || c.top_k < 1 || c.max_dets < 1) return TOD_OK;
+  TOD_TRY(detect_setup_kernels(c));
+  y->o_box = box_i; y->o_cls = cls_i; y->o_coef = coef_i; y->o_proto = proto_i;
+  y->dcfg = c;
+  const size_t mt = size_t(y->opt.max_tiles), fg = size_t(c.C - 1);
+  DetectBuffers& b = y->dbuf;
+  float *exp_diff, *box_deq, *box_exp;
+  TOD_TRY(dev_alloc(y, &y->d_priors, size_t(c.P) * 4));
+  TOD_TRY(dev_alloc(y, &exp_diff, 256));
+  TOD_TRY(dev_alloc(y, &box_deq, 256));
+  TOD_TRY(dev_alloc(y, &box_exp, 256));
+  TOD_TRY(dev_alloc(y, &b.boxes, mt * c.P * 4));
+  TOD_TRY(dev_alloc(y, &b.cand, mt * fg * c.P));
+  TOD_TRY(dev_alloc(y, &b.cand_count, mt * fg));
+  TOD_TRY(dev_alloc(y, &b.surv, mt * fg * c.top_k));
+  TOD_TRY(dev_alloc(y, &b.surv_count, mt));
+  TOD_TRY(dev_alloc(y, &b.det_count, mt));
+  TOD_TRY(dev_alloc(y, &b.det_box, mt * c.max_dets * 4));
+  TOD_TRY(dev_alloc(y, &b.det_score, mt * c.max_dets));
+  TOD_TRY(dev_alloc(y, &b.det_class, mt * c.max_dets));
+  TOD_TRY(dev_alloc(y, &b.det_prior, mt * c.max_dets));
+  TOD_TRY(dev_alloc(y, &b.masks, mt * c.max_dets * c.ph * c.pw));
+  TOD_TRY(dev_alloc(y, &b.masks_bin, mt * c.max_dets * c.ph * c.pw));
+  // exp() of a quantised logit is a function of the u8 code only: 256-entry tables built with the host libm
+  float h_exp[256], h_deq[256], h_bexp[256];
+  for (int d = 0; d < 256; ++d) h_exp[d] = std::exp(CL.scale() * float(d - 255));
+  for (int q = 0; q < 256; ++q) {
+    h_deq[q] = BX.scale() * float(q - c.box_zp);
+    h_bexp[q] = std::exp(h_deq[q] * 0.2f);
+  }
+  TOD_CUDA(cudaMemcpy(exp_diff, h_exp, sizeof(h_exp), cudaMemcpyHostToDevice));
+  TOD_CUDA(cudaMemcpy(box_deq, h_deq, sizeof(h_deq), cudaMemcpyHostToDevice));
+  TOD_CUDA(cudaMemcpy(box_exp, h_bexp, sizeof(h_bexp), cudaMemcpyHostToDevice));
+  b.priors = y->d_priors;
+  b.exp_diff = exp_diff;
+  b.box_deq = box_deq;
+  b.box_exp = box_exp;
+  y->det_ready = true;
+  std::vector<float> pri;
+  if (default_priors(c.P, &pri) == 0) {
+    TOD_CUDA(cudaMemcpy(y->d_priors, pri.data(), pri.size() * 4, cudaMemcpyHostToDevice));
+    y->have_priors = true;
+  }
+  return TOD_OK;
+}
+
+int enqueue_post(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+  if (y->seg_out >= 0) {
+    const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
+    const Place& ps = y->place[y->graph.outputs[y->seg_out]];
+    SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
+    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, s);
+  }
+  if (dets) {
+    const Place& pc = y->place[y->graph.outputs[y->o_cls]];
+    const Place& pb = y->place[y->graph.outputs[y->o_box]];
+    const Place& pf = y->place[y->graph.outputs[y->o_coef]];
+    const Place& pp = y->place[y->graph.outputs[y->o_proto]];
+    TOD_TRY(launch_detect(y->dcfg, y->dbuf, pc.base, pc.tile_stride, pb.base, pb.tile_stride, pf.base, pf.tile_stride, pp.base,
+                          pp.tile_stride, n, masks, s));
+  }
+  return TOD_OK;
+}
+
+// the per-batch pipeline after the input tiles are in place: graph steps + post-processing
+int enqueue_all(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+  for (const Step& st : y->steps) TOD_TRY(run_step(y, st, n, s));
+  TOD_TRY(enqueue_post(y, n, dets, masks, s));
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+int run_pipeline(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+  if (dets && !y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
+  if (dets && !y->have_priors) return fail(TOD_ERR_INVALID_ARG, "no priors for a %d-prior head: call tod_yolact_set_priors first", y->dcfg.P);
+  y->last_tiles = n;
+  if (!y->opt.use_cuda_graph) return enqueue_all(y, n, dets, masks, s);
+  const int key = (n << 2) | (dets ? 2 : 0) | (masks ? 1 : 0);
+  auto it = y->graphs.find(key);
+  if (it == y->graphs.end()) {
+    cudaGraph_t g = nullptr;
+    TOD_CUDA(cudaStreamBeginCapture(y->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_all(y, n, dets, masks, y->stream);
+    const cudaError_t ce = cudaStreamEndCapture(y->stream, &g);
+    if (rc < 0) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (ce != cudaSuccess) return fail(TOD_ERR_CUDA, "CUDA graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t ge = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) return fail(TOD_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    it = y->graphs.emplace(key, ge).first;
+  }
+  TOD_CUDA(cudaGraphLaunch(it->second, s));
+  return TOD_OK;
+}
+
+int fetch_strided(void* dst, const Place& p, int n, cudaStream_t s) {
+  TOD_CUDA(cudaMemcpy2DAsync(dst, size_t(p.bytes), p.base, size_t(p.tile_stride), size_t(p.bytes), size_t(n), cudaMemcpyDeviceToHost, s));
+  return TOD_OK;
+}
+
+int upload_axis(AxisTables* t) {
+  cudaFree(t->d_left); cudaFree(t->d_count); cudaFree(t->d_weight);
+  t->d_left = nullptr; t->d_count = nullptr; t->d_weight = nullptr;
+  TOD_CUDA(cudaMalloc(&t->d_left, t->left.size() * 4));
+  TOD_CUDA(cudaMalloc(&t->d_count, t->count.size() * 4));
+  TOD_CUDA(cudaMalloc(&t->d_weight, t->weight.size() * 4));
+  TOD_CUDA(cudaMemcpy(t->d_left, t->left.data(), t->left.size() * 4, cudaMemcpyHostToDevice));
+  TOD_CUDA(cudaMemcpy(t->d_count, t->count.data(), t->count.size() * 4, cudaMemcpyHostToDevice));
+  TOD_CUDA(cudaMemcpy(t->d_weight, t->weight.data(), t->weight.size() * 4, cudaMemcpyHostToDevice));
+  return TOD_OK;
+}
+
+ResampleAxis axis_of(const AxisTables& t) { return ResampleAxis{t.d_left, t.d_count, t.d_weight, t.in_size, t.out_size}; }
+
+int ensure_classify_buffers(tod_yolact* y, int W, int H) {
+  if (y->cw == W && y->chh == H) return TOD_OK;
+  if (W < 2 || H < 2 || W > 8192 || H > 8192) return fail(TOD_ERR_INVALID_ARG, "classify: unsupported frame size %dx%d", W, H);
+  const int tw = y->tile_w(), th = y->tile_h();
+  TOD_TRY(build_axis(H, th, &y->pre_v));       // 640x480 -> 448x224 (yolact.rs:208): vertical pass first
+  TOD_TRY(build_axis(W, 2 * tw, &y->pre_h));
+  TOD_TRY(build_axis(th, H, &y->post_v));      // 448x224 -> 640x480 (yolact.rs:231)
+  TOD_TRY(build_axis(2 * tw, W, &y->post_h));
+  TOD_TRY(upload_axis(&y->pre_v));
+  TOD_TRY(upload_axis(&y->pre_h));
+  TOD_TRY(upload_axis(&y->post_v));
+  TOD_TRY(upload_axis(&y->post_h));
+  const size_t frames = size_t(y->opt.max_tiles) / 2;
+  cudaFree(y->d_tmp); cudaFree(y->d_frames); cudaFree(y->d_tiles_rgb);
+  y->d_tmp = nullptr; y->d_frames = nullptr; y->d_tiles_rgb = nullptr;
+  const size_t tmp_px = std::max(size_t(th) * W, size_t(H) * 2 * tw);
+  TOD_CUDA(cudaMalloc(&y->d_tmp, frames * tmp_px * 3 * sizeof(float)));
+  TOD_CUDA(cudaMalloc(&y->d_frames, frames * size_t(W) * H * 4));
+  TOD_CUDA(cudaMalloc(&y->d_tiles_rgb, frames * 2 * size_t(tw) * th * 3));
+  y->cw = W;
+  y->chh = H;
+  return TOD_OK;
+}
+
+int classify_device(tod_yolact* y, uint32_t* d_frames, int n, int W, int H, uint16_t* d_target, cudaStream_t s) {
+  const int tw = y->tile_w(), th = y->tile_h();
+  if (y->seg_out < 0) return fail(TOD_ERR_UNSUPPORTED, "classify needs output #4 ([1,h,w,c] segmentation logits, yolact.rs:91)");
+  launch_classify_pre(d_frames, n, W, H, axis_of(y->pre_v), axis_of(y->pre_h), y->d_tmp, y->d_tiles_rgb, tw, th, s);
+  const Place& pin = y->place[y->graph.inputs[0]];
+  TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), y->d_tiles_rgb, size_t(pin.bytes), size_t(pin.bytes), size_t(2 * n),
+                             cudaMemcpyDeviceToDevice, s));
+  TOD_TRY(run_pipeline(y, 2 * n, false, false, s));
+  launch_classify_post(y->d_tile_classes, n, W, H, axis_of(y->post_v), axis_of(y->post_h), y->d_tmp, d_frames, d_target, tw, th, s);
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+int check_diverged(tod_yolact* y, int tiles, cudaStream_t s) {
+  if (y->opt.id_mode != 0 || y->seg_out < 0) return TOD_OK;
+  TOD_CUDA(cudaMemcpyAsync(y->h_diverges, y->d_diverges, sizeof(int) * tiles, cudaMemcpyDeviceToHost, s));
+  TOD_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < tiles; ++i)
+    if (y->h_diverges[i]) return TOD_WARN_REFERENCE_DIVERGES;
+  return TOD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tod_yolact_default_options(tod_yolact_options* o) {
+  if (!o) return;
+  o->max_tiles = 2;
+  o->id_mode = 0;
+  o->conf_thresh = 0.05f;
+  o->nms_thresh = 0.5f;
+  o->top_k = 200;
+  o->max_dets = 100;
+  o->use_cuda_graph = 1;
+  o->conv_impl = 0;
+  o->fusion = 1;
+}
+
+int tod_model_inspect(const char* tflite_path, int32_t* num_ops, int32_t* num_tensors, int64_t* macs) {
+  Graph g;
+  TOD_TRY(read_tflite(tflite_path, &g));
+  if (num_ops) *num_ops = int32_t(g.ops.size());
+  if (num_tensors) *num_tensors = int32_t(g.tensors.size());
+  if (macs) {
+    int64_t m = 0;
+    for (const GOp& op : g.ops) {
+      if (op.code != kConv2D && op.code != kDepthwise) continue;
+      if (op.inputs.size() < 2 || op.outputs.empty()) continue;
+      const GTensor& W = g.tensors[op.inputs[1]];
+      const GTensor& O = g.tensors[op.outputs[0]];
+      const int64_t per = op.code == kConv2D ? int64_t(W.dims[1]) * W.dims[2] * W.dims[3] : int64_t(W.dims[1]) * W.dims[2];
+      m += O.elems() * per;
+    }
+    *macs = m;
+  }
+  return TOD_OK;
+}
+
+void tod_yolact_destroy(tod_yolact* y) {
+  if (!y) return;
+  cudaSetDevice(y->device);
+  if (y->stream) cudaStreamSynchronize(y->stream);
+  for (auto& kv : y->graphs) cudaGraphExecDestroy(kv.second);
+  for (Step& s : y->steps)
+    if (s.tc) conv_tc_destroy(s.tc);
+  for (void* p : y->det_allocs) cudaFree(p);
+  for (AxisTables* t : {&y->pre_v, &y->pre_h, &y->post_v, &y->post_h}) {
+    cudaFree(t->d_left); cudaFree(t->d_count); cudaFree(t->d_weight);
+  }
+  cudaFree(y->d_tmp); cudaFree(y->d_frames); cudaFree(y->d_tiles_rgb);
+  cudaFree(y->d_tile_classes); cudaFree(y->d_diverges);
+  if (y->h_diverges) cudaFreeHost(y->h_diverges);
+  cudaFree(y->d_const); cudaFree(y->d_act);
+  if (y->stream) cudaStreamDestroy(y->stream);
+  delete y;
+}
+
+int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_options* opts, tod_yolact** out) {
+  if (!tflite_path || !out) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_create: null argument");
+  *out = nullptr;
+  tod_yolact_options o;
+  tod_yolact_default_options(&o);
+  if (opts) o = *opts;
+  if (o.max_tiles < 1 || o.max_tiles > 16384) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_create: max_tiles must be in [1,16384]");
+  if (o.id_mode != 0 && o.id_mode != 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_create: id_mode must be 0 or 1");
+  std::unique_ptr<tod_yolact> y(new tod_yolact());
+  y->device = device;
+  y->opt = o;
+  TOD_TRY(read_tflite(tflite_path, &y->graph));  // before touching the GPU: a bad model fails the same way everywhere
+  TOD_TRY(select_device(device));
+  tod_yolact* raw = y.release();
+  auto bail = [&](int rc) {
+    tod_yolact_destroy(raw);
+    return rc;
+  };
+  cudaError_t ce = cudaStreamCreateWithFlags(&raw->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
+  ConstArena arena;
+  int rc = plan(raw, &arena);
+  if (rc < 0) return bail(rc);
+  rc = upload_consts_and_bind(raw, arena);
+  if (rc < 0) return bail(rc);
+  // literal post-processing needs output #4 == [1,gh,gw,c] (yolact.rs:91,108,118)
+  const Graph& G = raw->graph;
+  if (G.outputs.size() > 4) {
+    const GTensor& S = G.tensors[G.outputs[4]];
+    if (S.type == kU8 && S.dims[1] > 1 && S.dims[1] * S.dims[2] <= 1024 && S.dims[3] >= 4 && raw->tile_w() % S.dims[2] == 0 &&
+        raw->tile_h() % S.dims[1] == 0 && raw->tile_w() / S.dims[2] == raw->tile_h() / S.dims[1])
+      raw->seg_out = 4;
+  }
+  const size_t mt = size_t(o.max_tiles);
+  if ((ce = cudaMalloc(&raw->d_tile_classes, mt * raw->tile_w() * raw->tile_h() * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&raw->d_diverges, mt * sizeof(int))) != cudaSuccess ||
+      (ce = cudaMallocHost(&raw->h_diverges, mt * sizeof(int))) != cudaSuccess)
+    return bail(fail(TOD_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(ce)));
+  cudaMemset(raw->d_diverges, 0, mt * sizeof(int));
+  rc = setup_detection(raw);
+  if (rc < 0) return bail(rc);
+  raw->launches_per_call = int(raw->steps.size());
+  *out = raw;
+  return TOD_OK;
+}
+
+int tod_yolact_set_priors(tod_yolact* y, const float* priors, int n) {
+  if (!y || !priors) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_set_priors: null argument");
+  if (!y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
+  if (n != y->dcfg.P) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_set_priors: the head has %d priors, got %d", y->dcfg.P, n);
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_CUDA(cudaMemcpy(y->d_priors, priors, size_t(n) * 16, cudaMemcpyHostToDevice));
+  y->have_priors = true;
+  return TOD_OK;
+}
+
+int tod_yolact_num_outputs(const tod_yolact* y) { return y ? int(y->graph.outputs.size()) : 0; }
+int tod_yolact_num_tensors(const tod_yolact* y) { return y ? int(y->graph.tensors.size()) : 0; }
+int tod_yolact_num_ops(const tod_yolact* y) { return y ? int(y->graph.ops.size()) : 0; }
+
+int tod_yolact_tensor_info(const tod_yolact* y, int tensor, int32_t shape4[4], int32_t* type, float* scale, int32_t* zero_point,
+                           int32_t* elems) {
+  if (!y || tensor < 0 || tensor >= int(y->graph.tensors.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_tensor_info: bad tensor index");
+  const GTensor& X = y->graph.tensors[tensor];
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = X.dims[i];
+  if (type) *type = X.type;
+  if (scale) *scale = X.scale();
+  if (zero_point) *zero_point = X.zp();
+  if (elems) *elems = int32_t(X.elems());
+  return TOD_OK;
+}
+
+int tod_yolact_output_info(const tod_yolact* y, int index, int32_t shape4[4], float* scale, int32_t* zero_point, int32_t* elems) {
+  if (!y || index < 0 || index >= int(y->graph.outputs.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_output_info: bad output index");
+  return tod_yolact_tensor_info(y, y->graph.outputs[index], shape4, nullptr, scale, zero_point, elems);
+}
+
+int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int n, void* stream) {
+  if (!y || !d_rgb_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_infer_tiles_device: null argument");
+  if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_infer_tiles_device: n=%d outside [1,%d]", n, y->opt.max_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : y->stream;
+  const Place& pin = y->place[y->graph.inputs[0]];
+  TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), d_rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n),
+                             cudaMemcpyDeviceToDevice, s));
+  const bool dets = y->det_ready && y->have_priors;
+  return run_pipeline(y, n, dets, dets, s);
+}
+
+int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out) {
+  if (!y || !out || index < 0 || index >= int(y->graph.outputs.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_output: bad argument");
+  if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_output: n=%d but the last call ran %d tiles", n, y->last_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_TRY(fetch_strided(out, y->place[y->graph.outputs[index]], n, y->stream));
+  TOD_CUDA(cudaStreamSynchronize(y->stream));
+  return TOD_OK;
+}
+
+int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t out_bytes) {
+  if (!y || !out || tensor < 0 || tensor >= int(y->graph.tensors.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: bad argument");
+  if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: n=%d but the last call ran %d tiles", n, y->last_tiles);
+  const Place& p = y->place[tensor];
+  if (!p.base) return fail(TOD_ERR_INVALID_ARG, "tensor %d is a constant or is not materialised", tensor);
+  if (out_bytes < size_t(p.bytes) * n) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: buffer too small (%zu < %lld)", out_bytes, (long long)(p.bytes * n));
+  // a PAD folded into its convolution is never written
+  for (size_t i = 0; i < y->graph.ops.size(); ++i)
+    if (y->graph.ops[i].code == kPad && y->graph.ops[i].outputs[0] == tensor) {
+      bool present = false;
+      for (const Step& s : y->steps) present |= (s.kind == kStepPad && s.op == int(i));
+      if (!present) return fail(TOD_ERR_INVALID_ARG, "tensor %d (a PAD output) is fused away; create the handle with fusion = 0 to fetch it", tensor);
+    }
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_TRY(fetch_strided(out, p, n, y->stream));
+  TOD_CUDA(cudaStreamSynchronize(y->stream));
+  return TOD_OK;
+}
+
+int tod_yolact_fetch_tile_classes(tod_yolact* y, int n, uint32_t* out) {
+  if (!y || !out) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tile_classes: null argument");
+  if (y->seg_out < 0) return fail(TOD_ERR_UNSUPPORTED, "the model has no segmentation output #4");
+  if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tile_classes: n=%d but the last call ran %d tiles", n, y->last_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_CUDA(cudaMemcpyAsync(out, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, y->stream));
+  TOD_CUDA(cudaStreamSynchronize(y->stream));
+  return check_diverged(y, n, y->stream);
+}
+
+int tod_yolact_last_diverged(tod_yolact* y, int* diverged) {
+  if (!y || !diverged) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_last_diverged: null argument");
+  *diverged = 0;
+  if (y->last_tiles < 1) return TOD_OK;
+  TOD_CUDA(cudaSetDevice(y->device));
+  const int rc = check_diverged(y, y->last_tiles, y->stream);
+  if (rc < 0) return rc;
+  *diverged = rc == TOD_WARN_REFERENCE_DIVERGES ? 1 : 0;
+  return TOD_OK;
+}
+
+int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
+  if (!y || !d) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: null argument");
+  if (!y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
+  if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: n=%d but the last call ran %d tiles", n, y->last_tiles);
+  const DetectCfg& c = y->dcfg;
+  if (d->max_dets != c.max_dets) return fail(TOD_ERR_INVALID_ARG, "tod_detections.max_dets=%d, handle was created with %d", d->max_dets, c.max_dets);
+  TOD_CUDA(cudaSetDevice(y->device));
+  cudaStream_t s = y->stream;
+  const size_t nd = size_t(n) * c.max_dets;
+  const DetectBuffers& b = y->dbuf;
+  if (d->count) TOD_CUDA(cudaMemcpyAsync(d->count, b.det_count, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+  if (d->boxes) TOD_CUDA(cudaMemcpyAsync(d->boxes, b.det_box, nd * 16, cudaMemcpyDeviceToHost, s));
+  if (d->scores) TOD_CUDA(cudaMemcpyAsync(d->scores, b.det_score, nd * 4, cudaMemcpyDeviceToHost, s));
+  if (d->classes) TOD_CUDA(cudaMemcpyAsync(d->classes, b.det_class, nd * 4, cudaMemcpyDeviceToHost, s));
+  if (d->priors) TOD_CUDA(cudaMemcpyAsync(d->priors, b.det_prior, nd * 4, cudaMemcpyDeviceToHost, s));
+  if (d->masks) TOD_CUDA(cudaMemcpyAsync(d->masks, b.masks, nd * c.ph * c.pw * 4, cudaMemcpyDeviceToHost, s));
+  if (d->masks_bin) TOD_CUDA(cudaMemcpyAsync(d->masks_bin, b.masks_bin, nd * c.ph * c.pw, cudaMemcpyDeviceToHost, s));
+  TOD_CUDA(cudaStreamSynchronize(s));
+  return TOD_OK;
+}
+
+int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8, uint32_t* tile_classes,
+                           tod_detections* dets) {
+  if (!y || !rgb_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_infer_tiles: null argument");
+  if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_infer_tiles: n=%d outside [1,%d]", n, y->opt.max_tiles);
+  if (tile_classes && y->seg_out < 0) return fail(TOD_ERR_UNSUPPORTED, "the model has no segmentation output #4");
+  TOD_CUDA(cudaSetDevice(y->device));
+  cudaStream_t s = y->stream;
+  const Place& pin = y->place[y->graph.inputs[0]];
+  // yolact.rs:161-162 copy_from_slice into the input tensor
+  TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n), cudaMemcpyHostToDevice, s));
+  const bool want_dets = dets != nullptr;
+  TOD_TRY(run_pipeline(y, n, want_dets, want_dets && (dets->masks || dets->masks_bin), s));
+  if (outputs_u8)
+    for (size_t k = 0; k < y->graph.outputs.size(); ++k)
+      if (outputs_u8[k]) TOD_TRY(fetch_strided(outputs_u8[k], y->place[y->graph.outputs[k]], n, s));
+  if (tile_classes) TOD_CUDA(cudaMemcpyAsync(tile_classes, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, s));
+  TOD_CUDA(cudaStreamSynchronize(s));
+  if (want_dets) TOD_TRY(tod_yolact_fetch_detections(y, n, dets));
+  return check_diverged(y, n, s);
+}
+
+int tod_yolact_classify_batch_device(tod_yolact* y, uint32_t* d_frames, int n, int width, int height, uint16_t* d_target, void* stream) {
+  if (!y || !d_frames) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_classify_batch_device: null argument");
+  if (n < 1 || 2 * n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "classify: %d frames need %d tiles, handle holds %d", n, 2 * n, y->opt.max_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_TRY(ensure_classify_buffers(y, width, height));
+  return classify_device(y, d_frames, n, width, height, d_target, stream ? static_cast<cudaStream_t>(stream) : y->stream);
+}
+
+int tod_yolact_classify_batch(tod_yolact* y, uint32_t* frames, int n, int width, int height) {
+  if (!y || !frames) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_classify_batch: null argument");
+  if (n < 1 || 2 * n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "classify: %d frames need %d tiles, handle holds %d", n, 2 * n, y->opt.max_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_TRY(ensure_classify_buffers(y, width, height));
+  cudaStream_t s = y->stream;
+  const size_t bytes = size_t(n) * width * height * 4;
+  TOD_CUDA(cudaMemcpyAsync(y->d_frames, frames, bytes, cudaMemcpyHostToDevice, s));
+  TOD_TRY(classify_device(y, y->d_frames, n, width, height, nullptr, s));
+  TOD_CUDA(cudaMemcpyAsync(frames, y->d_frames, bytes, cudaMemcpyDeviceToHost, s));  // yolact.rs:233 copy_from_slice
+  TOD_CUDA(cudaStreamSynchronize(s));
+  return check_diverged(y, 2 * n, s);
+}
+
+int tod_yolact_classify(tod_yolact* y, uint32_t* frame, int width, int height) { return tod_yolact_classify_batch(y, frame, 1, width, height); }
+
+int tod_yolact_stats(const tod_yolact* y, int64_t* macs_per_tile, int32_t* launches_per_call, int32_t* tc_conv_layers) {
+  if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_stats: null handle");
+  if (macs_per_tile) *macs_per_tile = y->macs_per_tile;
+  if (launches_per_call) *launches_per_call = y->launches_per_call + (y->seg_out >= 0 ? 1 : 0) + (y->det_ready && y->have_priors ? 4 : 0);
+  if (tc_conv_layers) *tc_conv_layers = y->tc_layers;
+  return TOD_OK;
+}
+
+int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int cap) {
+  if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_profile_ops: null handle");
+  if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_profile_ops: n=%d outside [1,%d]", n, y->opt.max_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  cudaEvent_t e0, e1;
+  TOD_CUDA(cudaEventCreate(&e0));
+  TOD_CUDA(cudaEventCreate(&e1));
+  cudaStream_t s = y->stream;
+  int i = 0;
+  for (const Step& st : y->steps) {
+    TOD_TRY(run_step(y, st, n, s));  // warm
+    TOD_CUDA(cudaEventRecord(e0, s));
+    TOD_TRY(run_step(y, st, n, s));
+    TOD_CUDA(cudaEventRecord(e1, s));
+    TOD_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    TOD_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (i < cap) {
+      if (ms) ms[i] = t;
+      if (kinds) kinds[i] = y->graph.ops[st.op].code | (st.kind == kStepConvTc ? 0x1000 : 0) | (st.kind == kStepCopy ? 0x2000 : 0);
+    }
+    ++i;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  y->last_tiles = n;
+  return i;
+}
+
+}  // extern "C"
