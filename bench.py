@@ -150,7 +150,12 @@ def main():
     n = args.tiles
     y = tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl)
     st = y.stats()
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the handle's own stream", and CUDA events
+    # recorded by torch must sit on the stream the kernels are launched on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     tiles_h = torch.from_numpy(synth.rgb_tiles(n, seed=2 + rank)).pin_memory()
     tiles_d = tiles_h.cuda()

@@ -206,6 +206,11 @@ int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int 
  * ====================================================================================== */
 int tod_i8_gemm_selftest(int device, int M, int N, int K, int iters, float* ms_per_iter, double* max_abs_err);
 
+/* One KxK (K = 1 or 3), stride-1, SAME convolution [tiles,H,W,IC] -> [tiles,H,W,OC] on seeded random data through
+ * both the tcgen05 implicit-GEMM kernel and the CUDA-core direct kernel: times both and counts differing bytes. */
+int tod_conv_selftest(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, float* ms_tc,
+                      float* ms_direct, long long* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

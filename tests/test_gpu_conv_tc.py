@@ -1,0 +1,31 @@
+"""tcgen05 int8 implicit-GEMM convolution vs the CUDA-core direct kernel on the same device buffers
+(the direct kernel itself is pinned against the CPU oracle in test_gpu_graph.py).  Bit-exact bar."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # tiles, H, W, IC, OC, K
+    (2, 28, 28, 256, 256, 3),    # FPN / protonet / head tower
+    (3, 56, 56, 256, 256, 3),    # proto_conv3 (odd tile count: pn = 2 tail masking)
+    (2, 28, 28, 256, 243, 3),    # class head: OC padded to 256, byte stores
+    (2, 14, 14, 256, 12, 3),     # box head
+    (5, 7, 7, 256, 96, 3),       # coefficient head on P5
+    (9, 4, 4, 256, 256, 3),      # P6
+    (33, 2, 2, 256, 256, 3),     # P7
+    (2, 56, 56, 256, 32, 1),     # proto_out
+    (2, 28, 28, 192, 32, 1),     # MobileNetV2 project (BK = 64)
+    (1, 112, 112, 16, 96, 1),    # block_1 expand: IC = 16 -> K chunk zero-filled to 32
+    (2, 56, 56, 144, 32, 1),     # IC = 144 -> 5 chunks of 32, last half zero-filled
+    (2, 14, 14, 96, 576, 1),     # OC = 576 -> 3 N tiles of 192
+    (2, 7, 7, 960, 160, 1),      # BK = 64, 15 chunks
+    (2, 28, 28, 32, 81, 1),      # seg head style: OC = 81
+    (1, 1, 1000, 256, 256, 1),   # plain GEMM, M not a multiple of 128
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_matches_direct(tod, shape):
+    from tod_b200 import _lib
+    ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=2)
+    assert bad == 0, "%d bytes differ (tcgen05 %.3f ms, direct %.3f ms)" % (bad, ms_tc, ms_direct)

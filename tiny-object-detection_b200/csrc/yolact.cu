@@ -249,9 +249,11 @@ int plan(tod_yolact* y, ConstArena* arena) {
     if (X.is_const() || alias_of[t] >= 0 || parent[t].tensor >= 0) continue;
     if (producer[t] < 0 && t != G.inputs[0]) continue;  // unused
     if (X.dims[0] != 1) return fail(TOD_ERR_UNSUPPORTED, "tensor '%s' has batch %d; the model must be exported with batch 1", X.name.c_str(), X.dims[0]);
-    root_stride[t] = round_up(X.elems() * X.elem_size(), kAlign);
+    // tile stride = dense size rounded to 16 B (what TMA needs): NHWC tensors with C % 16 == 0 stay dense, so a
+    // 1x1 convolution over the whole batch is one flat GEMM
+    root_stride[t] = round_up(X.elems() * X.elem_size(), 16);
     root_off[t] = total;
-    total += root_stride[t] * mt;
+    total = round_up(total + root_stride[t] * mt, 1024);
   }
   y->act_bytes = size_t(total);
   TOD_CUDA(cudaMalloc(&y->d_act, y->act_bytes ? y->act_bytes : 256));
