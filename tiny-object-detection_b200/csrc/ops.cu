@@ -155,6 +155,190 @@ __global__ void __launch_bounds__(256) depthwise_scalar_kernel(const int8_t* __r
   out[int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c] = requant_store(acc, __ldg(rq.mult + c), __ldg(rq.shift + c), rq);
 }
 
+// ------------------------------------------------------------------ pixel-parallel convolution (CUDA cores)
+// For the few CONV_2D shapes the tcgen05 path does not take: the Cin = 3 stem, Cin % 16 != 0 pointwise layers and
+// the strided 3x3 FPN down-samplers.  One thread = one output pixel x OCT output channels; the CTA's weight slab
+// ([K/4 words][OCT], K = taps * Cin padded to 4) sits in shared memory and is read as warp-wide broadcasts
+// (LDS.128 = 4 channels), so the inner loop is one input word + 4 LDS + 16 dp4a.
+constexpr int kPixOct = 16;
+constexpr int kPixThreads = 128;
+
+template <bool IC3>
+__global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                              const int8_t* __restrict__ w,
+                                                              const int32_t* __restrict__ bias,
+                                                              const int32_t* __restrict__ wsum, int32_t in_zp, ConvGeom g,
+                                                              Requant rq, int8_t* __restrict__ out, int64_t out_ts,
+                                                              int tiles) {
+  extern __shared__ int s_w[];  // [taps * icw][OCT] weight words, then [taps][OCT] tap sums
+  const int taps = g.KH * g.KW;
+  const int icw = (g.IC + 3) >> 2;  // input words per tap
+  int* s_ws = s_w + taps * icw * kPixOct;
+  const int oc0 = blockIdx.y * kPixOct;
+  for (int i = threadIdx.x; i < taps * icw * kPixOct; i += kPixThreads) {
+    const int j = i % kPixOct, kw = i / kPixOct;
+    const int tap = kw / icw, c4 = (kw - tap * icw) * 4;
+    int word = 0;
+    if (oc0 + j < g.OC) {
+      const int8_t* src = w + (int64_t(oc0 + j) * taps + tap) * g.IC + c4;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (c4 + b < g.IC) word |= (int(src[b]) & 0xFF) << (8 * b);
+    }
+    s_w[i] = word;
+  }
+  for (int i = threadIdx.x; i < taps * kPixOct; i += kPixThreads) {
+    const int j = i % kPixOct, tap = i / kPixOct;
+    s_ws[i] = (oc0 + j < g.OC) ? wsum[int64_t(oc0 + j) * taps + tap] : 0;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * kPixThreads + threadIdx.x;
+  const int total = tiles * g.OH * g.OW;
+  if (pix >= total) return;
+  const int ox = pix % g.OW;
+  const int oy = (pix / g.OW) % g.OH;
+  const int t = pix / (g.OW * g.OH);
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  int acc[kPixOct];
+#pragma unroll
+  for (int j = 0; j < kPixOct; ++j) acc[j] = 0;
+  for (int fy = 0; fy < g.KH; ++fy) {
+    const int iy = oy * g.stride_h - g.pad_top + fy * g.dil_h;
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int fx = 0; fx < g.KW; ++fx) {
+      const int ix = ox * g.stride_w - g.pad_left + fx * g.dil_w;
+      if (ix < 0 || ix >= g.IW) continue;
+      const int tap = fy * g.KW + fx;
+      const int8_t* ip = tin + (int64_t(iy) * g.IW + ix) * g.IC;
+      const int4* wrow = reinterpret_cast<const int4*>(s_w + tap * icw * kPixOct);
+      const int4* zs = reinterpret_cast<const int4*>(s_ws + tap * kPixOct);
+#pragma unroll
+      for (int q = 0; q < kPixOct / 4; ++q) {
+        const int4 z = zs[q];
+        acc[4 * q + 0] -= in_zp * z.x;
+        acc[4 * q + 1] -= in_zp * z.y;
+        acc[4 * q + 2] -= in_zp * z.z;
+        acc[4 * q + 3] -= in_zp * z.w;
+      }
+      if (IC3) {
+        const int a = (int(ip[0]) & 0xFF) | ((int(ip[1]) & 0xFF) << 8) | ((int(ip[2]) & 0xFF) << 16);
+#pragma unroll
+        for (int q = 0; q < kPixOct / 4; ++q) {
+          const int4 wv = wrow[q];
+          acc[4 * q + 0] = __dp4a(a, wv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = __dp4a(a, wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = __dp4a(a, wv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = __dp4a(a, wv.w, acc[4 * q + 3]);
+        }
+      } else {
+        for (int k = 0; k < icw; ++k) {
+          const int a = *reinterpret_cast<const int*>(ip + 4 * k);
+#pragma unroll
+          for (int q = 0; q < kPixOct / 4; ++q) {
+            const int4 wv = wrow[k * (kPixOct / 4) + q];
+            acc[4 * q + 0] = __dp4a(a, wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = __dp4a(a, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = __dp4a(a, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = __dp4a(a, wv.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  int8_t* op = out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + oc0;
+  int8_t res[kPixOct];
+#pragma unroll
+  for (int j = 0; j < kPixOct; ++j) {
+    const int oc = min(oc0 + j, g.OC - 1);
+    const int32_t a = acc[j] + (bias ? __ldg(bias + oc) : 0);
+    res[j] = requant_store(a, __ldg(rq.mult + oc), __ldg(rq.shift + oc), rq);
+  }
+  if (oc0 + kPixOct <= g.OC && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+    *reinterpret_cast<int4*>(op) = *reinterpret_cast<const int4*>(res);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPixOct; ++j)
+      if (oc0 + j < g.OC) op[j] = res[j];
+  }
+}
+
+// ------------------------------------------------------------------ depthwise, register-resident filters
+// blockDim = (channel groups of 4, pixel lanes).  A thread keeps the 3x3 taps of its 4 channels (pre-masked so a
+// dp4a isolates one channel), their bias and requantisation constants in registers and walks over output pixels;
+// consecutive threads cover consecutive channels, so every global access of a warp is one contiguous segment.
+template <int KK>
+__global__ void __launch_bounds__(256) depthwise_reg_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                           const int8_t* __restrict__ w,
+                                                           const int32_t* __restrict__ bias, int32_t in_zp, ConvGeom g,
+                                                           Requant rq, int8_t* __restrict__ out, int64_t out_ts,
+                                                           int tiles, int pix_per_block) {
+  const int cgi = blockIdx.x * blockDim.x + threadIdx.x;  // channel group
+  if (cgi * 4 >= g.OC) return;
+  const int c = cgi * 4;
+  int wm[KK * KK][4];
+  int wall[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int tp = 0; tp < KK * KK; ++tp) {
+    const int wv = *reinterpret_cast<const int*>(w + int64_t(tp) * g.OC + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wm[tp][j] = wv & (0xFF << (8 * j));
+      wall[j] += int(int8_t((wv >> (8 * j)) & 0xFF));
+    }
+  }
+  int mult[4], shift[4], bs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mult[j] = rq.mult[c + j];
+    shift[j] = rq.shift[c + j];
+    bs[j] = bias ? bias[c + j] : 0;
+  }
+  const int total = tiles * g.OH * g.OW;
+  const int p_end = min(total, (blockIdx.y + 1) * pix_per_block);
+  for (int pix = blockIdx.y * pix_per_block + threadIdx.y; pix < p_end; pix += blockDim.y) {
+    const int ox = pix % g.OW;
+    const int oy = (pix / g.OW) % g.OH;
+    const int t = pix / (g.OW * g.OH);
+    const int8_t* tin = in + int64_t(t) * in_ts + c;
+    const int iy0 = oy * g.stride_h - g.pad_top, ix0 = ox * g.stride_w - g.pad_left;
+    int acc[4] = {0, 0, 0, 0};
+    if (iy0 >= 0 && ix0 >= 0 && iy0 + KK <= g.IH && ix0 + KK <= g.IW) {
+#pragma unroll
+      for (int fy = 0; fy < KK; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < KK; ++fx) {
+          const int a = *reinterpret_cast<const int*>(tin + (int64_t(iy0 + fy) * g.IW + ix0 + fx) * g.IC);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __dp4a(a, wm[fy * KK + fx][j], acc[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] -= in_zp * wall[j];
+    } else {
+#pragma unroll
+      for (int fy = 0; fy < KK; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < KK; ++fx) {
+          const int iy = iy0 + fy, ix = ix0 + fx;
+          if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
+          const int a = *reinterpret_cast<const int*>(tin + (int64_t(iy) * g.IW + ix) * g.IC);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = __dp4a(a, wm[fy * KK + fx][j], acc[j]);
+            acc[j] -= in_zp * (wm[fy * KK + fx][j] << (24 - 8 * j) >> 24);
+          }
+        }
+    }
+    unsigned packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int32_t v = mul_by_quant_mult(acc[j] + bs[j], mult[j], shift[j]) + rq.out_zp;
+      v = max(rq.act_min, min(rq.act_max, v));
+      packed |= (unsigned(v) & 0xFFu) << (8 * j);
+    }
+    *reinterpret_cast<unsigned*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c) = packed;
+  }
+}
+
 // ------------------------------------------------------------------ ADD (residual / FPN merge)
 __device__ __forceinline__ int8_t add_one(int a, int b, const AddParams& p) {
   const int32_t xa = (a - p.zp_a) * (1 << 20);
@@ -286,6 +470,45 @@ __global__ void __launch_bounds__(256) resize_kernel(const int8_t* __restrict__ 
   }
 }
 
+// 16 channels per thread (one 16-byte access per corner); C % 16 == 0
+__global__ void __launch_bounds__(256) resize16_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
+                                                      int C, int8_t* __restrict__ out, int64_t out_ts, int OH, int OW,
+                                                      int hs, int ws, bool half_pixel) {
+  const int t = blockIdx.y;
+  const int c16n = C >> 4;
+  const int total = OH * OW * c16n;
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (i % c16n) * 16;
+    const int x = (i / c16n) % OW;
+    const int y = i / (c16n * OW);
+    int iy, y0, y1, ix, x0, x1;
+    resize_axis(y, hs, IH, half_pixel, &iy, &y0, &y1);
+    resize_axis(x, ws, IW, half_pixel, &ix, &x0, &x1);
+    // the four weights are < 2^20 and |pixel| <= 128, so the 4-term sum fits comfortably in int32
+    const int wy1 = iy - (1 << 10) * y0, wy0 = (1 << 10) - wy1;
+    const int wx1 = ix - (1 << 10) * x0, wx0 = (1 << 10) - wx1;
+    const int w00 = wy0 * wx0, w10 = wy1 * wx0, w01 = wy0 * wx1, w11 = wy1 * wx1;
+    const int4 p00 = *reinterpret_cast<const int4*>(tin + (int64_t(y0) * IW + x0) * C + c);
+    const int4 p10 = *reinterpret_cast<const int4*>(tin + (int64_t(y1) * IW + x0) * C + c);
+    const int4 p01 = *reinterpret_cast<const int4*>(tin + (int64_t(y0) * IW + x1) * C + c);
+    const int4 p11 = *reinterpret_cast<const int4*>(tin + (int64_t(y1) * IW + x1) * C + c);
+    const int8_t* a = reinterpret_cast<const int8_t*>(&p00);
+    const int8_t* b = reinterpret_cast<const int8_t*>(&p10);
+    const int8_t* d = reinterpret_cast<const int8_t*>(&p01);
+    const int8_t* e = reinterpret_cast<const int8_t*>(&p11);
+    int4 o;
+    int8_t* ob = reinterpret_cast<int8_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int o20 = int(a[j]) * w00 + int(b[j]) * w10 + int(d[j]) * w01 + int(e[j]) * w11;
+      const int rnd = o20 > 0 ? (1 << 19) : -(1 << 19);
+      ob[j] = int8_t((o20 + rnd) / (1 << 20));
+    }
+    *reinterpret_cast<int4*>(out + int64_t(t) * out_ts + (int64_t(y) * OW + x) * C + c) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const uint8_t* __restrict__ in, int64_t in_ts,
                                                   uint8_t* __restrict__ out, int64_t out_ts, int64_t bytes, bool vec) {
   const int t = blockIdx.y;
@@ -316,6 +539,19 @@ inline int grid_for(int64_t work_items, int threads, int tiles) {
 void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const int32_t* bias, const int32_t* wsum,
                         int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles,
                         cudaStream_t s) {
+  // preferred CUDA-core path: shared-memory weight slab, one thread per pixel x 16 channels
+  const int taps = g.KH * g.KW, icw = (g.IC + 3) / 4;
+  const size_t pix_smem = size_t(taps) * icw * kPixOct * 4 + size_t(taps) * kPixOct * 4;
+  const bool words_ok = g.IC == 3 || (g.IC % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (in_ts % 4) == 0);
+  if (words_ok && pix_smem <= 48 * 1024 && int64_t(tiles) * g.OH * g.OW < (int64_t(1) << 31)) {
+    const int total = tiles * g.OH * g.OW;
+    dim3 grid(unsigned((total + kPixThreads - 1) / kPixThreads), unsigned((g.OC + kPixOct - 1) / kPixOct));
+    if (g.IC == 3)
+      conv_pix_kernel<true><<<grid, kPixThreads, pix_smem, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+    else
+      conv_pix_kernel<false><<<grid, kPixThreads, pix_smem, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+    return;
+  }
   constexpr int OCT = 8;
   const int64_t pixels = int64_t(tiles) * g.OH * g.OW;
   dim3 grid(unsigned((pixels + 127) / 128), unsigned((g.OC + OCT - 1) / OCT));
@@ -332,6 +568,20 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
   const bool vec = (g.OC % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0) && (in_ts % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (out_ts % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(w) & 3) == 0);
+  if (vec && g.KH == 3 && g.KW == 3 && g.dil_h == 1 && g.dil_w == 1 && int64_t(tiles) * g.OH * g.OW < (int64_t(1) << 31)) {
+    const int cg = g.OC / 4;
+    const int bx = cg >= 32 ? 32 : cg;
+    const int by = 256 / bx;
+    const int total = tiles * g.OH * g.OW;
+    const int gx = (cg + bx - 1) / bx;
+    // enough CTAs for ~8 per SM, each walking a contiguous run of pixels
+    int pix_per_block = (total + (148 * 8 / gx + 1) - 1) / (148 * 8 / gx + 1);
+    pix_per_block = ((pix_per_block + by - 1) / by) * by;
+    if (pix_per_block < by) pix_per_block = by;
+    dim3 grid(gx, (total + pix_per_block - 1) / pix_per_block), block(bx, by);
+    depthwise_reg_kernel<3><<<grid, block, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles, pix_per_block);
+    return;
+  }
   if (vec) {
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / 4);
     depthwise_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
@@ -366,6 +616,11 @@ void launch_resize_bilinear(const int8_t* in, int64_t in_ts, int IH, int IW, int
   int hs = ((1 << 10) * IH + OH / 2) / OH, ws = ((1 << 10) * IW + OW / 2) / OW;
   if (align_corners && OH > 1) hs = ((1 << 10) * (IH - 1) + (OH - 1) / 2) / (OH - 1);
   if (align_corners && OW > 1) ws = ((1 << 10) * (IW - 1) + (OW - 1) / 2) / (OW - 1);
+  if (C % 16 == 0 && aligned16(in, in_ts) && aligned16(out, out_ts) && int64_t(OH) * OW * C < (int64_t(1) << 31)) {
+    dim3 grid16(grid_for(int64_t(OH) * OW * (C / 16), 256, tiles), tiles);
+    resize16_kernel<<<grid16, 256, 0, s>>>(in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
+    return;
+  }
   dim3 grid(grid_for(int64_t(OH) * OW * (C / 4), 256, tiles), tiles);
   resize_kernel<<<grid, 256, 0, s>>>(in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
 }
