@@ -1,0 +1,51 @@
+// Compares the product's fixed-point helpers (csrc/fixedpoint.cuh) with the oracle's literal restatement
+// (oracle/fixedpoint.h) on edge cases and random draws.  Built and run by tests/test_fixedpoint.py.
+#include <cstdint>
+#include <cstdio>
+#include <random>
+#include "../../oracle/fixedpoint.h"
+#include "../../tiny-object-detection_b200/csrc/fixedpoint.cuh"
+
+int main() {
+  std::mt19937_64 rng(42);
+  long long bad = 0, n = 0;
+  const int32_t edge[] = {0, 1, -1, 2, -2, 127, -128, 255, (1 << 20), -(1 << 20), (1 << 26) - 1, -(1 << 26), (1 << 30) - 1, -(1 << 30) + 1,
+                          1073741823, 1073741824 - 5, 123456789, -123456789};
+  const int32_t qs[] = {0, 1, 1 << 30, (1 << 30) + 1, 0x7FFFFFFF, 1518500250, 1073741824 + 12345, 2000000000};
+  auto check = [&](int32_t x, int32_t q, int sh) {
+    const int32_t a = oracle::MBQM(x, q, sh), b = tod::mul_by_quant_mult(x, q, sh);
+    ++n;
+    if (a != b) { if (bad < 5) std::printf("generic mismatch x=%d q=%d sh=%d: %d vs %d\n", x, q, sh, a, b); ++bad; }
+    const int64_t lim = int64_t(1) << 30;
+    const int64_t xs = sh > 0 ? (int64_t(x) << sh) : x;
+    if (q >= 0 && xs < lim && xs > -lim) {
+      const int32_t c = tod::mul_by_quant_mult_fast(x, q, sh);
+      if (a != c) { if (bad < 5) std::printf("fast mismatch x=%d q=%d sh=%d: %d vs %d\n", x, q, sh, a, c); ++bad; }
+    }
+  };
+  for (int32_t x : edge)
+    for (int32_t q : qs)
+      for (int sh = -31; sh <= 4; ++sh) check(x, q, sh);
+  // ties of the rounding shift: products landing exactly on .5
+  for (int sh = -12; sh <= 0; ++sh)
+    for (int k = -4000; k <= 4000; ++k) check(k, 1 << 30, sh), check(2 * k + 1, 1 << 30, sh), check(k, (1 << 30) + (1 << 29), sh);
+  for (long long i = 0; i < 10000000; ++i) {
+    const int32_t x = int32_t(rng() % (1u << 27)) - (1 << 26);
+    const int32_t q = int32_t((1u << 30) + rng() % (1u << 30));
+    const int sh = -int(rng() % 20) + (rng() % 50 == 0 ? 2 : 0);
+    check(x, q, sh);
+  }
+  for (long long i = 0; i < 2000000; ++i) {  // the generic form over the full int32 range, either sign of q
+    check(int32_t(rng()), int32_t(rng()), -int(rng() % 31));
+  }
+  int32_t q; int sh, q2, sh2;
+  for (int i = 0; i < 200000; ++i) {
+    const double m = std::ldexp(0.5 + (rng() % 1000000) / 2000000.0, -int(rng() % 40) + 3);
+    oracle::QuantizeMultiplier(m, &q, &sh);
+    tod::quantize_multiplier(m, &q2, &sh2);
+    ++n;
+    if (q != q2 || sh != sh2) ++bad;
+  }
+  std::printf("checked %lld cases, %lld mismatches\n", n, bad);
+  return bad ? 1 : 0;
+}

@@ -60,6 +60,7 @@ struct TcParams {
   uint32_t sbo;                // 8 rows * BK bytes
   uint32_t layout;             // UMMA swizzle code
   int vec_store;               // OC % 16 == 0 and 16B-aligned rows
+  int sc, pitch;               // epilogue staging: columns per pass, bytes per staged row
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -153,7 +154,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_b + size_t(p.stages) * p.b_stage);
+  uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;                      // [128][pitch] requantised bytes
+  long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + size_t(kBM) * p.pitch);  // [128] global offset of each row
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_rowoff + kBM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = p.flat ? tiles * p.HW : p.Wd;
@@ -247,8 +250,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers -> requantise -> shared staging tile -> coalesced 16-byte global stores.
     const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
     const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
+    const int et = threadIdx.x - 128;        // 0..127 among the epilogue threads
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int as = it & 1;
@@ -285,40 +290,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         cls = ymask * (1 << p.KW) + xmask;
       }
-      const int32_t* be = p.bias_eff + size_t(cls) * p.OCp + n_tile * p.BN;
-      const int32_t* mu = p.mult + n_tile * p.BN;
-      const int32_t* sh = p.shift + n_tile * p.BN;
-      int8_t* orow = p.out + (p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC;
+      const int ocb = n_tile * p.BN;
+      const int4* be = reinterpret_cast<const int4*>(p.bias_eff + size_t(cls) * p.OCp + ocb);
+      const int4* mu = reinterpret_cast<const int4*>(p.mult + ocb);
+      const int4* sh = reinterpret_cast<const int4*>(p.shift + ocb);
+      s_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
+      const int ncols_tile = min(p.BN, p.OC - ocb);
 
       mbar_wait(&ctl->acc_full[as], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_wait_ld();
-        const int ocb = n_tile * p.BN + c0;
-        if (valid && ocb < p.OC) {
-          uint32_t packed[4] = {0, 0, 0, 0};
+      for (int pass0 = 0; pass0 < p.BN; pass0 += p.sc) {
+        const int pass_cols = min(p.sc, p.BN - pass0);
+        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + pass0 + c0, v);
+          tmem_wait_ld();
+          uint32_t packed[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int32_t acc = int32_t(v[j]) + __ldg(be + c0 + j);
-            int32_t q = mul_by_quant_mult(acc, __ldg(mu + c0 + j), __ldg(sh + c0 + j)) + p.out_zp;
-            q = max(p.act_min, min(p.act_max, q));
-            packed[j >> 2] |= (uint32_t(q) & 0xFFu) << ((j & 3) * 8);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int4 b4 = __ldg(be + ((pass0 + c0) >> 2) + q4);
+            const int4 m4 = __ldg(mu + ((pass0 + c0) >> 2) + q4);
+            const int4 s4 = __ldg(sh + ((pass0 + c0) >> 2) + q4);
+            int q0 = mul_by_quant_mult_fast(int32_t(v[4 * q4 + 0]) + b4.x, m4.x, s4.x) + p.out_zp;
+            int q1 = mul_by_quant_mult_fast(int32_t(v[4 * q4 + 1]) + b4.y, m4.y, s4.y) + p.out_zp;
+            int q2 = mul_by_quant_mult_fast(int32_t(v[4 * q4 + 2]) + b4.z, m4.z, s4.z) + p.out_zp;
+            int q3 = mul_by_quant_mult_fast(int32_t(v[4 * q4 + 3]) + b4.w, m4.w, s4.w) + p.out_zp;
+            q0 = max(p.act_min, min(p.act_max, q0));
+            q1 = max(p.act_min, min(p.act_max, q1));
+            q2 = max(p.act_min, min(p.act_max, q2));
+            q3 = max(p.act_min, min(p.act_max, q3));
+            packed[q4] = (uint32_t(q0) & 0xFFu) | ((uint32_t(q1) & 0xFFu) << 8) | ((uint32_t(q2) & 0xFFu) << 16) | (uint32_t(q3) << 24);
           }
-          if (p.vec_store && ocb + 16 <= p.OC) {
-            *reinterpret_cast<uint4*>(orow + ocb) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *reinterpret_cast<uint4*>(stage_buf + size_t(r) * p.pitch + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (pass0 + p.sc >= p.BN) {  // accumulator fully read: hand the TMEM stage back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int ncols = min(pass_cols, ncols_tile - pass0);  // real output channels in this pass (<= 0: padding only)
+        if (ncols > 0) {
+          if (p.vec_store) {
+            const int cpr = ncols >> 4;
+            for (int idx = et; idx < kBM * cpr; idx += 128) {
+              const int rr = idx / cpr, ch = idx - rr * cpr;
+              const long long off = s_rowoff[rr];
+              if (off >= 0)
+                *reinterpret_cast<uint4*>(p.out + off + ocb + pass0 + ch * 16) = *reinterpret_cast<const uint4*>(stage_buf + size_t(rr) * p.pitch + ch * 16);
+            }
           } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ocb + j < p.OC) orow[ocb + j] = int8_t((packed[j >> 2] >> ((j & 3) * 8)) & 0xFFu);
+            for (int idx = et; idx < kBM * ncols; idx += 128) {
+              const int rr = idx / ncols, bb = idx - rr * ncols;
+              const long long off = s_rowoff[rr];
+              if (off >= 0) p.out[off + ocb + pass0 + bb] = int8_t(stage_buf[size_t(rr) * p.pitch + bb]);
+            }
           }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
     }
   }
 
@@ -474,10 +505,15 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.a_stage = uint32_t((kBM * p.BK + 1023) / 1024 * 1024);
   p.b_stage = uint32_t((p.BN * p.BK + 1023) / 1024 * 1024);
   p.tx_bytes = uint32_t(p.rows * p.BK + p.BN * p.BK);
-  const size_t budget = 200 * 1024;
+  p.sc = std::min(p.BN, 128);
+  int pitch16 = p.sc / 16 + 1;
+  if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
+  p.pitch = pitch16 * 16;
+  const size_t fixed = size_t(kBM) * p.pitch + size_t(kBM) * 8 + sizeof(SmemCtl) + 1024;
+  const size_t budget = 227 * 1024 - fixed;
   p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
-  c->smem_bytes = size_t(p.stages) * (p.a_stage + p.b_stage) + sizeof(SmemCtl) + 1024;
+  c->smem_bytes = size_t(p.stages) * (p.a_stage + p.b_stage) + fixed;
   // instruction descriptor: D = s32, A = B = s8, both K-major, N, M = 128
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
   p.out_zp = a.rq.out_zp;

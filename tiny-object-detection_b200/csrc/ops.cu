@@ -267,71 +267,72 @@ __global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __r
 // dp4a isolates one channel), their bias and requantisation constants in registers and walks over output pixels;
 // consecutive threads cover consecutive channels, so every global access of a warp is one contiguous segment.
 template <int KK>
-__global__ void __launch_bounds__(256) depthwise_reg_kernel(const int8_t* __restrict__ in, int64_t in_ts,
-                                                           const int8_t* __restrict__ w,
-                                                           const int32_t* __restrict__ bias, int32_t in_zp, ConvGeom g,
-                                                           Requant rq, int8_t* __restrict__ out, int64_t out_ts,
-                                                           int tiles, int pix_per_block) {
+__global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                              const int8_t* __restrict__ w,
+                                                              const int32_t* __restrict__ bias, int32_t in_zp, ConvGeom g,
+                                                              Requant rq, int8_t* __restrict__ out, int64_t out_ts,
+                                                              int tiles, int pix_per_block) {
   const int cgi = blockIdx.x * blockDim.x + threadIdx.x;  // channel group
   if (cgi * 4 >= g.OC) return;
   const int c = cgi * 4;
-  int wm[KK * KK][4];
+  int wv[KK * KK];
   int wall[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int tp = 0; tp < KK * KK; ++tp) {
-    const int wv = *reinterpret_cast<const int*>(w + int64_t(tp) * g.OC + c);
+    wv[tp] = *reinterpret_cast<const int*>(w + int64_t(tp) * g.OC + c);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      wm[tp][j] = wv & (0xFF << (8 * j));
-      wall[j] += int(int8_t((wv >> (8 * j)) & 0xFF));
-    }
+    for (int j = 0; j < 4; ++j) wall[j] += (wv[tp] << (24 - 8 * j)) >> 24;
   }
   int mult[4], shift[4], bs[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     mult[j] = rq.mult[c + j];
     shift[j] = rq.shift[c + j];
-    bs[j] = bias ? bias[c + j] : 0;
+    bs[j] = (bias ? bias[c + j] : 0) - in_zp * wall[j];  // interior pixels: every tap is inside
   }
   const int total = tiles * g.OH * g.OW;
   const int p_end = min(total, (blockIdx.y + 1) * pix_per_block);
+#pragma unroll 2
   for (int pix = blockIdx.y * pix_per_block + threadIdx.y; pix < p_end; pix += blockDim.y) {
     const int ox = pix % g.OW;
     const int oy = (pix / g.OW) % g.OH;
     const int t = pix / (g.OW * g.OH);
     const int8_t* tin = in + int64_t(t) * in_ts + c;
     const int iy0 = oy * g.stride_h - g.pad_top, ix0 = ox * g.stride_w - g.pad_left;
-    int acc[4] = {0, 0, 0, 0};
+    int acc[4];
     if (iy0 >= 0 && ix0 >= 0 && iy0 + KK <= g.IH && ix0 + KK <= g.IW) {
+      int a[KK * KK];
 #pragma unroll
       for (int fy = 0; fy < KK; ++fy)
 #pragma unroll
-        for (int fx = 0; fx < KK; ++fx) {
-          const int a = *reinterpret_cast<const int*>(tin + (int64_t(iy0 + fy) * g.IW + ix0 + fx) * g.IC);
+        for (int fx = 0; fx < KK; ++fx) a[fy * KK + fx] = *reinterpret_cast<const int*>(tin + (int64_t(iy0 + fy) * g.IW + ix0 + fx) * g.IC);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = __dp4a(a, wm[fy * KK + fx][j], acc[j]);
-        }
+      for (int j = 0; j < 4; ++j) acc[j] = bs[j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] -= in_zp * wall[j];
+      for (int tp = 0; tp < KK * KK; ++tp)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(a[tp] & (0xFF << (8 * j)), wv[tp], acc[j]);
     } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = bs[j] + in_zp * wall[j];
 #pragma unroll
       for (int fy = 0; fy < KK; ++fy)
 #pragma unroll
         for (int fx = 0; fx < KK; ++fx) {
           const int iy = iy0 + fy, ix = ix0 + fx;
           if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
-          const int a = *reinterpret_cast<const int*>(tin + (int64_t(iy) * g.IW + ix) * g.IC);
+          const int av = *reinterpret_cast<const int*>(tin + (int64_t(iy) * g.IW + ix) * g.IC);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc[j] = __dp4a(a, wm[fy * KK + fx][j], acc[j]);
-            acc[j] -= in_zp * (wm[fy * KK + fx][j] << (24 - 8 * j) >> 24);
+            acc[j] = __dp4a(av & (0xFF << (8 * j)), wv[fy * KK + fx], acc[j]);
+            acc[j] -= in_zp * ((wv[fy * KK + fx] << (24 - 8 * j)) >> 24);
           }
         }
     }
     unsigned packed = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int32_t v = mul_by_quant_mult(acc[j] + bs[j], mult[j], shift[j]) + rq.out_zp;
+      int32_t v = mul_by_quant_mult(acc[j], mult[j], shift[j]) + rq.out_zp;
       v = max(rq.act_min, min(rq.act_max, v));
       packed |= (unsigned(v) & 0xFFu) << (8 * j);
     }
