@@ -11,7 +11,7 @@
 //                           instruction) accumulating s32 in TMEM; tcgen05.commit releases smem stages / publishes
 //                           the accumulator
 //   warp 2   TMEM allocator 512 columns = two accumulator stages, so the epilogue of tile i overlaps the MMAs of i+1
-//   warps 4-7 epilogue      tcgen05.ld 32 lanes x 16 columns -> registers; + bias with the input-zero-point
+//   warps 4-11 epilogue     tcgen05.ld 32 lanes x 16 columns -> registers; + bias with the input-zero-point
 //                           correction of the taps that were inside the image; TFLite fixed-point requantisation
 //                           (SRDHM + rounding shift, bit-exact); activation clamp; int8 store
 //
@@ -34,7 +34,8 @@ namespace tod {
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 384;  // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -173,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], 4);
+      mbar_init(&ctl->acc_empty[s], kEpiThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -251,9 +252,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // TMEM -> registers -> requantise -> shared staging tile -> coalesced 16-byte global stores.
+    // Two warps share each TMEM lane quarter and split the columns (even / odd 16-column chunks).
     const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;        // which 16-column chunks of a pass this warp converts
     const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
-    const int et = threadIdx.x - 128;        // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 128;        // 0..255 among the epilogue threads
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int as = it & 1;
@@ -302,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
       for (int pass0 = 0; pass0 < p.BN; pass0 += p.sc) {
         const int pass_cols = min(p.sc, p.BN - pass0);
-        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
+        for (int c0 = half * 16; c0 < pass_cols; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + pass0 + c0, v);
           tmem_wait_ld();
@@ -329,26 +332,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int ncols = min(pass_cols, ncols_tile - pass0);  // real output channels in this pass (<= 0: padding only)
         if (ncols > 0) {
           if (p.vec_store) {
             const int cpr = ncols >> 4;
-            for (int idx = et; idx < kBM * cpr; idx += 128) {
+            for (int idx = et; idx < kBM * cpr; idx += kEpiThreads) {
               const int rr = idx / cpr, ch = idx - rr * cpr;
               const long long off = s_rowoff[rr];
               if (off >= 0)
                 *reinterpret_cast<uint4*>(p.out + off + ocb + pass0 + ch * 16) = *reinterpret_cast<const uint4*>(stage_buf + size_t(rr) * p.pitch + ch * 16);
             }
           } else {
-            for (int idx = et; idx < kBM * ncols; idx += 128) {
+            for (int idx = et; idx < kBM * ncols; idx += kEpiThreads) {
               const int rr = idx / ncols, bb = idx - rr * ncols;
               const long long off = s_rowoff[rr];
               if (off >= 0) p.out[off + ocb + pass0 + bb] = int8_t(stage_buf[size_t(rr) * p.pitch + bb]);
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }

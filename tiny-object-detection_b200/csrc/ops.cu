@@ -12,7 +12,7 @@ namespace tod {
 namespace {
 
 __device__ __forceinline__ int8_t requant_store(int32_t acc, int32_t mult, int32_t shift, const Requant& rq) {
-  int32_t v = mul_by_quant_mult(acc, mult, shift) + rq.out_zp;
+  int32_t v = mul_by_quant_mult_fast(acc, mult, shift) + rq.out_zp;  // q >= 0, |acc| < 2^30
   v = max(rq.act_min, min(rq.act_max, v));
   return int8_t(v);
 }
@@ -275,13 +275,16 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
   const int cgi = blockIdx.x * blockDim.x + threadIdx.x;  // channel group
   if (cgi * 4 >= g.OC) return;
   const int c = cgi * 4;
-  int wv[KK * KK];
+  int wm[KK * KK][4];  // tap weights, masked to one byte lane each: dp4a(a, wm[tap][j]) == a_j * w_j
   int wall[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int tp = 0; tp < KK * KK; ++tp) {
-    wv[tp] = *reinterpret_cast<const int*>(w + int64_t(tp) * g.OC + c);
+    const int wv = *reinterpret_cast<const int*>(w + int64_t(tp) * g.OC + c);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wall[j] += (wv[tp] << (24 - 8 * j)) >> 24;
+    for (int j = 0; j < 4; ++j) {
+      wm[tp][j] = wv & (0xFF << (8 * j));
+      wall[j] += (wv << (24 - 8 * j)) >> 24;
+    }
   }
   int mult[4], shift[4], bs[4];
 #pragma unroll
@@ -292,26 +295,27 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
   }
   const int total = tiles * g.OH * g.OW;
   const int p_end = min(total, (blockIdx.y + 1) * pix_per_block);
-#pragma unroll 2
-  for (int pix = blockIdx.y * pix_per_block + threadIdx.y; pix < p_end; pix += blockDim.y) {
-    const int ox = pix % g.OW;
-    const int oy = (pix / g.OW) % g.OH;
-    const int t = pix / (g.OW * g.OH);
+  int pix = blockIdx.y * pix_per_block + threadIdx.y;
+  int ox = pix % g.OW;
+  int oy = (pix / g.OW) % g.OH;
+  int t = pix / (g.OW * g.OH);
+  for (; pix < p_end; pix += blockDim.y) {
     const int8_t* tin = in + int64_t(t) * in_ts + c;
     const int iy0 = oy * g.stride_h - g.pad_top, ix0 = ox * g.stride_w - g.pad_left;
     int acc[4];
     if (iy0 >= 0 && ix0 >= 0 && iy0 + KK <= g.IH && ix0 + KK <= g.IW) {
       int a[KK * KK];
+      const int8_t* p0 = tin + (int64_t(iy0) * g.IW + ix0) * g.IC;
 #pragma unroll
       for (int fy = 0; fy < KK; ++fy)
 #pragma unroll
-        for (int fx = 0; fx < KK; ++fx) a[fy * KK + fx] = *reinterpret_cast<const int*>(tin + (int64_t(iy0 + fy) * g.IW + ix0 + fx) * g.IC);
+        for (int fx = 0; fx < KK; ++fx) a[fy * KK + fx] = *reinterpret_cast<const int*>(p0 + (fy * g.IW + fx) * g.IC);
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = bs[j];
 #pragma unroll
       for (int tp = 0; tp < KK * KK; ++tp)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(a[tp] & (0xFF << (8 * j)), wv[tp], acc[j]);
+        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(a[tp], wm[tp][j], acc[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = bs[j] + in_zp * wall[j];
@@ -324,29 +328,36 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
           const int av = *reinterpret_cast<const int*>(tin + (int64_t(iy) * g.IW + ix) * g.IC);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc[j] = __dp4a(av & (0xFF << (8 * j)), wv[fy * KK + fx], acc[j]);
-            acc[j] -= in_zp * ((wv[fy * KK + fx] << (24 - 8 * j)) >> 24);
+            acc[j] = __dp4a(av, wm[fy * KK + fx][j], acc[j]);
+            acc[j] -= in_zp * ((wm[fy * KK + fx][j] << (24 - 8 * j)) >> 24);
           }
         }
     }
     unsigned packed = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int32_t v = mul_by_quant_mult(acc[j], mult[j], shift[j]) + rq.out_zp;
+      int32_t v = mul_by_quant_mult_fast(acc[j], mult[j], shift[j]) + rq.out_zp;
       v = max(rq.act_min, min(rq.act_max, v));
       packed |= (unsigned(v) & 0xFFu) << (8 * j);
     }
     *reinterpret_cast<unsigned*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c) = packed;
+    // next pixel of this thread (pix += blockDim.y) without divisions
+    ox += blockDim.y;
+    while (ox >= g.OW) {
+      ox -= g.OW;
+      if (++oy == g.OH) {
+        oy = 0;
+        ++t;
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------ ADD (residual / FPN merge)
-__device__ __forceinline__ int8_t add_one(int a, int b, const AddParams& p) {
-  const int32_t xa = (a - p.zp_a) * (1 << 20);
-  const int32_t xb = (b - p.zp_b) * (1 << 20);
-  const int32_t ya = mul_by_quant_mult(xa, p.mult_a, p.shift_a);
-  const int32_t yb = mul_by_quant_mult(xb, p.mult_b, p.shift_b);
-  int32_t r = mul_by_quant_mult(ya + yb, p.mult_out, p.shift_out) + p.zp_out;
+// The two input rescales depend on one byte each, so they are tabulated per CTA (256 entries each, built with
+// the literal arithmetic); the output rescale uses the fast exact form (|ya + yb| < 2^29).
+__device__ __forceinline__ int8_t add_one(int a, int b, const int* s_a, const int* s_b, const AddParams& p) {
+  int32_t r = mul_by_quant_mult_fast(s_a[a & 0xFF] + s_b[b & 0xFF], p.mult_out, p.shift_out) + p.zp_out;
   r = max(p.act_min, min(p.act_max, r));
   return int8_t(r);
 }
@@ -354,6 +365,13 @@ __device__ __forceinline__ int8_t add_one(int a, int b, const AddParams& p) {
 __global__ void __launch_bounds__(256) add_kernel(const int8_t* __restrict__ a, int64_t a_ts,
                                                  const int8_t* __restrict__ b, int64_t b_ts, int8_t* __restrict__ out,
                                                  int64_t out_ts, int64_t elems, int tiles, AddParams p, bool vec) {
+  __shared__ int s_a[256], s_b[256];
+  {
+    const int v = int(int8_t(threadIdx.x));  // table index = the byte pattern
+    s_a[threadIdx.x] = mul_by_quant_mult((v - p.zp_a) * (1 << 20), p.mult_a, p.shift_a);
+    s_b[threadIdx.x] = mul_by_quant_mult((v - p.zp_b) * (1 << 20), p.mult_b, p.shift_b);
+  }
+  __syncthreads();
   const int t = blockIdx.y;
   const int8_t* pa = a + int64_t(t) * a_ts;
   const int8_t* pb = b + int64_t(t) * b_ts;
@@ -369,13 +387,13 @@ __global__ void __launch_bounds__(256) add_kernel(const int8_t* __restrict__ a, 
       const int8_t* bb = reinterpret_cast<const int8_t*>(&vb);
       int8_t* bo = reinterpret_cast<int8_t*>(&vo);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bo[j] = add_one(ba[j], bb[j], p);
+      for (int j = 0; j < 16; ++j) bo[j] = add_one(ba[j], bb[j], s_a, s_b, p);
       reinterpret_cast<int4*>(po)[i] = vo;
     }
     for (int64_t i = (n16 << 4) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride)
-      po[i] = add_one(pa[i], pb[i], p);
+      po[i] = add_one(pa[i], pb[i], s_a, s_b, p);
   } else {
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) po[i] = add_one(pa[i], pb[i], p);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) po[i] = add_one(pa[i], pb[i], s_a, s_b, p);
   }
 }
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <vector>
@@ -52,6 +53,7 @@ struct Step {
   int64_t copy_dst_off = 0, copy_bytes = 0;
   int64_t macs = 0;
   ConvTc* tc = nullptr;
+  std::vector<int> deps;   // indices of the steps whose output this step reads (RESHAPE / CONCAT are transparent)
 };
 
 void conv_out_pad(int padding, int in, int k, int stride, int dil, int* out, int* pad) {
@@ -164,6 +166,12 @@ struct tod_yolact {
   float* d_tmp = nullptr;
   uint32_t* d_frames = nullptr;
   uint8_t* d_tiles_rgb = nullptr;
+  // independent branches of the graph (FPN levels, the five head levels, protonet) are captured on separate
+  // streams so the CUDA graph runs them concurrently
+  static constexpr int kLanes = 6;
+  cudaStream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> step_events;
+  cudaEvent_t fork_event = nullptr;
   // CUDA graphs, keyed by (tiles << 2 | dets << 1 | masks)
   std::map<int, cudaGraphExec_t> graphs;
   int last_tiles = 0;
@@ -481,6 +489,52 @@ int plan(tod_yolact* y, ConstArena* arena) {
     y->macs_per_tile += s.macs;
     if (s.in0 >= 0 && !y->place[s.in0].base) return fail(TOD_ERR_MODEL, "operator %d reads tensor %d which nothing produces", s.op, s.in0);
   }
+  // ---- data dependencies between steps
+  std::vector<std::vector<int>> op_steps(G.ops.size());  // steps generated for an op (its kernel, or a concat's copies)
+  for (size_t i = 0; i < y->steps.size(); ++i) op_steps[y->steps[i].op].push_back(int(i));
+  std::vector<std::vector<int>> memo(nt);
+  std::vector<char> done(nt, 0);
+  std::function<const std::vector<int>&(int)> producers = [&](int t) -> const std::vector<int>& {
+    if (done[t]) return memo[t];
+    done[t] = 1;
+    std::vector<int> out;
+    const int po = producer[t];
+    if (po >= 0) {
+      const GOp& op = G.ops[po];
+      if (op.code == kReshape || (op.code == kPad && pad_folded[po])) {
+        out = producers(op.inputs[0]);
+      } else if (op.code == kConcat) {
+        for (int in : op.inputs) {
+          const std::vector<int>& p = producers(in);
+          out.insert(out.end(), p.begin(), p.end());
+        }
+        out.insert(out.end(), op_steps[po].begin(), op_steps[po].end());
+      } else {
+        out = op_steps[po];
+      }
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    memo[t] = out;
+    return memo[t];
+  };
+  for (size_t i = 0; i < y->steps.size(); ++i) {
+    Step& st = y->steps[i];
+    std::vector<int> d;
+    for (int t : {st.in0, st.in1})
+      if (t >= 0) {
+        const std::vector<int>& p = producers(t);
+        d.insert(d.end(), p.begin(), p.end());
+      }
+    if (st.kind == kStepCopy) {
+      // a residual concat copy also has to follow whatever else writes the destination's other regions? No: regions
+      // are disjoint; it only reads its source.
+    }
+    std::sort(d.begin(), d.end());
+    d.erase(std::unique(d.begin(), d.end()), d.end());
+    d.erase(std::remove_if(d.begin(), d.end(), [&](int v) { return v >= int(i); }), d.end());
+    st.deps = d;
+  }
   return TOD_OK;
 }
 
@@ -715,6 +769,42 @@ int enqueue_all(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
   return TOD_OK;
 }
 
+// Same work as enqueue_all, spread over the handle's lane streams by data dependency.  Only used while capturing:
+// the resulting CUDA graph has one node per kernel and an edge per dependency, so independent branches overlap.
+int enqueue_all_parallel(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t origin) {
+  const int L = tod_yolact::kLanes;
+  std::vector<int> lane_of(y->steps.size(), 0), tail(L, -1);
+  std::vector<char> forked(L, 0);
+  TOD_CUDA(cudaEventRecord(y->fork_event, origin));
+  for (size_t i = 0; i < y->steps.size(); ++i) {
+    const Step& st = y->steps[i];
+    int lane = -1;
+    for (auto it = st.deps.rbegin(); it != st.deps.rend() && lane < 0; ++it)
+      if (tail[lane_of[*it]] == *it) lane = lane_of[*it];  // continue the chain of a producer that is still a lane tail
+    if (lane < 0) {
+      lane = 0;
+      for (int l = 1; l < L; ++l)
+        if (tail[l] < tail[lane]) lane = l;  // least recently used lane
+    }
+    cudaStream_t ls = y->lanes[lane];
+    if (!forked[lane]) {
+      TOD_CUDA(cudaStreamWaitEvent(ls, y->fork_event, 0));
+      forked[lane] = 1;
+    }
+    for (int d : st.deps)
+      if (lane_of[d] != lane) TOD_CUDA(cudaStreamWaitEvent(ls, y->step_events[d], 0));
+    TOD_TRY(run_step(y, st, n, ls));
+    TOD_CUDA(cudaEventRecord(y->step_events[i], ls));
+    lane_of[i] = lane;
+    tail[lane] = int(i);
+  }
+  for (int l = 0; l < L; ++l)
+    if (forked[l] && tail[l] >= 0) TOD_CUDA(cudaStreamWaitEvent(origin, y->step_events[tail[l]], 0));
+  TOD_TRY(enqueue_post(y, n, dets, masks, origin));
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
 int run_pipeline(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
   if (dets && !y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
   if (dets && !y->have_priors) return fail(TOD_ERR_INVALID_ARG, "no priors for a %d-prior head: call tod_yolact_set_priors first", y->dcfg.P);
@@ -725,7 +815,7 @@ int run_pipeline(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
   if (it == y->graphs.end()) {
     cudaGraph_t g = nullptr;
     TOD_CUDA(cudaStreamBeginCapture(y->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_all(y, n, dets, masks, y->stream);
+    const int rc = enqueue_all_parallel(y, n, dets, masks, y->stream);
     const cudaError_t ce = cudaStreamEndCapture(y->stream, &g);
     if (rc < 0) {
       if (g) cudaGraphDestroy(g);
@@ -849,6 +939,11 @@ void tod_yolact_destroy(tod_yolact* y) {
   cudaSetDevice(y->device);
   if (y->stream) cudaStreamSynchronize(y->stream);
   for (auto& kv : y->graphs) cudaGraphExecDestroy(kv.second);
+  for (cudaStream_t l : y->lanes)
+    if (l) cudaStreamDestroy(l);
+  for (cudaEvent_t e : y->step_events)
+    if (e) cudaEventDestroy(e);
+  if (y->fork_event) cudaEventDestroy(y->fork_event);
   for (Step& s : y->steps)
     if (s.tc) conv_tc_destroy(s.tc);
   for (void* p : y->det_allocs) cudaFree(p);
@@ -905,6 +1000,12 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
   rc = setup_detection(raw);
   if (rc < 0) return bail(rc);
   raw->launches_per_call = int(raw->steps.size());
+  for (cudaStream_t& l : raw->lanes)
+    if ((ce = cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
+  raw->step_events.assign(raw->steps.size(), nullptr);
+  for (cudaEvent_t& e : raw->step_events)
+    if ((ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
+  if ((ce = cudaEventCreateWithFlags(&raw->fork_event, cudaEventDisableTiming)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
   *out = raw;
   return TOD_OK;
 }
