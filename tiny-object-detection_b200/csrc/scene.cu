@@ -170,6 +170,126 @@ __global__ void __launch_bounds__(32) stamp_kernel(const uint16_t* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ stamp, packed (terrain bump size 10)
+// Same ownership scheme (one warp = 32 columns, lane = column), tuned for throughput:
+//  * two map rows share one 32-bit shared-memory word (lo = even row, hi = odd row), so a 20-row stamp is
+//    11 word-wide read / vmaxu2 / write triples instead of 20 half-word ones;
+//  * the stamp column for (source row y, column offset ox) comes pre-packed from the host in both row
+//    alignments (12 words each, 3 x LDG.128, warp-uniform); a lane picks the alignment of its landing row;
+//  * the 11 triples are fully unrolled and independent, which is what hides the shared-memory latency with
+//    only ~6 resident warps per SM (one strip = 36 KB of shared memory);
+//  * lanes without a terrain source pixel write zeros into a scratch word row instead of branching.
+// Robot pixels (40x40 stamps) are rare and take the generic half-word loop on the same tile.
+constexpr int kPackWords = 12;
+
+__device__ __forceinline__ unsigned vmaxu2(unsigned a, unsigned b) { return __vmaxu2(a, b); }
+
+__global__ void __launch_bounds__(32) stamp_packed_kernel(const uint16_t* __restrict__ land,
+                                                         const unsigned int* __restrict__ row_robot,
+                                                         const uint4* __restrict__ lut_pack,      // [H][20][2 alignments][3] uint4
+                                                         const unsigned int* __restrict__ row_mask,  // [H] bit ox: column non-empty
+                                                         const uint16_t* __restrict__ lut_b, const uint8_t* __restrict__ span_b,
+                                                         SceneDev P, uint32_t* __restrict__ map) {
+  extern __shared__ uint32_t wtile[];  // [(rows/2) + kPackWords scratch][32] words, then one staged LUT row
+  constexpr int S = 10, D = 20, kRowVec = D * 6;  // uint4 per staged LUT row
+  const int lane = threadIdx.x;
+  const int f = blockIdx.y;
+  const int x0 = blockIdx.x * kStripW;
+  const int lx = x0 + lane;
+  const int rows = P.H + 2 * P.pad_rows;
+  const int pair_rows = (rows + 1) / 2;
+  const int scratch = pair_rows;                   // first scratch word row
+  uint4* s_lut = reinterpret_cast<uint4*>(wtile + (pair_rows + kPackWords) * kStripW);
+  for (int i = lane; i < (pair_rows + kPackWords) * kStripW; i += 32) wtile[i] = 0u;
+  const uint16_t* L = land + int64_t(f) * P.W * P.H;
+  const unsigned int* RR = row_robot + int64_t(f) * P.H;
+  uint16_t* htile = reinterpret_cast<uint16_t*>(wtile);
+  // source columns needed by this strip: x0 - 9 .. x0 + 41, held as two registers per lane and read by shuffle
+  const int xa = x0 - (S - 1) + lane, xb = xa + 32;
+  auto ld_land = [&](int y, int x) -> unsigned {
+    return (x >= 0 && x < P.W) ? unsigned(L[int64_t(y) * P.W + x]) : unsigned(kKindNone << 14);
+  };
+  unsigned r0v = ld_land(0, xa), r1v = ld_land(0, xb);
+  for (int i = lane; i < kRowVec; i += 32) s_lut[i] = __ldg(lut_pack + i);
+  __syncwarp();
+  for (int y = 0; y < P.H; ++y) {
+    // prefetch the next row (land + packed stamps) while this row is stamped
+    const int yn = min(y + 1, P.H - 1);
+    const unsigned n0v = ld_land(yn, xa), n1v = ld_land(yn, xb);
+    uint4 nl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k;
+      nl[k] = i < kRowVec ? __ldg(lut_pack + int64_t(yn) * kRowVec + i) : make_uint4(0, 0, 0, 0);
+    }
+    const unsigned mask = __ldg(row_mask + y);
+#pragma unroll 2
+    for (int ox = 0; ox < D; ++ox) {
+      if (!((mask >> ox) & 1u)) continue;  // all-zero stamp column (warp-uniform)
+      const int j = lane + (D - 1) - ox;    // index into the 64 staged source pixels: x = lx + S - ox
+      const unsigned va = __shfl_sync(0xffffffffu, r0v, j & 31), vb = __shfl_sync(0xffffffffu, r1v, j & 31);
+      const unsigned v = j < 32 ? va : vb;
+      const bool active = (v >> 14) == kKindTerrain && lx < P.W;
+      if (!__any_sync(0xffffffffu, active)) continue;
+      const int r0 = int(v & 0x3FFF) - P.py_bias - S + P.pad_rows;  // first tile row of the stamp
+      const int base = active ? (r0 >> 1) : scratch;
+      const bool odd = active && (r0 & 1);
+      const uint4* lp = s_lut + ox * 6 + (odd ? 3 : 0);
+      const uint4 a0 = lp[0], a1 = lp[1], a2 = lp[2];
+      const unsigned am = active ? 0xFFFFFFFFu : 0u;
+      const unsigned w[11] = {a0.x & am, a0.y & am, a0.z & am, a0.w & am, a1.x & am, a1.y & am,
+                              a1.z & am, a1.w & am, a2.x & am, a2.y & am, a2.z & am};
+      uint32_t* q = wtile + base * kStripW + lane;
+      unsigned cur[11];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) cur[k] = q[k * kStripW];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) q[k * kStripW] = vmaxu2(cur[k], w[k]);
+    }
+    if (RR[y]) {
+      const uint16_t* Lr = L + int64_t(y) * P.W;
+      const int d_b = 2 * P.s_b;
+      for (int ox = 0; ox < d_b; ++ox) {
+        const int x = lx + P.s_b - ox;
+        unsigned v = kKindNone << 14;
+        if (x >= 0 && x < P.W) v = Lr[x];
+        const bool active = (v >> 14) == kKindRobot && lx < P.W;
+        if (!__any_sync(0xffffffffu, active)) continue;
+        const int r0 = int(v & 0x3FFF) - P.py_bias - P.s_b + P.pad_rows;
+        const int lo = span_b[2 * ox], hi = span_b[2 * ox + 1];
+        for (int oy = lo; oy < hi; ++oy) {
+          const uint16_t val = __ldg(lut_b + ox * d_b + oy);
+          if (active) {
+            const int r = r0 + oy;
+            uint16_t* hq = htile + ((r >> 1) * kStripW + lane) * 2 + (r & 1);
+            if (val > *hq) *hq = val;
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k;
+      if (i < kRowVec) s_lut[i] = nl[k];
+    }
+    r0v = n0v;
+    r1v = n1v;
+    __syncwarp();
+  }
+  if (lx < P.W) {
+    uint32_t* M = map + int64_t(f) * P.W * P.H;
+    const bool col_ok = lx > 0 && lx < P.W - 1;  // pt_cloud.comp:67
+    for (int r = 0; r < P.H; ++r) {
+      const int tr = r + P.pad_rows;
+      const uint32_t wv = wtile[(tr >> 1) * kStripW + lane];
+      const uint32_t val = (tr & 1) ? (wv >> 16) : (wv & 0xFFFFu);
+      const bool ok = col_ok && r > 0 && r < P.H - 1;
+      M[int64_t(r) * P.W + lx] = ok ? val : 0u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ weights
 // pt_cloud_weights.comp:49-123 as one streaming pass: every thread recomputes the (at most 8)
 // distances it needs from the 3x3 map neighbourhood instead of exchanging them through images, which
@@ -298,6 +418,9 @@ struct tod_scene {
   float *cy = nullptr, *cx = nullptr;
   uint16_t *lut_t = nullptr, *lut_b = nullptr;
   uint8_t *span_t = nullptr, *span_b = nullptr;
+  uint4* lut_pack = nullptr;         // packed terrain stamps, both row alignments (terrain_norm_const == 10 only)
+  unsigned int* row_mask = nullptr;  // per source row: which stamp columns are non-empty
+  size_t packed_smem = 0;
   // per-batch buffers
   uint16_t *depth = nullptr, *target = nullptr, *land = nullptr;
   unsigned int* row_robot = nullptr;
@@ -333,7 +456,7 @@ void tod_scene_default_params(tod_scene_params* p) {
 void tod_scene_destroy(tod_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  void* ptrs[] = {s->cy, s->cx, s->lut_t, s->lut_b, s->span_t, s->span_b, s->depth, s->target, s->land, s->row_robot,
+  void* ptrs[] = {s->lut_pack, s->row_mask, s->cy, s->cx, s->lut_t, s->lut_b, s->span_t, s->span_b, s->depth, s->target, s->land, s->row_robot,
                   s->ball_sums, s->map, s->world, s->conn0, s->conn1, s->balls, s->m_height, s->m_pos, s->m_conn, s->m_balls};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -426,6 +549,29 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
   SC_CUDA(cudaMalloc(&s->m_conn, npx * 32));
   SC_CUDA(cudaMalloc(&s->m_balls, kMaxBalls * 8));
   SC_CUDA(cudaFuncSetAttribute(stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->stamp_smem)));
+  if (st == 10) {
+    // word k of a stamp column covers tile rows (2k, 2k+1) counted from the even-aligned start row; per (y, ox)
+    // the table holds the even-aligned and the odd-aligned packing, 12 words each
+    std::vector<uint32_t> pk(size_t(H) * dt * 2 * kPackWords, 0u);
+    std::vector<unsigned int> rmask(H, 0u);
+    for (int y = 0; y < H; ++y)
+      for (int ox = 0; ox < dt; ++ox) {
+        const uint16_t* col = &lut_t[(size_t(y) * dt + ox) * dt];
+        uint32_t* E = &pk[((size_t(y) * dt + ox) * 2 + 0) * kPackWords];
+        uint32_t* O = &pk[((size_t(y) * dt + ox) * 2 + 1) * kPackWords];
+        for (int k = 0; k < 10; ++k) E[k] = uint32_t(col[2 * k]) | (uint32_t(col[2 * k + 1]) << 16);
+        O[0] = uint32_t(col[0]) << 16;
+        for (int k = 1; k < 10; ++k) O[k] = uint32_t(col[2 * k - 1]) | (uint32_t(col[2 * k]) << 16);
+        O[10] = uint32_t(col[19]);
+        if (span_t[(size_t(y) * dt + ox) * 2 + 1] != 0) rmask[y] |= 1u << ox;
+      }
+    SC_CUDA(cudaMalloc(&s->lut_pack, pk.size() * 4));
+    SC_CUDA(cudaMalloc(&s->row_mask, rmask.size() * 4));
+    SC_CUDA(cudaMemcpy(s->lut_pack, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    SC_CUDA(cudaMemcpy(s->row_mask, rmask.data(), rmask.size() * 4, cudaMemcpyHostToDevice));
+    s->packed_smem = (size_t(H + 2 * s->dev.pad_rows + 1) / 2 + kPackWords) * kStripW * sizeof(uint32_t) + size_t(dt) * 6 * 16;
+    SC_CUDA(cudaFuncSetAttribute(stamp_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->packed_smem)));
+  }
 #undef SC_CUDA
   *out = s;
   return TOD_OK;
@@ -442,7 +588,10 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   land_kernel<<<blocks, 256, 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums, n);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[0], st));
   dim3 grid((P.W + kStripW - 1) / kStripW, n);
-  stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
+  if (s->lut_pack)
+    stamp_packed_kernel<<<grid, 32, s->packed_smem, st>>>(s->land, s->row_robot, s->lut_pack, s->row_mask, s->lut_b, s->span_b, P, d_map);
+  else
+    stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[1], st));
   if (d_world || d_conn0 || d_conn1)
     weights_kernel<<<blocks, 256, 0, st>>>(d_map, P, reinterpret_cast<float4*>(d_world), reinterpret_cast<float4*>(d_conn0),
