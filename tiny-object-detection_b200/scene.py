@@ -31,13 +31,13 @@ class Scene:
     def neighbors(self, px):
         """scene.rs:134-143, including its literal 680 typo."""
         out = []
-        if px >= 1:
+        if px > 0:
             out.append(px - 1)
-        if px + 1 < 680 * 480:
+        if px < 680 * 480 - 1:
             out.append(px + 1)
-        if px >= 640:
+        if px // 640 > 0:
             out.append(px - 640)
-        if px + 640 < 680 * 480:
+        if px // 640 < 480 - 1:
             out.append(px + 640)
         return out
 
