@@ -62,6 +62,7 @@ struct TcParams {
   uint32_t layout;             // UMMA swizzle code
   int vec_store;               // OC % 16 == 0 and 16B-aligned rows
   int sc, pitch;               // epilogue staging: columns per pass, bytes per staged row
+  const uint8_t* post_lut;     // optional fused byte map (QUANTIZE / RELU / TANH chain), 256 entries
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -146,6 +147,7 @@ struct SmemCtl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  uint8_t lut[256];
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -178,6 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (p.post_lut && threadIdx.x >= 128) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -323,6 +326,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             q1 = max(p.act_min, min(p.act_max, q1));
             q2 = max(p.act_min, min(p.act_max, q2));
             q3 = max(p.act_min, min(p.act_max, q3));
+            if (p.post_lut) {
+              q0 = ctl->lut[q0 & 0xFF];
+              q1 = ctl->lut[q1 & 0xFF];
+              q2 = ctl->lut[q2 & 0xFF];
+              q3 = ctl->lut[q3 & 0xFF];
+            }
             packed[q4] = (uint32_t(q0) & 0xFFu) | ((uint32_t(q1) & 0xFFu) << 8) | ((uint32_t(q2) & 0xFFu) << 16) | (uint32_t(q3) << 24);
           }
           *reinterpret_cast<uint4*>(stage_buf + size_t(r) * p.pitch + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -522,6 +531,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.out_zp = a.rq.out_zp;
   p.act_min = a.rq.act_min;
   p.act_max = a.rq.act_max;
+  p.post_lut = a.rq.post_lut;
   p.out = a.out;
   p.out_ts = a.out_tile_stride;
   p.vec_store = (g.OC % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.out_tile_stride & 15) == 0) ? 1 : 0;
@@ -655,7 +665,7 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   TOD_CUDA(cudaMemset(d_o1, 0x55, out_elems));
   TOD_CUDA(cudaMemset(d_o2, 0x33, out_elems));
   const int32_t in_zp = -3;
-  Requant rq{d_mult, d_shift, 5, -128, 127};
+  Requant rq{d_mult, d_shift, 5, -128, 127, nullptr};
   const int64_t in_ts = int64_t(H) * W * IC, out_ts = int64_t(H) * W * OC;
   int rc = TOD_OK;
   ConvTc* plan = nullptr;

@@ -14,6 +14,7 @@ namespace {
 __device__ __forceinline__ int8_t requant_store(int32_t acc, int32_t mult, int32_t shift, const Requant& rq) {
   int32_t v = mul_by_quant_mult_fast(acc, mult, shift) + rq.out_zp;  // q >= 0, |acc| < 2^30
   v = max(rq.act_min, min(rq.act_max, v));
+  if (rq.post_lut) v = __ldg(rq.post_lut + (v & 0xFF));
   return int8_t(v);
 }
 
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
     for (int j = 0; j < 4; ++j) {
       int32_t v = mul_by_quant_mult_fast(acc[j], mult[j], shift[j]) + rq.out_zp;
       v = max(rq.act_min, min(rq.act_max, v));
+      if (rq.post_lut) v = __ldg(rq.post_lut + (v & 0xFF));
       packed |= (unsigned(v) & 0xFFu) << (8 * j);
     }
     *reinterpret_cast<unsigned*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + c) = packed;

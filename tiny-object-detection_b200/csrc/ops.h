@@ -19,6 +19,7 @@ struct Requant {          // per-output-channel fixed point requantisation + act
   const int32_t* mult;    // [OC] Q31
   const int32_t* shift;   // [OC] exponent (<= 0: right shift)
   int32_t out_zp, act_min, act_max;
+  const uint8_t* post_lut;  // optional 256-entry byte map applied to the requantised byte (fused QUANTIZE / RELU / TANH chain)
 };
 
 // CONV_2D, any geometry.  w: [OC][KH][KW][IC] int8.  bias: [OC] int32 (may be null).

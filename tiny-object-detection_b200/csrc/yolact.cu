@@ -54,6 +54,10 @@ struct Step {
   int64_t macs = 0;
   ConvTc* tc = nullptr;
   std::vector<int> deps;   // indices of the steps whose output this step reads (RESHAPE / CONCAT are transparent)
+  std::vector<uint8_t> lut_host;  // kStepLut: the table; conv steps: the composed byte map fused behind the requantisation
+  int64_t post_lut_off = -1;
+  bool out_moved = false;  // the conv writes where a fused byte-map chain's last output lives
+  Place out_place;
 };
 
 void conv_out_pad(int padding, int in, int k, int stride, int dil, int* out, int* pad) {
@@ -142,6 +146,7 @@ struct tod_yolact {
   Graph graph;
   std::vector<Step> steps;
   std::vector<Place> place;   // per tensor
+  std::vector<char> fused_away;  // per tensor: never written because its byte map was fused into the producing conv
   int64_t macs_per_tile = 0;
   int tc_layers = 0;
   cudaStream_t stream = nullptr;
@@ -433,6 +438,7 @@ int plan(tod_yolact* y, ConstArena* arena) {
         st.kind = kStepLut;
         st.in0 = op.inputs[0]; st.out = op.outputs[0];
         st.lut_off = arena->add(lut, 256);
+        st.lut_host.assign(lut, lut + 256);
         break;
       }
       case kPad: {
@@ -489,17 +495,105 @@ int plan(tod_yolact* y, ConstArena* arena) {
     y->macs_per_tile += s.macs;
     if (s.in0 >= 0 && !y->place[s.in0].base) return fail(TOD_ERR_MODEL, "operator %d reads tensor %d which nothing produces", s.op, s.in0);
   }
+  // ---- byte-map fusion: QUANTIZE / RELU / TANH are pure functions of one byte.  A chain  conv -> [RESHAPE | placed
+  // CONCATENATION | byte map]*  whose tensors have no other reader collapses into the conv's epilogue: the maps are
+  // composed on the host into one 256-entry table and the conv writes straight into the chain's last buffer (e.g. the
+  // uint8 class / box / coefficient outputs come directly from the five head levels' convolutions).
+  y->fused_away.assign(nt, 0);
+  if (fuse) {
+    std::vector<int> op_of_tensor_consumer_count(consumers);  // readers per tensor (graph outputs count as one)
+    auto single_reader = [&](int t) { return op_of_tensor_consumer_count[t] == 1; };
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (size_t li = 0; li < y->steps.size(); ++li) {
+        Step& L = y->steps[li];
+        if (L.kind != kStepLut) continue;
+        // walk back from the map's input through aliases to the producing steps
+        std::vector<int> srcs;  // conv step indices
+        bool ok = true;
+        std::function<void(int)> back = [&](int t) {
+          if (!ok) return;
+          if (!single_reader(t) || G.tensors[t].is_const() || t == G.inputs[0]) {
+            ok = false;
+            return;
+          }
+          int found = -1;
+          for (size_t k = 0; k < y->steps.size(); ++k)
+            if (y->steps[k].out == t && y->steps[k].kind != kStepCopy) found = int(k);
+          if (found >= 0) {  // a kernel writes t (possibly a conv that already absorbed an earlier map)
+            const StepKind kd = y->steps[found].kind;
+            if (kd != kStepConvDirect && kd != kStepDepthwise) ok = false;
+            else srcs.push_back(found);
+            return;
+          }
+          const int po = producer[t];
+          if (po < 0) {
+            ok = false;
+            return;
+          }
+          const GOp& op = G.ops[po];
+          if (op.code == kReshape) return back(op.inputs[0]);
+          if (op.code == kConcat) {
+            for (const CopyJob& c : copies)
+              if (c.op == po) ok = false;  // an input that had to be copied: keep the concat buffer
+            for (int in : op.inputs) back(in);
+            return;
+          }
+          ok = false;
+        };
+        back(L.in0);
+        if (!ok || srcs.empty()) continue;
+        const Place& lin = y->place[L.in0];
+        const Place& lout = y->place[L.out];
+        for (int si : srcs) {
+          Step& P = y->steps[si];
+          const Place cur = P.out_moved ? P.out_place : y->place[P.out];
+          Place np;
+          np.base = lout.base + (cur.base - lin.base);
+          np.tile_stride = lout.tile_stride;
+          np.bytes = cur.bytes;
+          std::vector<uint8_t> composed(256);
+          for (int b = 0; b < 256; ++b) composed[b] = L.lut_host[P.lut_host.empty() ? b : P.lut_host[b]];
+          P.lut_host = composed;
+          y->fused_away[P.out] = 1;
+          P.out_moved = true;
+          P.out_place = np;
+          P.out = L.out;  // for dependency tracking and fetches the conv now *is* the producer of the map's output
+        }
+        // tensors on the way are no longer written
+        std::function<void(int)> mark = [&](int t) {
+          y->fused_away[t] = 1;
+          const int po = producer[t];
+          if (po < 0) return;
+          const GOp& op = G.ops[po];
+          if (op.code == kReshape) mark(op.inputs[0]);
+          else if (op.code == kConcat)
+            for (int in : op.inputs) mark(in);
+        };
+        mark(L.in0);
+        y->steps.erase(y->steps.begin() + li);
+        changed = true;
+        break;
+      }
+    }
+  }
+  for (Step& st : y->steps)
+    if ((st.kind == kStepConvDirect || st.kind == kStepDepthwise) && !st.lut_host.empty()) st.post_lut_off = arena->add(st.lut_host.data(), 256);
   // ---- data dependencies between steps
   std::vector<std::vector<int>> op_steps(G.ops.size());  // steps generated for an op (its kernel, or a concat's copies)
   for (size_t i = 0; i < y->steps.size(); ++i) op_steps[y->steps[i].op].push_back(int(i));
+  std::vector<std::vector<int>> writers(nt);  // steps whose (possibly moved) output is tensor t
+  for (size_t i = 0; i < y->steps.size(); ++i)
+    if (y->steps[i].out_moved) writers[y->steps[i].out].push_back(int(i));
   std::vector<std::vector<int>> memo(nt);
   std::vector<char> done(nt, 0);
   std::function<const std::vector<int>&(int)> producers = [&](int t) -> const std::vector<int>& {
     if (done[t]) return memo[t];
     done[t] = 1;
-    std::vector<int> out;
+    std::vector<int> out = writers[t];
     const int po = producer[t];
-    if (po >= 0) {
+    if (po >= 0 && writers[t].empty()) {
       const GOp& op = G.ops[po];
       if (op.code == kReshape || (op.code == kPad && pad_folded[po])) {
         out = producers(op.inputs[0]);
@@ -544,7 +638,7 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
   for (Step& st : y->steps) {
     if (st.kind != kStepConvDirect || y->opt.conv_impl != 0) continue;
     const Place& pi = y->place[st.in0];
-    const Place& po = y->place[st.out];
+    const Place& po = st.out_moved ? st.out_place : y->place[st.out];
     const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
     if (!conv_tc_supported(st.g, pi.tile_stride, pi.base, w)) continue;
     ConvTcArgs a{};
@@ -554,7 +648,7 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
     a.w = w;
     a.in_zp = st.in_zp;
     a.rq = Requant{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
-                   st.out_zp, st.act_min, st.act_max};
+                   st.out_zp, st.act_min, st.act_max, st.post_lut_off >= 0 ? y->d_const + st.post_lut_off : nullptr};
     a.out = reinterpret_cast<int8_t*>(po.base);
     a.out_tile_stride = po.tile_stride;
     a.max_tiles = y->opt.max_tiles;
@@ -569,14 +663,14 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
 
 int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
   const Place& pi = y->place[st.in0];
-  const Place& po = y->place[st.out];
+  const Place& po = st.out_moved ? st.out_place : y->place[st.out];
   switch (st.kind) {
     case kStepConvTc:
       return conv_tc_launch(st.tc, n, s);
     case kStepConvDirect:
     case kStepDepthwise: {
       Requant rq{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
-                 st.out_zp, st.act_min, st.act_max};
+                 st.out_zp, st.act_min, st.act_max, st.post_lut_off >= 0 ? y->d_const + st.post_lut_off : nullptr};
       const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
       const int32_t* bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(y->d_const + st.bias_off) : nullptr;
       if (st.kind == kStepDepthwise)
@@ -1068,6 +1162,8 @@ int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t 
   const Place& p = y->place[tensor];
   if (!p.base) return fail(TOD_ERR_INVALID_ARG, "tensor %d is a constant or is not materialised", tensor);
   if (out_bytes < size_t(p.bytes) * n) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: buffer too small (%zu < %lld)", out_bytes, (long long)(p.bytes * n));
+  if (!y->fused_away.empty() && y->fused_away[tensor])
+    return fail(TOD_ERR_INVALID_ARG, "tensor %d is fused into the producing convolution's epilogue; create the handle with fusion = 0 to fetch it", tensor);
   // a PAD folded into its convolution is never written
   for (size_t i = 0; i < y->graph.ops.size(); ++i)
     if (y->graph.ops[i].code == kPad && y->graph.ops[i].outputs[0] == tensor) {
