@@ -295,9 +295,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
     bool keep = false;
     if (j < m) {
       const float4 bj = s_box[j];
-      float mx = 0.f;
-      for (int i = 0; i < j; ++i) mx = fmaxf(mx, iou_rn(s_box[i], bj));
-      keep = mx <= c.nms_thresh;
+      keep = true;  // column max of the upper-triangular IoU matrix <= thresh  <=>  no row i < j exceeds it
+      for (int i = 0; i < j && keep; ++i) keep = !(iou_rn(s_box[i], bj) > c.nms_thresh);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     int base = 0;
