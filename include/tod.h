@@ -210,6 +210,11 @@ int tod_i8_gemm_selftest(int device, int M, int N, int K, int iters, float* ms_p
  * both the tcgen05 implicit-GEMM kernel and the CUDA-core direct kernel: times both and counts differing bytes. */
 int tod_conv_selftest(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, float* ms_tc,
                       float* ms_direct, long long* mismatches);
+/* Same, selecting the epilogue variant under test.  flags: 1 = ReLU6-style clamp instead of the full int8 range,
+ * 2 = a fused 256-entry byte map behind the requantisation, 4 = force the general epilogue, 8 = multipliers >= 0.5
+ * (the planner must itself fall back to the general epilogue), 16 = activation minimum above -128. */
+int tod_conv_selftest_ex(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, int flags,
+                         float* ms_tc, float* ms_direct, long long* mismatches);
 
 #ifdef __cplusplus
 }

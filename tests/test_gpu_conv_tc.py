@@ -29,3 +29,17 @@ def test_conv_tc_matches_direct(tod, shape):
     from tod_b200 import _lib
     ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=2)
     assert bad == 0, "%d bytes differ (tcgen05 %.3f ms, direct %.3f ms)" % (bad, ms_tc, ms_direct)
+
+
+# epilogue variants: (flags, meaning) — see tod_conv_selftest_ex in include/tod.h
+VARIANTS = [(1, "relu6-clamp"), (2, "byte-map"), (3, "clamp+byte-map"), (16, "act-min"), (4, "general-epilogue"), (8, "shift0-fallback")]
+VARIANT_SHAPES = [(3, 28, 28, 256, 256, 3), (2, 14, 14, 256, 243, 3), (5, 7, 7, 256, 96, 3), (2, 56, 56, 144, 32, 1),
+                  (1, 112, 112, 16, 96, 1), (2, 7, 7, 960, 160, 1), (2, 14, 14, 96, 576, 1), (3, 28, 28, 32, 16, 1)]
+
+
+@pytest.mark.parametrize("flags", [v[0] for v in VARIANTS], ids=[v[1] for v in VARIANTS])
+@pytest.mark.parametrize("shape", VARIANT_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_epilogue_variants(tod, shape, flags):
+    from tod_b200 import _lib
+    ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=1, flags=flags)
+    assert bad == 0, "%d bytes differ with epilogue flags %d" % (bad, flags)

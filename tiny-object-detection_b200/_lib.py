@@ -25,6 +25,7 @@ SYMBOLS = [
     "tod_yolact_num_ops", "tod_yolact_tensor_info", "tod_yolact_infer_tiles", "tod_yolact_infer_tiles_device",
     "tod_yolact_fetch_output", "tod_yolact_fetch_tensor", "tod_yolact_fetch_tile_classes", "tod_yolact_fetch_detections",
     "tod_yolact_stats", "tod_yolact_profile_ops", "tod_i8_gemm_selftest", "tod_conv_selftest",
+    "tod_conv_selftest_ex",
 ]
 
 
@@ -100,6 +101,7 @@ def lib():
         L.tod_yolact_profile_ops.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.tod_i8_gemm_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.tod_conv_selftest.argtypes = [C.c_int] * 8 + [vp, vp, vp]
+        L.tod_conv_selftest_ex.argtypes = [C.c_int] * 9 + [vp, vp, vp]
         _lib = L
     return _lib
 
@@ -111,10 +113,10 @@ def check(rc):
     return rc
 
 
-def conv_selftest(tiles, H, W, IC, OC, K, iters=3, device=0):
+def conv_selftest(tiles, H, W, IC, OC, K, iters=3, device=0, flags=0):
     """(ms_tcgen05, ms_direct, mismatching bytes) of one convolution run through both kernels."""
     a, b, bad = C.c_float(), C.c_float(), C.c_longlong(-1)
-    check(lib().tod_conv_selftest(device, tiles, H, W, IC, OC, K, iters, C.byref(a), C.byref(b), C.byref(bad)))
+    check(lib().tod_conv_selftest_ex(device, tiles, H, W, IC, OC, K, iters, flags, C.byref(a), C.byref(b), C.byref(bad)))
     return a.value, b.value, bad.value
 
 

@@ -63,6 +63,13 @@ struct TcParams {
   int vec_store;               // OC % 16 == 0 and 16B-aligned rows
   int sc, pitch;               // epilogue staging: columns per pass, bytes per staged row
   const uint8_t* post_lut;     // optional fused byte map (QUANTIZE / RELU / TANH chain), 256 entries
+  // ---- fast epilogue (conv_tc_fast_kernel)
+  const int4* qtab;            // [OCp] {Q31 multiplier, rounding term with the output zero point folded in, right shift, 0}
+  const int32_t* b2tab;        // [ncls][OCp] 2 * (bias - zp * sum of in-image tap sums), compact border classes
+  int ncls, ncls_x;            // compact border classes: cls = ymap[ymask] * ncls_x + xmap[xmask]
+  uint8_t ymap[8], xmap[8];
+  int wo;                      // TMA-store staging row bytes (16 / 32 / 64 / 128), 0 = manual stores
+  uint32_t stage_bytes;        // shared memory reserved for output staging
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -130,6 +137,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// d = sat_s8(hi) << 8 | sat_s8(lo) in the low half, `upper`'s low half in the high half
+__device__ __forceinline__ uint32_t pack_sat_s8(int hi, int lo, uint32_t upper) {
+  uint32_t d;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+  return d;
+}
+
 // K-major, swizzled shared-memory matrix descriptor (SM100 format: version 1 at bit 46)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
@@ -154,7 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p, const int tiles) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible to the compiler
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
   uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;                      // [128][pitch] requantised bytes
@@ -373,6 +395,273 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ fast-epilogue variant
+// Same producer / MMA pipeline; the epilogue is rebuilt around what the first profile showed (it executed ~26 SASS
+// instructions per output element and bounded every layer, large or small):
+//   * per-channel constants live in shared memory ({q, rounding term, shift} and 2*bias per border class), read as
+//     warp-wide broadcasts instead of three __ldg streams;
+//   * TFLite's MultiplyByQuantizedMultiplier for shift <= -1 collapses to
+//         x2 = 2*acc + 2*bias;   out = (hi32(x2 * q + 2^31 + ((half + (zp << rs)) << 32)) + (x2 >> 31)) >> rs
+//     (identical to the double-rounding reference form: hi32(x2*q + 2^31) is SRDHM's result v, and sign(x2) differs
+//     from sign(v) only where v == 0 and the rounding term cannot change the quotient; the host verifies the
+//     preconditions, tests/test_fixedpoint.py checks the identity), 4 integer instructions + one LDS.128;
+//   * a full-range clamp is the saturation of cvt.pack.sat.s8.s32;
+//   * requantised bytes go to a swizzled staging tile and leave with ONE TMA store per 128-column pass (the TMA unit
+//     clips rows / columns outside the tensor), double-buffered so a pass needs a single CTA-wide barrier.
+enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4 };
+
+struct WorkItem { int n_tile, tx, ty, g; };
+__device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles_x, int tiles_y) {
+  WorkItem w;
+  unsigned m = unsigned(work);
+  if (n_tiles > 1) {
+    w.n_tile = int(m % unsigned(n_tiles));
+    m /= unsigned(n_tiles);
+  } else {
+    w.n_tile = 0;
+  }
+  w.tx = int(m % unsigned(tiles_x));
+  m /= unsigned(tiles_x);
+  if (tiles_y > 1) {
+    w.ty = int(m % unsigned(tiles_y));
+    w.g = int(m / unsigned(tiles_y));
+  } else {
+    w.ty = 0;
+    w.g = int(m);
+  }
+  return w;
+}
+
+template <uint32_t MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible to the compiler
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
+  uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;  // 1024-aligned (both stage sizes are)
+  long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + p.stage_bytes);
+  int4* s_qtab = reinterpret_cast<int4*>(s_rowoff + kBM);
+  int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wd = p.flat ? tiles * p.HW : p.Wd;
+  const int tiles_x = p.flat ? (Wd + kBM - 1) / kBM : p.tiles_x;
+  const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
+  const int total_work = groups * p.tiles_y * tiles_x * p.n_tiles;
+  const int k_iters = p.taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->acc_full[s], 1);
+      mbar_init(&ctl->acc_empty[s], kEpiThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
+  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
+  if ((MODE & kEpiLut) && threadIdx.x >= 128) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
+        const int x0 = w.tx * p.pw, y0 = w.ty * p.ph, n0 = w.g * p.pn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int fy = tap / p.KW, fx = tap - fy * p.KW;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
+            tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 + fx - p.pad_left, y0 + fy - p.pad_top, n0);
+            tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, w.n_tile * p.BN);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t use = uint32_t(it >> 1);
+      mbar_wait(&ctl->acc_empty[as], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + size_t(stage) * p.a_stage);
+          const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * p.b_stage);
+          for (int kk = 0; kk < p.BK / 32; ++kk) {
+            const uint64_t ad = make_desc(a_addr + kk * 32, p.sbo, p.layout);
+            const uint64_t bd = make_desc(b_addr + kk * 32, p.sbo, p.layout);
+            umma_i8(tmem_d, ad, bd, p.idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&ctl->empty[stage]);
+          if (k == k_iters - 1) umma_commit(&ctl->acc_full[as]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;        // which 16-column chunks of a pass this warp converts
+    const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
+    const int et = threadIdx.x - 128;
+    const int wx = r % p.pw;
+    const int wy = (r / p.pw) % p.ph;
+    const int wn = r / (p.pw * p.ph);
+    // staging: TMA mode = dense rows of p.wo bytes in the tensor map's swizzle; manual mode = padded pitch
+    const uint32_t swz_mask = p.wo == 128 ? 7u : (p.wo == 64 ? 3u : (p.wo == 32 ? 1u : 0u));
+    const uint32_t row_base = (MODE & kEpiTma) ? uint32_t(r) * uint32_t(p.wo) : uint32_t(r) * uint32_t(p.pitch);
+    const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.wo);
+    uint32_t pass_count = 0;
+    int it = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t use = uint32_t(it >> 1);
+      const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
+      const int x = w.tx * p.pw + wx, yy = w.ty * p.ph + wy, n = w.g * p.pn + wn;
+      int cls = 0;
+      if (p.ncls > 1) {  // border class of this pixel: which filter rows / columns are inside the image
+        int ymask = 0, xmask = 0;
+        for (int f = 0; f < p.KH; ++f) {
+          const int iy = yy + f - p.pad_top;
+          ymask |= (iy >= 0 && iy < p.IH) ? (1 << f) : 0;
+        }
+        for (int f = 0; f < p.KW; ++f) {
+          const int ix = x + f - p.pad_left;
+          xmask |= (ix >= 0 && ix < p.IW) ? (1 << f) : 0;
+        }
+        cls = int(p.ymap[ymask & 7]) * p.ncls_x + int(p.xmap[xmask & 7]);
+      }
+      const int ocb = w.n_tile * p.BN;
+      const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
+      const int4* qrow = s_qtab + ocb;
+      if (!(MODE & kEpiTma)) {
+        const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
+        s_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
+      }
+      const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
+
+      mbar_wait(&ctl->acc_full[as], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
+      for (int pass0 = 0; pass0 < ncols_tile; pass0 += p.sc) {
+        const int pass_cols = min(p.sc, ncols_tile - pass0);
+        uint8_t* sbuf = stage_buf + ((MODE & kEpiTma) ? (pass_count & 1u) * buf_bytes : 0u);
+        ++pass_count;
+        for (int c0 = half * 16; c0 < pass_cols; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld16(taddr + pass0 + c0, v);
+          tmem_wait_ld();
+          uint32_t packed[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int col = pass0 + c0 + 4 * q4;
+            const int4 b4 = b2row[col >> 2];
+            int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int4 k = qrow[col + j];  // {q, rs, 2^31, half + (zp << rs)}: z:w is the 64-bit addend, in place
+              const int bj = j == 0 ? b4.x : (j == 1 ? b4.y : (j == 2 ? b4.z : b4.w));
+              const int x2 = int(v[4 * q4 + j]) * 2 + bj;
+              const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
+              const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
+              o[j] = (t + (x2 >> 31)) >> k.y;  // sign(x2) == sign(v) wherever the rounding term can matter
+            }
+            if ((MODE & kEpiSat) && !(MODE & kEpiLut)) {
+              packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o[j] = max(p.act_min, min(p.act_max, o[j]));
+                if (MODE & kEpiLut) o[j] = ctl->lut[o[j] & 0xFF];
+              }
+              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+            }
+          }
+          uint32_t off = row_base + uint32_t(c0);
+          if (MODE & kEpiTma) off ^= ((off >> 7) & swz_mask) << 4;
+          *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (pass0 + p.sc >= ncols_tile) {  // accumulator fully read: hand the TMEM stage back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
+        }
+        if (MODE & kEpiTma) {
+          if (et == 0) tma_store_wait_read();   // the previous pass' store has drained the *other* buffer
+          fence_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * kBM, 0, 0);
+            else tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * p.pw, w.ty * p.ph, w.g * p.pn);
+            tma_store_commit();
+          }
+        } else {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (p.vec_store) {
+            const int cpr = pass_cols >> 4;
+            for (int idx = et; idx < kBM * cpr; idx += kEpiThreads) {
+              const int rr = idx / cpr, ch = idx - rr * cpr;
+              const long long off = s_rowoff[rr];
+              if (off >= 0)
+                *reinterpret_cast<uint4*>(p.out + off + ocb + pass0 + ch * 16) = *reinterpret_cast<const uint4*>(sbuf + size_t(rr) * p.pitch + ch * 16);
+            }
+          } else {
+            for (int idx = et; idx < kBM * pass_cols; idx += kEpiThreads) {
+              const int rr = idx / pass_cols, bb = idx - rr * pass_cols;
+              const long long off = s_rowoff[rr];
+              if (off >= 0) p.out[off + ocb + pass0 + bb] = int8_t(sbuf[size_t(rr) * p.pitch + bb]);
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+    }
+    if ((MODE & kEpiTma) && et == 0) tma_store_wait_read();  // staging must outlive the last store's reads
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -388,8 +677,9 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int encode(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk) {
+int encode(CUtensorMap* map, const void* base_c, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk) {
   EncodeTiledFn fn = encode_fn();
+  void* base = const_cast<void*>(base_c);
   if (!fn) return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gd[5];
   cuuint64_t gs[4];
@@ -400,7 +690,8 @@ int encode(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const u
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  const CUtensorMapSwizzle sw = bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, cuuint32_t(rank), base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu/%llu, box %u/%u)", int(r), rank,
@@ -422,11 +713,14 @@ int sm_count() {
 }  // namespace
 
 struct ConvTc {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_o;
   TcParams p{};
-  int32_t *d_bias_eff = nullptr, *d_mult = nullptr, *d_shift = nullptr;
+  int32_t *d_bias_eff = nullptr, *d_mult = nullptr, *d_shift = nullptr, *d_b2 = nullptr;
+  int4* d_qtab = nullptr;
   size_t smem_bytes = 0;
   int max_tiles = 0;
+  int fast = 0;        // conv_tc_fast_kernel is eligible
+  uint32_t mode = 0;   // kEpi* bits
 };
 
 bool conv_tc_supported(const ConvGeom& g, int64_t in_ts, const void* in, const void* w) {
@@ -448,6 +742,8 @@ void conv_tc_destroy(ConvTc* c) {
   cudaFree(c->d_bias_eff);
   cudaFree(c->d_mult);
   cudaFree(c->d_shift);
+  cudaFree(c->d_b2);
+  cudaFree(c->d_qtab);
   delete c;
 }
 
@@ -472,7 +768,9 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.BK = (g.IC % 128 == 0) ? 128 : ((g.IC % 64 == 0) ? 64 : 32);
   p.kchunks = (g.IC + p.BK - 1) / p.BK;
   p.n_tiles = (g.OC + 255) / 256;
-  p.BN = ((g.OC + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;
+  // several N tiles: full 256-column tiles, so a 128-column TMA-store pass never overhangs into the next tile's
+  // columns (the last tile's overhang is clipped at the tensor edge; its weight rows past OC are TMA zero fill)
+  p.BN = p.n_tiles > 1 ? 256 : (g.OC + 15) / 16 * 16;
   p.OCp = p.n_tiles * p.BN;
   p.HW = g.OH * g.OW;
   const bool one = g.KH == 1 && g.KW == 1;
@@ -517,11 +815,79 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.a_stage = uint32_t((kBM * p.BK + 1023) / 1024 * 1024);
   p.b_stage = uint32_t((p.BN * p.BK + 1023) / 1024 * 1024);
   p.tx_bytes = uint32_t(p.rows * p.BK + p.BN * p.BK);
-  p.sc = std::min(p.BN, 128);
-  int pitch16 = p.sc / 16 + 1;
-  if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
-  p.pitch = pitch16 * 16;
-  const size_t fixed = size_t(kBM) * p.pitch + size_t(kBM) * 8 + sizeof(SmemCtl) + 1024;
+  p.vec_store = (g.OC % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.out_tile_stride & 15) == 0) ? 1 : 0;
+  // ---- fast epilogue eligibility: every channel requantises with a right shift in [1, 22], a non-negative multiplier,
+  // and 2 * (accumulator + bias) stays inside int32
+  const int ncls_full = (1 << g.KH) * (1 << g.KW);
+  std::vector<int32_t> be(size_t(ncls_full) * p.OCp, 0);
+  int64_t max_bias = 0;
+  for (int ym = 0; ym < (1 << g.KH); ++ym)
+    for (int xm = 0; xm < (1 << g.KW); ++xm) {
+      int32_t* row = &be[size_t(ym * (1 << g.KW) + xm) * p.OCp];
+      for (int oc = 0; oc < g.OC; ++oc) {
+        int32_t s = 0;
+        for (int fy = 0; fy < g.KH; ++fy)
+          for (int fx = 0; fx < g.KW; ++fx)
+            if (((ym >> fy) & 1) && ((xm >> fx) & 1)) s += a.h_wsum[size_t(oc) * p.taps + fy * g.KW + fx];
+        row[oc] = int32_t(uint32_t(a.h_bias ? a.h_bias[oc] : 0) - uint32_t(a.in_zp) * uint32_t(s));
+        max_bias = std::max<int64_t>(max_bias, std::llabs(int64_t(a.h_bias ? a.h_bias[oc] : 0) - int64_t(a.in_zp) * s));
+      }
+    }
+  c->fast = (a.h_mult && a.h_shift && a.fast_epilogue && g.KH <= 3 && g.KW <= 3) ? 1 : 0;
+  if (c->fast) {
+    if (int64_t(p.taps) * g.IC * 128 * 128 + max_bias >= (int64_t(1) << 29)) c->fast = 0;
+    for (int oc = 0; oc < g.OC && c->fast; ++oc)
+      if (a.h_shift[oc] > -1 || a.h_shift[oc] < -22 || a.h_mult[oc] < 0) c->fast = 0;
+    if (std::abs(a.rq.out_zp) > 128) c->fast = 0;
+  }
+  // compact border classes: the (row mask, column mask) pairs that occur for some output pixel
+  std::vector<int> ymasks, xmasks;
+  std::memset(p.ymap, 0, sizeof(p.ymap));
+  std::memset(p.xmap, 0, sizeof(p.xmap));
+  if (p.taps == 1) {
+    ymasks.push_back(1);
+    xmasks.push_back(1);
+  } else {
+    for (int oy = 0; oy < g.OH; ++oy) {
+      int m = 0;
+      for (int f = 0; f < g.KH; ++f) m |= (oy + f - g.pad_top >= 0 && oy + f - g.pad_top < g.IH) ? (1 << f) : 0;
+      if (std::find(ymasks.begin(), ymasks.end(), m) == ymasks.end()) ymasks.push_back(m);
+    }
+    for (int ox = 0; ox < g.OW; ++ox) {
+      int m = 0;
+      for (int f = 0; f < g.KW; ++f) m |= (ox + f - g.pad_left >= 0 && ox + f - g.pad_left < g.IW) ? (1 << f) : 0;
+      if (std::find(xmasks.begin(), xmasks.end(), m) == xmasks.end()) xmasks.push_back(m);
+    }
+  }
+  p.ncls_x = int(xmasks.size());
+  p.ncls = int(ymasks.size() * xmasks.size());
+  if (c->fast)
+    for (size_t i = 0; i < ymasks.size(); ++i) p.ymap[ymasks[i] & 7] = uint8_t(i);
+  if (c->fast)
+    for (size_t i = 0; i < xmasks.size(); ++i) p.xmap[xmasks[i] & 7] = uint8_t(i);
+  const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * 4 : 0;
+  if (table_bytes > 40 * 1024) c->fast = 0;
+  c->mode = 0;
+  if (c->fast) {
+    if (a.rq.act_min == -128 && a.rq.act_max == 127) c->mode |= kEpiSat;
+    if (a.rq.post_lut) c->mode |= kEpiLut;
+    if (p.vec_store) c->mode |= kEpiTma;
+  }
+  if (c->mode & kEpiTma) {
+    const int width = std::min(p.BN, 128);
+    p.wo = width <= 16 ? 16 : (width <= 32 ? 32 : (width <= 64 ? 64 : 128));
+    p.sc = p.wo;
+    p.pitch = p.wo;
+    p.stage_bytes = uint32_t(2 * kBM * p.wo);
+  } else {
+    p.wo = 0;
+    p.sc = std::min(p.BN, 128);
+    int pitch16 = p.sc / 16 + 1;
+    if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
+    p.pitch = pitch16 * 16;
+    p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024);
+  }
+  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 8 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
   const size_t budget = 227 * 1024 - fixed;
   p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
@@ -534,23 +900,33 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.post_lut = a.rq.post_lut;
   p.out = a.out;
   p.out_ts = a.out_tile_stride;
-  p.vec_store = (g.OC % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.out_tile_stride & 15) == 0) ? 1 : 0;
 
   // ---- epilogue tables
-  const int ncls = (1 << g.KH) * (1 << g.KW);
-  std::vector<int32_t> be(size_t(ncls) * p.OCp, 0), mu(p.OCp, 0), sh(p.OCp, 0);
-  for (int ym = 0; ym < (1 << g.KH); ++ym)
-    for (int xm = 0; xm < (1 << g.KW); ++xm) {
-      int32_t* row = &be[size_t(ym * (1 << g.KW) + xm) * p.OCp];
-      for (int oc = 0; oc < g.OC; ++oc) {
-        int32_t s = 0;
-        for (int fy = 0; fy < g.KH; ++fy)
-          for (int fx = 0; fx < g.KW; ++fx)
-            if (((ym >> fy) & 1) && ((xm >> fx) & 1)) s += a.h_wsum[size_t(oc) * p.taps + fy * g.KW + fx];
-        row[oc] = int32_t(uint32_t(a.h_bias ? a.h_bias[oc] : 0) - uint32_t(a.in_zp) * uint32_t(s));
-      }
-    }
+  std::vector<int32_t> mu(p.OCp, 0), sh(p.OCp, 0);
   cudaError_t ce;
+  if (c->fast) {
+    std::vector<int32_t> qt(size_t(p.OCp) * 4, 0), b2(size_t(p.ncls) * p.OCp, 0);
+    for (int oc = 0; oc < g.OC; ++oc) {
+      const int rs = -a.h_shift[oc];
+      qt[size_t(oc) * 4 + 0] = a.h_mult[oc];
+      qt[size_t(oc) * 4 + 1] = rs;
+      qt[size_t(oc) * 4 + 2] = int32_t(0x80000000u);
+      qt[size_t(oc) * 4 + 3] = (1 << (rs - 1)) + a.rq.out_zp * (1 << rs);
+    }
+    for (size_t yi = 0; yi < ymasks.size(); ++yi)
+      for (size_t xi = 0; xi < xmasks.size(); ++xi) {
+        const int code = p.taps == 1 ? ((1 << g.KW) + 1) : (ymasks[yi] * (1 << g.KW) + xmasks[xi]);
+        const int32_t* src = &be[size_t(code) * p.OCp];
+        int32_t* dst = &b2[(yi * xmasks.size() + xi) * p.OCp];
+        for (int oc = 0; oc < g.OC; ++oc) dst[oc] = 2 * src[oc];
+      }
+    if ((ce = cudaMalloc(&c->d_qtab, qt.size() * 4)) != cudaSuccess || (ce = cudaMalloc(&c->d_b2, b2.size() * 4)) != cudaSuccess)
+      return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
+    cudaMemcpy(c->d_qtab, qt.data(), qt.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_b2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice);
+    p.qtab = c->d_qtab;
+    p.b2tab = c->d_b2;
+  }
   if ((ce = cudaMalloc(&c->d_bias_eff, be.size() * 4)) != cudaSuccess || (ce = cudaMalloc(&c->d_mult, mu.size() * 4)) != cudaSuccess ||
       (ce = cudaMalloc(&c->d_shift, sh.size() * 4)) != cudaSuccess)
     return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
@@ -589,10 +965,37 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     rc = encode(&c->map_b, const_cast<int8_t*>(a.w), 3, dims, str, box, p.BK);
   }
   if (rc < 0) return bail(rc);
+  std::memset(&c->map_o, 0, sizeof(c->map_o));
+  if (c->mode & kEpiTma) {
+    // the output seen through the same patch tiling as the A operand; the box is [wo channels x patch]
+    if (p.flat) {
+      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(a.max_tiles) * p.HW, 1, 1};
+      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(a.max_tiles) * p.HW * g.OC, uint64_t(a.max_tiles) * p.HW * g.OC};
+      const uint32_t box[4] = {uint32_t(p.wo), uint32_t(kBM), 1, 1};
+      rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
+    } else if (one) {
+      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(p.Wd), 1, uint64_t(a.max_tiles)};
+      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(a.out_tile_stride), uint64_t(a.out_tile_stride)};
+      const uint32_t box[4] = {uint32_t(p.wo), uint32_t(p.pw), 1, uint32_t(p.pn)};
+      rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
+    } else {
+      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(g.OW), uint64_t(g.OH), uint64_t(a.max_tiles)};
+      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(g.OW) * g.OC, uint64_t(a.out_tile_stride)};
+      const uint32_t box[4] = {uint32_t(p.wo), uint32_t(p.pw), uint32_t(p.ph), uint32_t(p.pn)};
+      rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
+    }
+    if (rc < 0) return bail(rc);
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
+    const void* kernels[] = {(const void*)conv_tc_kernel,
+                             (const void*)conv_tc_fast_kernel<0>, (const void*)conv_tc_fast_kernel<1>, (const void*)conv_tc_fast_kernel<2>,
+                             (const void*)conv_tc_fast_kernel<3>, (const void*)conv_tc_fast_kernel<4>, (const void*)conv_tc_fast_kernel<5>,
+                             (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>};
+    for (const void* k : kernels) {
+      ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
+    }
     attr_set = true;
   }
   *out = c;
@@ -606,7 +1009,15 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
   const long long work = (long long)groups * p.tiles_y * tiles_x * p.n_tiles;
   const int grid = int(std::min<long long>(work, sm_count()));
-  conv_tc_kernel<<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, p, tiles);
+  if (!c->fast) {
+    conv_tc_kernel<<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, p, tiles);
+  } else {
+    switch (c->mode) {
+#define TOD_TC_CASE(M) case M: conv_tc_fast_kernel<M><<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, c->map_o, p, tiles); break;
+      TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
+#undef TOD_TC_CASE
+    }
+  }
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
 }
@@ -618,7 +1029,7 @@ using namespace tod;
 
 namespace {
 // runs one convolution through both the tcgen05 path and the CUDA-core direct kernel on random data
-int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, float* ms_tc, float* ms_direct, long long* mismatches) {
+int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, int flags, float* ms_tc, float* ms_direct, long long* mismatches) {
   TOD_TRY(select_device(device));
   ConvGeom g{};
   g.IH = g.OH = H;
@@ -638,7 +1049,7 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   for (int oc = 0; oc < OC; ++oc) {
     h_bias[oc] = int32_t(rng() % 20001) - 10000;
     int sh;
-    quantize_multiplier(eff * (0.5 + (rng() % 1000) / 1000.0), &h_mult[oc], &sh);
+    quantize_multiplier(((flags & 8) ? 0.75 : eff) * (0.5 + (rng() % 1000) / 1000.0), &h_mult[oc], &sh);
     h_shift[oc] = sh;
     for (int t = 0; t < K * K; ++t) {
       int32_t s = 0;
@@ -665,7 +1076,15 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   TOD_CUDA(cudaMemset(d_o1, 0x55, out_elems));
   TOD_CUDA(cudaMemset(d_o2, 0x33, out_elems));
   const int32_t in_zp = -3;
-  Requant rq{d_mult, d_shift, 5, -128, 127, nullptr};
+  uint8_t* d_lut = nullptr;
+  if (flags & 2) {  // a fused byte map (any permutation-free table will do)
+    uint8_t h_lut[256];
+    for (int i = 0; i < 256; ++i) h_lut[i] = uint8_t((i * 7 + 13) ^ (i >> 3));
+    TOD_CUDA(cudaMalloc(&d_lut, 256));
+    TOD_CUDA(cudaMemcpy(d_lut, h_lut, 256, cudaMemcpyHostToDevice));
+  }
+  Requant rq{d_mult, d_shift, (flags & 1) ? -128 : 5, (flags & 1) ? -128 : -128, (flags & 1) ? 90 : 127, d_lut};
+  if (flags & 16) rq.act_min = -77;
   const int64_t in_ts = int64_t(H) * W * IC, out_ts = int64_t(H) * W * OC;
   int rc = TOD_OK;
   ConvTc* plan = nullptr;
@@ -675,6 +1094,9 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   if (!conv_tc_supported(g, in_ts, d_in, d_w)) rc = fail(TOD_ERR_UNSUPPORTED, "selftest shape is not eligible for the tcgen05 path");
   if (rc == TOD_OK) {
     ConvTcArgs a{g, d_in, in_ts, d_w, in_zp, rq, d_o1, out_ts, tiles, h_bias.data(), h_wsum.data()};
+    a.h_mult = h_mult.data();
+    a.h_shift = h_shift.data();
+    a.fast_epilogue = (flags & 4) ? 0 : 1;
     rc = conv_tc_create(a, &plan);
   }
   if (rc == TOD_OK) rc = conv_tc_launch(plan, tiles, nullptr);
@@ -711,6 +1133,7 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   cudaEventDestroy(e1);
   cudaFree(d_in); cudaFree(d_w); cudaFree(d_o1); cudaFree(d_o2);
   cudaFree(d_bias); cudaFree(d_mult); cudaFree(d_shift); cudaFree(d_wsum);
+  cudaFree(d_lut);
   return rc;
 }
 }  // namespace
@@ -719,7 +1142,15 @@ extern "C" {
 
 int tod_conv_selftest(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, float* ms_tc, float* ms_direct, long long* mismatches) {
   if (tiles < 1 || H < 1 || W < 1 || IC < 1 || OC < 1 || (K != 1 && K != 3)) return fail(TOD_ERR_INVALID_ARG, "tod_conv_selftest: bad shape");
-  return conv_selftest_impl(device, tiles, H, W, IC, OC, K, iters, ms_tc, ms_direct, mismatches);
+  return conv_selftest_impl(device, tiles, H, W, IC, OC, K, iters, 0, ms_tc, ms_direct, mismatches);
+}
+
+// flags: 1 = ReLU6-style clamp (not the full int8 range), 2 = fused byte map, 4 = force the general epilogue,
+//        8 = multipliers >= 0.5 (shift 0: the planner must fall back to the general epilogue), 16 = act_min above -128
+int tod_conv_selftest_ex(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, int flags, float* ms_tc, float* ms_direct,
+                         long long* mismatches) {
+  if (tiles < 1 || H < 1 || W < 1 || IC < 1 || OC < 1 || (K != 1 && K != 3)) return fail(TOD_ERR_INVALID_ARG, "tod_conv_selftest_ex: bad shape");
+  return conv_selftest_impl(device, tiles, H, W, IC, OC, K, iters, flags, ms_tc, ms_direct, mismatches);
 }
 
 // plain GEMM C[M,N] = A[M,K] * B[N,K]^T as a 1x1 convolution over M "pixels": the int8 roofline denominator
@@ -727,7 +1158,7 @@ int tod_i8_gemm_selftest(int device, int M, int N, int K, int iters, float* ms_p
   if (M < 1 || N < 1 || K < 16) return fail(TOD_ERR_INVALID_ARG, "tod_i8_gemm_selftest: bad shape");
   long long bad = 0;
   float ms_direct = 0;
-  const int rc = conv_selftest_impl(device, 1, 1, M, K, N, 1, iters, ms_per_iter, &ms_direct, &bad);
+  const int rc = conv_selftest_impl(device, 1, 1, M, K, N, 1, iters, 0, ms_per_iter, &ms_direct, &bad);
   if (max_abs_err) *max_abs_err = double(bad);
   return rc;
 }

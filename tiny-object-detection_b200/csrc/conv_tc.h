@@ -25,6 +25,9 @@ struct ConvTcArgs {
   int max_tiles;
   const int32_t* h_bias; // host copies used to build the per-border-class bias tables (may be null)
   const int32_t* h_wsum; // host [OC][KH*KW]
+  const int32_t* h_mult = nullptr;   // host copies of rq.mult / rq.shift: the fast epilogue is planned from them
+  const int32_t* h_shift = nullptr;  // (null: general epilogue)
+  int fast_epilogue = 1;             // 0 forces the general epilogue (cross-check)
 };
 
 // shape / alignment test only (no CUDA calls)

@@ -636,7 +636,7 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
   TOD_CUDA(cudaMalloc(&y->d_const, arena.host.size() ? arena.host.size() : 256));
   TOD_CUDA(cudaMemcpy(y->d_const, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
   for (Step& st : y->steps) {
-    if (st.kind != kStepConvDirect || y->opt.conv_impl != 0) continue;
+    if (st.kind != kStepConvDirect || y->opt.conv_impl == 1) continue;  // conv_impl: 0 = tcgen05, 1 = CUDA cores only, 2 = tcgen05 with the general epilogue
     const Place& pi = y->place[st.in0];
     const Place& po = st.out_moved ? st.out_place : y->place[st.out];
     const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
@@ -654,6 +654,9 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
     a.max_tiles = y->opt.max_tiles;
     a.h_bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(arena.host.data() + st.bias_off) : nullptr;
     a.h_wsum = reinterpret_cast<const int32_t*>(arena.host.data() + st.wsum_off);
+    a.h_mult = reinterpret_cast<const int32_t*>(arena.host.data() + st.mult_off);
+    a.h_shift = reinterpret_cast<const int32_t*>(arena.host.data() + st.shift_off);
+    a.fast_epilogue = y->opt.conv_impl == 2 ? 0 : 1;
     TOD_TRY(conv_tc_create(a, &st.tc));
     st.kind = kStepConvTc;
     y->tc_layers++;
