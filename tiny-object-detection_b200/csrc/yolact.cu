@@ -34,7 +34,8 @@ enum StepKind { kStepConvDirect, kStepConvTc, kStepDepthwise, kStepAdd, kStepLut
 struct Place {   // where a tensor lives at run time
   uint8_t* base = nullptr;   // tile 0
   int64_t tile_stride = 0;   // bytes between tiles
-  int64_t bytes = 0;         // dense bytes per tile
+  int64_t bytes = 0;         // stored bytes per tile (pixels * c_store for a channel-padded tensor)
+  int c = 0, c_store = 0;    // real / stored channels per pixel (c_store > c: zero-weight padding lanes, see plan())
 };
 
 struct Step {
@@ -253,6 +254,54 @@ int plan(tod_yolact* y, ConstArena* arena) {
     }
   }
 
+  // ---- channel padding.  A 16- or 24-channel NHWC tensor cannot feed the tensor-core path as it is: TMA needs a
+  // 16-byte pixel stride, and a K chunk that is half out-of-bounds fill loads several times slower than a full one
+  // (measured: 16 -> 96 at 112x112 took 133 us against 58 us for 64 -> 96).  Such tensors, when every producer is a
+  // CONV_2D / ADD and every consumer a CONV_2D / ADD, are stored with 32 channels per pixel: the producing convolution
+  // gets zero weight rows (the extra lanes hold the output zero point), the consuming one zero weight columns, and an
+  // ADD runs over the padded buffers of all three of its tensors.  tod_yolact_fetch_tensor strips the padding.
+  std::vector<int> cstore(nt, 0);
+  for (int t = 0; t < nt; ++t) cstore[t] = G.tensors[t].dims[3];
+  {
+    std::vector<char> cand(nt, 0);
+    for (int t = 0; t < nt; ++t) {
+      const GTensor& X = G.tensors[t];
+      if (X.is_const() || X.type != kI8 || X.dims[0] != 1 || alias_of[t] >= 0 || parent[t].tensor >= 0 || producer[t] < 0) continue;
+      const int C = X.dims[3];
+      if (!(C % 16 != 0 || C == 16) || C > 256) continue;
+      if (std::find(G.outputs.begin(), G.outputs.end(), t) != G.outputs.end()) continue;
+      const int pc = G.ops[producer[t]].code;
+      cand[t] = (pc == kConv2D || pc == kAdd) ? 1 : 0;
+    }
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (const GOp& op : G.ops) {
+        bool touches = false;
+        for (int t : op.inputs) touches |= (t >= 0 && cand[t]);
+        for (int t : op.outputs) touches |= (cand[t] != 0);
+        if (!touches) continue;
+        bool ok = true;
+        if (op.code == kConv2D) {
+          // only the activation input / output may be padded (weights and bias are constants, never candidates)
+          ok = op.stride_h == 1 && op.stride_w == 1;
+        } else if (op.code == kAdd) {
+          ok = cand[op.inputs[0]] && cand[op.inputs[1]] && cand[op.outputs[0]] &&
+               G.tensors[op.inputs[0]].dims[3] == G.tensors[op.outputs[0]].dims[3] && G.tensors[op.inputs[1]].dims[3] == G.tensors[op.outputs[0]].dims[3];
+        } else {
+          ok = false;
+        }
+        if (ok) continue;
+        for (int t : op.inputs)
+          if (t >= 0 && cand[t]) { cand[t] = 0; changed = true; }
+        for (int t : op.outputs)
+          if (cand[t]) { cand[t] = 0; changed = true; }
+      }
+    }
+    for (int t = 0; t < nt; ++t)
+      if (cand[t]) cstore[t] = int(round_up(G.tensors[t].dims[3], 32));
+  }
+
   // ---- activation arena: one block per root storage, [max_tiles][stride]
   std::vector<int64_t> root_off(nt, -1), root_stride(nt, 0);
   int64_t total = 0;
@@ -264,7 +313,7 @@ int plan(tod_yolact* y, ConstArena* arena) {
     if (X.dims[0] != 1) return fail(TOD_ERR_UNSUPPORTED, "tensor '%s' has batch %d; the model must be exported with batch 1", X.name.c_str(), X.dims[0]);
     // tile stride = dense size rounded to 16 B (what TMA needs): NHWC tensors with C % 16 == 0 stay dense, so a
     // 1x1 convolution over the whole batch is one flat GEMM
-    root_stride[t] = round_up(X.elems() * X.elem_size(), 16);
+    root_stride[t] = round_up(X.elems() / std::max(1, X.dims[3]) * cstore[t] * X.elem_size(), 16);
     root_off[t] = total;
     total = round_up(total + root_stride[t] * mt, 1024);
   }
@@ -282,23 +331,10 @@ int plan(tod_yolact* y, ConstArena* arena) {
       s = storage(parent[s].tensor);
     }
     if (root_off[s] < 0) continue;
-    y->place[t] = Place{y->d_act + root_off[s] + off, root_stride[s], X.elems() * X.elem_size()};
+    y->place[t] = Place{y->d_act + root_off[s] + off, root_stride[s], X.elems() / std::max(1, X.dims[3]) * cstore[t] * X.elem_size(), X.dims[3], cstore[t]};
   }
 
   // ---- steps
-  auto requant_tables = [&](const GTensor& I, const GTensor& Wt, const GTensor& O, int channels, Step* st) {
-    std::vector<int32_t> q(channels), sh(channels);
-    for (int c = 0; c < channels; ++c) {
-      const float ws = Wt.scales.size() > 1 ? Wt.scales[c] : Wt.scale();
-      const double eff = double(I.scale()) * double(ws) / double(O.scale());
-      int s = 0;
-      quantize_multiplier(eff, &q[c], &s);
-      sh[c] = s;
-    }
-    st->mult_off = arena->add(q.data(), q.size() * 4);
-    st->shift_off = arena->add(sh.data(), sh.size() * 4);
-  };
-
   std::vector<bool> pad_folded(G.ops.size(), false);
   for (size_t i = 0; i < G.ops.size(); ++i) {
     const GOp& op = G.ops[i];
@@ -358,29 +394,59 @@ int plan(tod_yolact* y, ConstArena* arena) {
         st.in_zp = I->zp();
         st.out_zp = O.zp();
         activation_range(op.activation, O, &st.act_min, &st.act_max);
-        requant_tables(*I, Wt, O, g.OC, &st);
-        st.w_off = arena->add(Wt.const_data, Wt.const_bytes);
-        if (bias_t >= 0) {
-          const GTensor& B = G.tensors[bias_t];
-          if (!B.is_const() || B.type != kI32 || B.elems() != g.OC) return fail(TOD_ERR_UNSUPPORTED, "conv operator %zu: bias must be constant int32[OC]", i);
-          st.bias_off = arena->add(B.const_data, B.const_bytes);
+        const int ICr = g.IC, OCr = g.OC;                       // real channel counts
+        const int ICs = dw ? ICr : cstore[src], OCs = dw ? OCr : cstore[op.outputs[0]];  // stored (padded) ones
+        const int taps = g.KH * g.KW;
+        {
+          // requantisation tables; padding lanes copy channel 0's constants so a layer stays eligible for the fast epilogue
+          std::vector<int32_t> q(OCs), sh(OCs);
+          for (int c = 0; c < OCs; ++c) {
+            const int cr = c < OCr ? c : 0;
+            const float ws = Wt.scales.size() > 1 ? Wt.scales[cr] : Wt.scale();
+            const double eff = double(I->scale()) * double(ws) / double(O.scale());
+            int sft = 0;
+            quantize_multiplier(eff, &q[c], &sft);
+            sh[c] = sft;
+          }
+          st.mult_off = arena->add(q.data(), q.size() * 4);
+          st.shift_off = arena->add(sh.data(), sh.size() * 4);
+        }
+        const int8_t* w_real = reinterpret_cast<const int8_t*>(Wt.const_data);
+        std::vector<int8_t> w_pad;
+        if (ICs != ICr || OCs != OCr) {  // OHWI with zero columns / rows for the padding lanes
+          w_pad.assign(size_t(OCs) * taps * ICs, 0);
+          for (int oc = 0; oc < OCr; ++oc)
+            for (int tp = 0; tp < taps; ++tp)
+              std::memcpy(&w_pad[(size_t(oc) * taps + tp) * ICs], w_real + (size_t(oc) * taps + tp) * ICr, size_t(ICr));
+          st.w_off = arena->add(w_pad.data(), w_pad.size());
+        } else {
+          st.w_off = arena->add(Wt.const_data, Wt.const_bytes);
+        }
+        if (bias_t >= 0 || OCs != OCr) {
+          std::vector<int32_t> b(OCs, 0);
+          if (bias_t >= 0) {
+            const GTensor& B = G.tensors[bias_t];
+            if (!B.is_const() || B.type != kI32 || B.elems() != OCr) return fail(TOD_ERR_UNSUPPORTED, "conv operator %zu: bias must be constant int32[OC]", i);
+            std::memcpy(b.data(), B.const_data, size_t(OCr) * 4);
+          }
+          st.bias_off = arena->add(b.data(), b.size() * 4);
         }
         if (dw) {
           st.kind = kStepDepthwise;
           st.macs = int64_t(OH) * OW * g.OC * g.KH * g.KW;
         } else {
           st.kind = kStepConvDirect;
-          const int taps = g.KH * g.KW;
-          std::vector<int32_t> wsum(size_t(g.OC) * taps, 0);
-          const int8_t* w = reinterpret_cast<const int8_t*>(Wt.const_data);
-          for (int oc = 0; oc < g.OC; ++oc)
+          std::vector<int32_t> wsum(size_t(OCs) * taps, 0);
+          for (int oc = 0; oc < OCr; ++oc)
             for (int tp = 0; tp < taps; ++tp) {
-              int32_t s = 0;
-              for (int ic = 0; ic < g.IC; ++ic) s += w[(size_t(oc) * taps + tp) * g.IC + ic];
-              wsum[size_t(oc) * taps + tp] = s;
+              int32_t sm = 0;
+              for (int ic = 0; ic < ICr; ++ic) sm += w_real[(size_t(oc) * taps + tp) * ICr + ic];
+              wsum[size_t(oc) * taps + tp] = sm;
             }
           st.wsum_off = arena->add(wsum.data(), wsum.size() * 4);
-          st.macs = int64_t(OH) * OW * g.OC * taps * g.IC;
+          st.macs = int64_t(OH) * OW * OCr * taps * ICr;
+          st.g.IC = ICs;
+          st.g.OC = OCs;
         }
         break;
       }
@@ -930,6 +996,13 @@ int run_pipeline(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
 }
 
 int fetch_strided(void* dst, const Place& p, int n, cudaStream_t s) {
+  if (p.c_store != p.c && p.c > 0) {  // channel-padded storage: copy the real channels of every pixel
+    const size_t pixels = size_t(p.bytes / p.c_store);
+    for (int t = 0; t < n; ++t)
+      TOD_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t*>(dst) + size_t(t) * pixels * p.c, size_t(p.c), p.base + size_t(t) * p.tile_stride, size_t(p.c_store),
+                                 size_t(p.c), pixels, cudaMemcpyDeviceToHost, s));
+    return TOD_OK;
+  }
   TOD_CUDA(cudaMemcpy2DAsync(dst, size_t(p.bytes), p.base, size_t(p.tile_stride), size_t(p.bytes), size_t(n), cudaMemcpyDeviceToHost, s));
   return TOD_OK;
 }
@@ -1164,7 +1237,8 @@ int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t 
   if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: n=%d but the last call ran %d tiles", n, y->last_tiles);
   const Place& p = y->place[tensor];
   if (!p.base) return fail(TOD_ERR_INVALID_ARG, "tensor %d is a constant or is not materialised", tensor);
-  if (out_bytes < size_t(p.bytes) * n) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: buffer too small (%zu < %lld)", out_bytes, (long long)(p.bytes * n));
+  const int64_t real_bytes = p.c_store > 0 ? p.bytes / p.c_store * p.c : p.bytes;
+  if (out_bytes < size_t(real_bytes) * n) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: buffer too small (%zu < %lld)", out_bytes, (long long)(real_bytes * n));
   if (!y->fused_away.empty() && y->fused_away[tensor])
     return fail(TOD_ERR_INVALID_ARG, "tensor %d is fused into the producing convolution's epilogue; create the handle with fusion = 0 to fetch it", tensor);
   // a PAD folded into its convolution is never written
