@@ -43,3 +43,13 @@ def test_conv_tc_epilogue_variants(tod, shape, flags):
     from tod_b200 import _lib
     ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=1, flags=flags)
     assert bad == 0, "%d bytes differ with epilogue flags %d" % (bad, flags)
+
+
+# stride-2 3x3 (FPN P6 / P7 down-samplers): the A box walks the input with TMA element strides
+@pytest.mark.parametrize("shape", [(9, 7, 7, 256, 256, 3), (33, 4, 4, 256, 256, 3), (2, 15, 15, 64, 32, 3), (3, 28, 28, 32, 48, 3)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("flags", [32, 32 | 1, 32 | 4], ids=["s2", "s2-clamp", "s2-general"])
+def test_conv_tc_stride2(tod, shape, flags):
+    from tod_b200 import _lib
+    ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=1, flags=flags)
+    assert bad == 0, "%d bytes differ (stride 2, flags %d)" % (bad, flags)

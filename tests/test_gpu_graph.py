@@ -17,7 +17,7 @@ def _oracle_run(path, tile):
     return m
 
 
-@pytest.mark.parametrize("conv_impl", [1, 0])
+@pytest.mark.parametrize("conv_impl", [1, 0, 2])
 def test_small_model_every_tensor(tod, models, conv_impl):
     _, small = models
     tiles = synth.rgb_tiles(3, S=64, seed=31)
@@ -34,7 +34,7 @@ def test_small_model_every_tensor(tod, models, conv_impl):
                 t, op, m.op_code(op), ti, (got.reshape(-1) != want.reshape(-1)).sum(), want.size)
 
 
-@pytest.mark.parametrize("conv_impl", [1, 0])
+@pytest.mark.parametrize("conv_impl", [1, 0, 2])
 def test_full_model_outputs(tod, models, conv_impl):
     full, _ = models
     tiles = synth.rgb_tiles(2, seed=32)

@@ -47,6 +47,7 @@ struct TcParams {
   int tiles_x, tiles_y;
   int KW, taps, kchunks, BK, BN, n_tiles;
   int KH, pad_top, pad_left, IH, IW;
+  int stride;                  // 1 or 2 (both axes): the A box walks the input with TMA element strides
   int stages;
   int flat, HW;
   const int32_t* bias_eff;     // [classes][OCp]
@@ -70,6 +71,11 @@ struct TcParams {
   uint8_t ymap[8], xmap[8];
   int wo;                      // TMA-store staging row bytes (16 / 32 / 64 / 128), 0 = manual stores
   uint32_t stage_bytes;        // shared memory reserved for output staging
+  // ---- fused residual ADD (kEpiAdd): out = requant_out(tab[conv byte] + tab[256 + residual byte])
+  const int8_t* resid;         // same geometry as the output
+  long long resid_ts;
+  const int32_t* add_tab;      // device [512]: conv-side table, then residual-side table (terms rescaled to 2^20 fixed point)
+  int32_t add_mult, add_shift, add_zp, add_min, add_max;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -170,6 +176,7 @@ struct SmemCtl {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint8_t lut[256];
+  int32_t add_tab[512];
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -232,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
-            tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 + fx - p.pad_left, y0 + fy - p.pad_top, n0);
+            tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left, y0 * p.stride + fy - p.pad_top, n0);
             tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, n_tile * p.BN);
             if (++stage == p.stages) {
               stage = 0;
@@ -309,11 +316,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         int ymask = 0, xmask = 0;
         for (int f = 0; f < p.KH; ++f) {
-          const int iy = py + f - p.pad_top;
+          const int iy = py * p.stride + f - p.pad_top;
           ymask |= (iy >= 0 && iy < p.IH) ? (1 << f) : 0;
         }
         for (int f = 0; f < p.KW; ++f) {
-          const int ix = px + f - p.pad_left;
+          const int ix = px * p.stride + f - p.pad_left;
           xmask |= (ix >= 0 && ix < p.IW) ? (1 << f) : 0;
         }
         cls = ymask * (1 << p.KW) + xmask;
@@ -408,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   * a full-range clamp is the saturation of cvt.pack.sat.s8.s32;
 //   * requantised bytes go to a swizzled staging tile and leave with ONE TMA store per 128-column pass (the TMA unit
 //     clips rows / columns outside the tensor), double-buffered so a pass needs a single CTA-wide barrier.
-enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4 };
+enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4, kEpiAdd = 8 };
 
 struct WorkItem { int n_tile, tx, ty, g; };
 __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles_x, int tiles_y) {
@@ -467,6 +474,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
   for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
   if ((MODE & kEpiLut) && threadIdx.x >= 128) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
+  if (MODE & kEpiAdd)
+    for (int i = threadIdx.x; i < 512; i += kTcThreads) ctl->add_tab[i] = p.add_tab[i];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -491,7 +500,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
-            tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 + fx - p.pad_left, y0 + fy - p.pad_top, n0);
+            tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left, y0 * p.stride + fy - p.pad_top, n0);
             tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, w.n_tile * p.BN);
             if (++stage == p.stages) {
               stage = 0;
@@ -557,11 +566,11 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.ncls > 1) {  // border class of this pixel: which filter rows / columns are inside the image
         int ymask = 0, xmask = 0;
         for (int f = 0; f < p.KH; ++f) {
-          const int iy = yy + f - p.pad_top;
+          const int iy = yy * p.stride + f - p.pad_top;
           ymask |= (iy >= 0 && iy < p.IH) ? (1 << f) : 0;
         }
         for (int f = 0; f < p.KW; ++f) {
-          const int ix = x + f - p.pad_left;
+          const int ix = x * p.stride + f - p.pad_left;
           xmask |= (ix >= 0 && ix < p.IW) ? (1 << f) : 0;
         }
         cls = int(p.ymap[ymask & 7]) * p.ncls_x + int(p.xmap[xmask & 7]);
@@ -574,6 +583,11 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         s_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
       }
       const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
+      const int8_t* rrow = nullptr;                   // this pixel's residual bytes (kEpiAdd)
+      if (MODE & kEpiAdd) {
+        const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
+        if (valid) rrow = p.resid + (p.flat ? 0ll : (long long)n * p.resid_ts) + ((long long)yy * Wd + x) * p.OC + ocb;
+      }
 
       mbar_wait(&ctl->acc_full[as], use & 1);
       tc_fence_after();
@@ -585,6 +599,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int c0 = half * 16; c0 < pass_cols; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + pass0 + c0, v);
+          uint4 rres = make_uint4(0u, 0u, 0u, 0u);
+          if ((MODE & kEpiAdd) && rrow) rres = *reinterpret_cast<const uint4*>(rrow + pass0 + c0);
           tmem_wait_ld();
           uint32_t packed[4];
 #pragma unroll
@@ -601,7 +617,17 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
               o[j] = (t + (x2 >> 31)) >> k.y;  // sign(x2) == sign(v) wherever the rounding term can matter
             }
-            if ((MODE & kEpiSat) && !(MODE & kEpiLut)) {
+            if (MODE & kEpiAdd) {
+              const uint32_t rw = q4 == 0 ? rres.x : (q4 == 1 ? rres.y : (q4 == 2 ? rres.z : rres.w));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (!(MODE & kEpiSat)) o[j] = max(p.act_min, min(p.act_max, o[j]));
+                else o[j] = max(-128, min(127, o[j]));
+                const int sum = ctl->add_tab[o[j] & 0xFF] + ctl->add_tab[256 + ((rw >> (8 * j)) & 0xFFu)];
+                o[j] = max(p.add_min, min(p.add_max, mul_by_quant_mult_fast(sum, p.add_mult, p.add_shift) + p.add_zp));
+              }
+              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+            } else if ((MODE & kEpiSat) && !(MODE & kEpiLut)) {
               packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
             } else {
 #pragma unroll
@@ -677,7 +703,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int encode(CUtensorMap* map, const void* base_c, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk) {
+int encode(CUtensorMap* map, const void* base_c, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk,
+           const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   void* base = const_cast<void*>(base_c);
   if (!fn) return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -687,7 +714,7 @@ int encode(CUtensorMap* map, const void* base_c, int rank, const uint64_t* dims,
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   const CUtensorMapSwizzle sw = bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -717,6 +744,7 @@ struct ConvTc {
   TcParams p{};
   int32_t *d_bias_eff = nullptr, *d_mult = nullptr, *d_shift = nullptr, *d_b2 = nullptr;
   int4* d_qtab = nullptr;
+  int32_t* d_add_tab = nullptr;
   size_t smem_bytes = 0;
   int max_tiles = 0;
   int fast = 0;        // conv_tc_fast_kernel is eligible
@@ -724,14 +752,11 @@ struct ConvTc {
 };
 
 bool conv_tc_supported(const ConvGeom& g, int64_t in_ts, const void* in, const void* w) {
-  if (g.stride_h != 1 || g.stride_w != 1 || g.dil_h != 1 || g.dil_w != 1) return false;
+  if (g.stride_h != g.stride_w || (g.stride_h != 1 && g.stride_h != 2) || g.dil_h != 1 || g.dil_w != 1) return false;
+  if (g.stride_h == 2 && !(g.KH == 3 && g.KW == 3)) return false;
   if (!((g.KH == 1 && g.KW == 1) || (g.KH == 3 && g.KW == 3))) return false;
   if (g.IC % 16 != 0 || g.IC < 16) return false;
-  if (g.OH != g.IH || g.OW != g.IW) {
-    // stride-1 VALID (no padding) shrinks the output; the patch tiling assumes output == input extent only for
-    // addressing the *output*, and input coordinates are derived per tap, so this is fine as long as pads >= 0
-    if (g.OH > g.IH || g.OW > g.IW) return false;
-  }
+  if (g.OH > g.IH || g.OW > g.IW) return false;  // input coordinates are derived per tap from the output pixel
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (in_ts & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return false;
   if (g.OW > 100000 || g.OH > 100000) return false;
   return true;
@@ -744,6 +769,7 @@ void conv_tc_destroy(ConvTc* c) {
   cudaFree(c->d_shift);
   cudaFree(c->d_b2);
   cudaFree(c->d_qtab);
+  cudaFree(c->d_add_tab);
   delete c;
 }
 
@@ -765,6 +791,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.pad_left = g.pad_left;
   p.IH = g.IH;
   p.IW = g.IW;
+  p.stride = g.stride_h;
   p.BK = (g.IC % 128 == 0) ? 128 : ((g.IC % 64 == 0) ? 64 : 32);
   p.kchunks = (g.IC + p.BK - 1) / p.BK;
   p.n_tiles = (g.OC + 255) / 256;
@@ -775,7 +802,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.HW = g.OH * g.OW;
   const bool one = g.KH == 1 && g.KW == 1;
   const bool dense = a.in_tile_stride == int64_t(g.IH) * g.IW * g.IC && a.out_tile_stride == int64_t(g.OH) * g.OW * g.OC && g.IH == g.OH && g.IW == g.OW;
-  p.flat = (one && dense) ? 1 : 0;
+  p.flat = (one && dense && g.stride_h == 1) ? 1 : 0;
   if (p.flat) {
     p.Wd = 0;  // runtime: tiles * HW
     p.Hd = 1;
@@ -850,12 +877,12 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   } else {
     for (int oy = 0; oy < g.OH; ++oy) {
       int m = 0;
-      for (int f = 0; f < g.KH; ++f) m |= (oy + f - g.pad_top >= 0 && oy + f - g.pad_top < g.IH) ? (1 << f) : 0;
+      for (int f = 0; f < g.KH; ++f) m |= (oy * g.stride_h + f - g.pad_top >= 0 && oy * g.stride_h + f - g.pad_top < g.IH) ? (1 << f) : 0;
       if (std::find(ymasks.begin(), ymasks.end(), m) == ymasks.end()) ymasks.push_back(m);
     }
     for (int ox = 0; ox < g.OW; ++ox) {
       int m = 0;
-      for (int f = 0; f < g.KW; ++f) m |= (ox + f - g.pad_left >= 0 && ox + f - g.pad_left < g.IW) ? (1 << f) : 0;
+      for (int f = 0; f < g.KW; ++f) m |= (ox * g.stride_w + f - g.pad_left >= 0 && ox * g.stride_w + f - g.pad_left < g.IW) ? (1 << f) : 0;
       if (std::find(xmasks.begin(), xmasks.end(), m) == xmasks.end()) xmasks.push_back(m);
     }
   }
@@ -872,7 +899,10 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     if (a.rq.act_min == -128 && a.rq.act_max == 127) c->mode |= kEpiSat;
     if (a.rq.post_lut) c->mode |= kEpiLut;
     if (p.vec_store) c->mode |= kEpiTma;
+    if (a.add) c->mode |= kEpiAdd;
   }
+  if (a.add && (!c->fast || (c->mode & kEpiLut) || !p.vec_store))
+    return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: a fused residual ADD needs the fast epilogue, 16-byte rows and no byte map"));
   if (c->mode & kEpiTma) {
     const int width = std::min(p.BN, 128);
     p.wo = width <= 16 ? 16 : (width <= 32 ? 32 : (width <= 64 ? 64 : 128));
@@ -927,6 +957,18 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     p.qtab = c->d_qtab;
     p.b2tab = c->d_b2;
   }
+  if (a.add) {
+    if ((ce = cudaMalloc(&c->d_add_tab, 512 * 4)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
+    cudaMemcpy(c->d_add_tab, a.add->tab, 512 * 4, cudaMemcpyHostToDevice);
+    p.add_tab = c->d_add_tab;
+    p.resid = a.add->resid;
+    p.resid_ts = a.add->resid_tile_stride;
+    p.add_mult = a.add->mult_out;
+    p.add_shift = a.add->shift_out;
+    p.add_zp = a.add->zp_out;
+    p.add_min = a.add->act_min;
+    p.add_max = a.add->act_max;
+  }
   if ((ce = cudaMalloc(&c->d_bias_eff, be.size() * 4)) != cudaSuccess || (ce = cudaMalloc(&c->d_mult, mu.size() * 4)) != cudaSuccess ||
       (ce = cudaMalloc(&c->d_shift, sh.size() * 4)) != cudaSuccess)
     return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
@@ -954,8 +996,11 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   } else {
     const uint64_t dims[4] = {uint64_t(g.IC), uint64_t(g.IW), uint64_t(g.IH), uint64_t(a.max_tiles)};
     const uint64_t str[3] = {uint64_t(g.IC), uint64_t(g.IW) * g.IC, uint64_t(a.in_tile_stride)};
-    const uint32_t box[4] = {uint32_t(p.BK), uint32_t(p.pw), uint32_t(p.ph), uint32_t(p.pn)};
-    rc = encode(&c->map_a, const_cast<int8_t*>(a.in), 4, dims, str, box, p.BK);
+    const uint32_t sd = uint32_t(p.stride);
+    const uint32_t box[4] = {uint32_t(p.BK), uint32_t(p.pw) * sd, uint32_t(p.ph) * sd, uint32_t(p.pn)};
+    const uint32_t es[4] = {1, sd, sd, 1};
+    if (box[1] > 256 || box[2] > 256) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: strided patch exceeds the TMA box limit"));
+    rc = encode(&c->map_a, const_cast<int8_t*>(a.in), 4, dims, str, box, p.BK, es);
   }
   if (rc < 0) return bail(rc);
   {
@@ -991,7 +1036,8 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     const void* kernels[] = {(const void*)conv_tc_kernel,
                              (const void*)conv_tc_fast_kernel<0>, (const void*)conv_tc_fast_kernel<1>, (const void*)conv_tc_fast_kernel<2>,
                              (const void*)conv_tc_fast_kernel<3>, (const void*)conv_tc_fast_kernel<4>, (const void*)conv_tc_fast_kernel<5>,
-                             (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>};
+                             (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>,
+                             (const void*)conv_tc_fast_kernel<12>, (const void*)conv_tc_fast_kernel<13>};
     for (const void* k : kernels) {
       ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
@@ -1015,6 +1061,8 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
     switch (c->mode) {
 #define TOD_TC_CASE(M) case M: conv_tc_fast_kernel<M><<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, c->map_o, p, tiles); break;
       TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
+      TOD_TC_CASE(12) TOD_TC_CASE(13)
+      default: return fail(TOD_ERR_UNSUPPORTED, "conv_tc: no kernel for epilogue mode %u", c->mode);
 #undef TOD_TC_CASE
     }
   }
@@ -1032,14 +1080,19 @@ namespace {
 int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, int flags, float* ms_tc, float* ms_direct, long long* mismatches) {
   TOD_TRY(select_device(device));
   ConvGeom g{};
-  g.IH = g.OH = H;
-  g.IW = g.OW = W;
+  const int sd = (flags & 32) ? 2 : 1;
+  g.IH = H;
+  g.IW = W;
+  g.OH = (H + sd - 1) / sd;
+  g.OW = (W + sd - 1) / sd;
   g.IC = IC;
   g.OC = OC;
   g.KH = g.KW = K;
-  g.stride_h = g.stride_w = g.dil_h = g.dil_w = 1;
-  g.pad_top = g.pad_left = K / 2;
-  const size_t in_elems = size_t(tiles) * H * W * IC, out_elems = size_t(tiles) * H * W * OC, w_elems = size_t(OC) * K * K * IC;
+  g.stride_h = g.stride_w = sd;
+  g.dil_h = g.dil_w = 1;
+  g.pad_top = std::max(0, (g.OH - 1) * sd + K - H) / 2;   // TFLite SAME
+  g.pad_left = std::max(0, (g.OW - 1) * sd + K - W) / 2;
+  const size_t in_elems = size_t(tiles) * H * W * IC, out_elems = size_t(tiles) * g.OH * g.OW * OC, w_elems = size_t(OC) * K * K * IC;
   std::mt19937 rng(1234);
   std::vector<int8_t> h_in(in_elems), h_w(w_elems);
   for (auto& v : h_in) v = int8_t(int(rng() % 255) - 127);
@@ -1085,7 +1138,7 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
   }
   Requant rq{d_mult, d_shift, (flags & 1) ? -128 : 5, (flags & 1) ? -128 : -128, (flags & 1) ? 90 : 127, d_lut};
   if (flags & 16) rq.act_min = -77;
-  const int64_t in_ts = int64_t(H) * W * IC, out_ts = int64_t(H) * W * OC;
+  const int64_t in_ts = int64_t(H) * W * IC, out_ts = int64_t(g.OH) * g.OW * OC;
   int rc = TOD_OK;
   ConvTc* plan = nullptr;
   cudaEvent_t e0, e1;

@@ -13,6 +13,16 @@ namespace tod {
 
 struct ConvTc;  // one planned layer (tensor maps, epilogue tables)
 
+// A residual / FPN ADD fused behind the convolution: out = clamp(rescale_out(tab[conv byte] + tab[256 + other byte]) + zp).
+// The two 256-entry tables hold each input's term already rescaled to the common 2^20 fixed point with the literal
+// TFLite arithmetic (index = the int8 byte pattern), exactly what ops.cu::add_kernel tabulates per CTA.
+struct ConvTcAdd {
+  const int8_t* resid;        // device, the ADD's other input, same geometry and tile stride rules as the output
+  int64_t resid_tile_stride;
+  int32_t tab[512];
+  int32_t mult_out, shift_out, zp_out, act_min, act_max;
+};
+
 struct ConvTcArgs {
   ConvGeom g;
   const int8_t* in;      // device, [tile][IH][IW][IC]
@@ -28,6 +38,7 @@ struct ConvTcArgs {
   const int32_t* h_mult = nullptr;   // host copies of rq.mult / rq.shift: the fast epilogue is planned from them
   const int32_t* h_shift = nullptr;  // (null: general epilogue)
   int fast_epilogue = 1;             // 0 forces the general epilogue (cross-check)
+  const ConvTcAdd* add = nullptr;    // fused ADD (requires the fast epilogue + TMA-storable output)
 };
 
 // shape / alignment test only (no CUDA calls)

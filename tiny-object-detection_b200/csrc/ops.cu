@@ -6,6 +6,8 @@
 // interpreter.invoke() (/root/reference/src/yolact.rs:163).
 #include "ops.h"
 
+#include <algorithm>
+
 #include "fixedpoint.cuh"
 
 namespace tod {
@@ -355,6 +357,119 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
   }
 }
 
+// ------------------------------------------------------------------ depthwise 3x3, sliding window
+// Thread = one 4-channel word of one output column, walking down a run of output rows.  The (column, channel word)
+// pair is a flattened index along the NHWC row, so consecutive lanes read consecutive words whatever C is.  The
+// 3x3 input window lives in nine registers and slides vertically: a stride-1 row costs three new words (two rows of
+// three for stride 2) instead of nine.  Out-of-image taps read as the input zero point, which makes their
+// (in - zp) * w term vanish with the bias pre-folded as bias - zp * sum(w): no branches in the arithmetic.
+// Requantisation is the 4-instruction form of Requant::fast_tab.
+constexpr int kDwThreads = 128;
+
+template <int STRIDE, bool SAT>
+__global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                                       const int8_t* __restrict__ w,
+                                                                       const int32_t* __restrict__ bias, int32_t in_zp,
+                                                                       ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                                       int64_t out_ts, int rows_per_block) {
+  const int C = g.OC, CW = C >> 2;
+  const int j = blockIdx.x * kDwThreads + threadIdx.x;
+  if (j >= g.OW * CW) return;
+  const int ox = j / CW, c = (j - ox * CW) * 4;
+  int wm[9][4];
+  int wall[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const int wv = __ldg(reinterpret_cast<const int*>(w + int64_t(tp) * C + c));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      wm[tp][q] = wv & (0xFF << (8 * q));
+      wall[q] += (wv << (24 - 8 * q)) >> 24;
+    }
+  }
+  int4 k[4];
+  int bs[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    k[q] = __ldg(rq.fast_tab + c + q);
+    bs[q] = (bias ? __ldg(bias + c + q) : 0) - in_zp * wall[q];
+  }
+  const int zp4 = (in_zp & 0xFF) * 0x01010101;
+  const int ix0 = ox * STRIDE - g.pad_left;
+  const bool vx0 = ix0 >= 0 && ix0 < g.IW, vx1 = ix0 + 1 >= 0 && ix0 + 1 < g.IW, vx2 = ix0 + 2 >= 0 && ix0 + 2 < g.IW;
+  const int8_t* base = in + int64_t(blockIdx.z) * in_ts + int64_t(ix0) * C + c;
+  auto load_row = [&](int iy, int& a0, int& a1, int& a2) {
+    a0 = a1 = a2 = zp4;
+    if (iy >= 0 && iy < g.IH) {
+      const int8_t* p = base + int64_t(iy) * g.IW * C;
+      if (vx0) a0 = *reinterpret_cast<const int*>(p);
+      if (vx1) a1 = *reinterpret_cast<const int*>(p + C);
+      if (vx2) a2 = *reinterpret_cast<const int*>(p + 2 * C);
+    }
+  };
+  const int oy0 = blockIdx.y * rows_per_block, oy1 = min(g.OH, oy0 + rows_per_block);
+  int r0[3], r1[3], r2[3], n1[3], n2[3];
+  int iy = oy0 * STRIDE - g.pad_top;
+  load_row(iy, r0[0], r0[1], r0[2]);
+  load_row(iy + 1, r1[0], r1[1], r1[2]);
+  load_row(iy + 2, r2[0], r2[1], r2[2]);
+  int8_t* op = out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c;
+  for (int oy = oy0; oy < oy1; ++oy, iy += STRIDE, op += int64_t(g.OW) * C) {
+    // the next output row's new input rows are requested before this row's arithmetic (software pipelining)
+    if (oy + 1 < oy1) {
+      if (STRIDE == 1) {
+        load_row(iy + 3, n2[0], n2[1], n2[2]);
+      } else {
+        load_row(iy + 3, n1[0], n1[1], n1[2]);
+        load_row(iy + 4, n2[0], n2[1], n2[2]);
+      }
+    }
+    int acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int a = bs[q];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        a = __dp4a(r0[f], wm[f][q], a);
+        a = __dp4a(r1[f], wm[3 + f][q], a);
+        a = __dp4a(r2[f], wm[6 + f][q], a);
+      }
+      acc[q] = a;
+    }
+    int o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int x2 = acc[q] * 2;
+      const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k[q].w)) << 32) | uint32_t(k[q].z));
+      const int t = int((static_cast<long long>(x2) * k[q].x + addend) >> 32);
+      o[q] = (t + (x2 >> 31)) >> k[q].y;
+    }
+    unsigned packed;
+    if (SAT) {
+      unsigned hi;
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o[3]), "r"(o[2]), "r"(0u));
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(packed) : "r"(o[1]), "r"(o[0]), "r"(hi));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = max(rq.act_min, min(rq.act_max, o[q]));
+      packed = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
+    }
+    *reinterpret_cast<unsigned*>(op) = packed;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      if (STRIDE == 1) {
+        r0[f] = r1[f];
+        r1[f] = r2[f];
+        r2[f] = n2[f];
+      } else {
+        r0[f] = r2[f];
+        r1[f] = n1[f];
+        r2[f] = n2[f];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ ADD (residual / FPN merge)
 // The two input rescales depend on one byte each, so they are tabulated per CTA (256 entries each, built with
 // the literal arithmetic); the output rescale uses the fast exact form (|ya + yb| < 2^29).
@@ -589,6 +704,25 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
   const bool vec = (g.OC % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0) && (in_ts % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (out_ts % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(w) & 3) == 0);
+  if (vec && rq.fast_tab && !rq.post_lut && g.KH == 3 && g.KW == 3 && g.dil_h == 1 && g.dil_w == 1 && g.stride_h == g.stride_w &&
+      (g.stride_h == 1 || g.stride_h == 2) && tiles <= 65535) {
+    const int words = g.OW * (g.OC / 4);
+    const int gx = (words + kDwThreads - 1) / kDwThreads;
+    // rows per block: long enough to amortise the two warm-up rows, short enough for >= ~4 CTAs per SM
+    int rpb = g.OH;
+    while (rpb > 4 && int64_t(gx) * ((g.OH + rpb - 1) / rpb) * tiles < 148 * 8) rpb = (rpb + 1) / 2;
+    rpb = std::min(rpb, 16);
+    dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
+    const bool sat = rq.act_min == -128 && rq.act_max == 127;
+    if (g.stride_h == 1) {
+      if (sat) depthwise3x3_slide_kernel<1, true><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      else depthwise3x3_slide_kernel<1, false><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+    } else {
+      if (sat) depthwise3x3_slide_kernel<2, true><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      else depthwise3x3_slide_kernel<2, false><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+    }
+    return;
+  }
   if (vec && g.KH == 3 && g.KW == 3 && g.dil_h == 1 && g.dil_w == 1 && int64_t(tiles) * g.OH * g.OW < (int64_t(1) << 31)) {
     const int cg = g.OC / 4;
     const int bx = cg >= 32 ? 32 : cg;

@@ -20,6 +20,9 @@ struct Requant {          // per-output-channel fixed point requantisation + act
   const int32_t* shift;   // [OC] exponent (<= 0: right shift)
   int32_t out_zp, act_min, act_max;
   const uint8_t* post_lut;  // optional 256-entry byte map applied to the requantised byte (fused QUANTIZE / RELU / TANH chain)
+  // optional [OC] {q, rs, 0x80000000, (1 << (rs-1)) + (out_zp << rs)}: present when every channel has shift in [-22,-1]
+  // and q >= 0, so  out = (hi32(2*acc*q + 2^31 + (w << 32)) + (acc >> 31)) >> rs  equals the reference form
+  const int4* fast_tab = nullptr;
 };
 
 // CONV_2D, any geometry.  w: [OC][KH][KW][IC] int8.  bias: [OC] int32 (may be null).

@@ -266,14 +266,31 @@ __device__ __forceinline__ float iou_rn(const float4 a, const float4 b) {
   return uni > 0.f ? __fdiv_rn(inter, uni) : 0.f;
 }
 
+// `iou_rn(a, b) > thresh` without the division in all but the borderline cases: fl(inter / uni) > t is implied by
+// inter > t * uni * (1 + 4e-7) and excluded by inter < t * uni * (1 - 4e-7) (the margins cover the roundings of the
+// two products and of the quotient: 2.8e-7 > 2 ulp); in between, the exact quotient decides.
+__device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const float4 b, float area_b, float thresh) {
+  const float ix = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float iy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  const float inter = __fmul_rn(ix > 0.f ? ix : 0.f, iy > 0.f ? iy : 0.f);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (!(uni > 0.f)) return 0.f > thresh;
+  const float tu = __fmul_rn(thresh, uni);
+  if (thresh > 0.f) {
+    if (inter > __fmul_rn(tu, 1.0000004f)) return true;
+    if (inter < __fmul_rn(tu, 0.9999996f)) return false;
+  }
+  return __fdiv_rn(inter, uni) > thresh;
+}
+
 // Fast-NMS for one (class, tile): sort the class' candidates, keep top_k, then each warp lane owns a
 // column j of the IoU matrix and scans the rows i < j (upper triangle); survivors are compacted with
 // ballot/popc and appended to the tile's survivor list.
 constexpr int kNmsThreads = 256;
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap) {
-  extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k]
+  extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k]
   float4* s_box = reinterpret_cast<float4*>(s_keys + sort_cap);
-  __shared__ int s_base;
+  float* s_area = reinterpret_cast<float*>(s_box + c.top_k);
   const int k = blockIdx.x;  // foreground class
   const int t = blockIdx.y;
   const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
@@ -286,7 +303,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
   const int m = min(n, c.top_k);
   for (int i = threadIdx.x; i < m; i += kNmsThreads) {
     const int prior = int(0xFFFFFFFFu - unsigned(s_keys[i] & 0xFFFFFFFFull));
-    s_box[i] = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
+    const float4 bx = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
+    s_box[i] = bx;
+    s_area[i] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -295,8 +314,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
     bool keep = false;
     if (j < m) {
       const float4 bj = s_box[j];
+      const float aj = s_area[j];
       keep = true;  // column max of the upper-triangular IoU matrix <= thresh  <=>  no row i < j exceeds it
-      for (int i = 0; i < j && keep; ++i) keep = !(iou_rn(s_box[i], bj) > c.nms_thresh);
+      for (int i = 0; i < j && keep; ++i) keep = !iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     int base = 0;
@@ -310,7 +330,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
           (key & 0xFFFFFFFF00000000ull) | (static_cast<unsigned long long>(order) << 16) | prior;
     }
   }
-  (void)s_base;
 }
 
 // merge the classes of one tile: sort survivors by score, keep max_dets
@@ -438,7 +457,7 @@ void launch_classify_post(const uint32_t* tile_px, int n, int W, int H, const Re
 }
 
 size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8; }
-static size_t nms_smem(const DetectCfg& c) { return size_t(next_pow2(c.P)) * 8 + size_t(c.top_k) * 16; }
+static size_t nms_smem(const DetectCfg& c) { return size_t(next_pow2(c.P)) * 8 + size_t(c.top_k) * 20; }
 static size_t mask_smem(const DetectCfg& c) { return size_t(c.max_dets) * (c.K + 4 + 16); }
 
 int detect_setup_kernels(const DetectCfg& c) {

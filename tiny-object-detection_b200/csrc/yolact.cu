@@ -45,7 +45,7 @@ struct Step {
   ConvGeom g{};
   int32_t in_zp = 0;
   // offsets into the constant arena (-1 = absent)
-  int64_t w_off = -1, bias_off = -1, wsum_off = -1, mult_off = -1, shift_off = -1, lut_off = -1;
+  int64_t w_off = -1, bias_off = -1, wsum_off = -1, mult_off = -1, shift_off = -1, lut_off = -1, fast_off = -1;
   int32_t out_zp = 0, act_min = 0, act_max = 0;
   AddParams add{};
   int pad_top = 0, pad_left = 0;
@@ -57,7 +57,9 @@ struct Step {
   std::vector<int> deps;   // indices of the steps whose output this step reads (RESHAPE / CONCAT are transparent)
   std::vector<uint8_t> lut_host;  // kStepLut: the table; conv steps: the composed byte map fused behind the requantisation
   int64_t post_lut_off = -1;
-  bool out_moved = false;  // the conv writes where a fused byte-map chain's last output lives
+  bool out_moved = false;  // the conv writes where a fused byte-map chain's last output (or a fused ADD's output) lives
+  bool fused_add = false;  // `add` holds a residual ADD applied in this conv's epilogue; in1 = the ADD's other input
+  bool add_conv_is_a = true;
   Place out_place;
 };
 
@@ -410,6 +412,20 @@ int plan(tod_yolact* y, ConstArena* arena) {
           }
           st.mult_off = arena->add(q.data(), q.size() * 4);
           st.shift_off = arena->add(sh.data(), sh.size() * 4);
+          // the 4-instruction requantisation (Requant::fast_tab) when every channel qualifies
+          bool fast_ok = std::abs(O.zp()) <= 128;
+          for (int c = 0; c < OCs && fast_ok; ++c) fast_ok = sh[c] <= -1 && sh[c] >= -22 && q[c] >= 0;
+          if (fast_ok) {
+            std::vector<int32_t> ft(size_t(OCs) * 4);
+            for (int c = 0; c < OCs; ++c) {
+              const int rs = -sh[c];
+              ft[size_t(c) * 4 + 0] = q[c];
+              ft[size_t(c) * 4 + 1] = rs;
+              ft[size_t(c) * 4 + 2] = int32_t(0x80000000u);
+              ft[size_t(c) * 4 + 3] = (1 << (rs - 1)) + O.zp() * (1 << rs);
+            }
+            st.fast_off = arena->add(ft.data(), ft.size() * 4);
+          }
         }
         const int8_t* w_real = reinterpret_cast<const int8_t*>(Wt.const_data);
         std::vector<int8_t> w_pad;
@@ -644,6 +660,49 @@ int plan(tod_yolact* y, ConstArena* arena) {
       }
     }
   }
+  // ---- residual / FPN ADD fusion: an ADD one of whose inputs is a tensor-core convolution's only-read output runs in
+  // that convolution's epilogue (two 256-entry rescale tables + one output rescale, the arithmetic of ops.cu::add_kernel).
+  // The convolution moves to the ADD's position in the step list, so the other operand is always produced before it.
+  if (fuse && y->opt.conv_impl == 0) {
+    for (size_t ai = 0; ai < y->steps.size(); ++ai) {
+      if (y->steps[ai].kind != kStepAdd) continue;
+      const Step A = y->steps[ai];
+      int pick = -1;
+      bool conv_is_a = true;
+      for (int side = 0; side < 2 && pick < 0; ++side) {
+        const int t = side == 0 ? A.in0 : A.in1;
+        if (consumers[t] != 1) continue;
+        for (size_t k = 0; k < ai; ++k) {
+          const Step& P = y->steps[k];
+          if (P.kind != kStepConvDirect || P.out != t || P.out_moved || P.fused_add || !P.lut_host.empty() || P.fast_off < 0) continue;
+          const Place& pin = y->place[P.in0];
+          const Place& pout = y->place[P.out];
+          const Place& padd = y->place[A.out];
+          const Place& pres = y->place[side == 0 ? A.in1 : A.in0];
+          if (!conv_tc_supported(P.g, pin.tile_stride, pin.base, reinterpret_cast<const void*>(uintptr_t(256)))) continue;
+          if (P.g.OC % 16 != 0 || (reinterpret_cast<uintptr_t>(padd.base) & 15) || (padd.tile_stride & 15) || (reinterpret_cast<uintptr_t>(pres.base) & 15) ||
+              (pres.tile_stride & 15))
+            continue;
+          if (padd.bytes != pout.bytes || pres.bytes != pout.bytes || padd.c_store != pout.c_store || pres.c_store != pout.c_store) continue;
+          pick = int(k);
+          conv_is_a = side == 0;
+        }
+      }
+      if (pick < 0) continue;
+      Step P = y->steps[pick];
+      P.fused_add = true;
+      P.add_conv_is_a = conv_is_a;
+      P.add = A.add;
+      P.in1 = conv_is_a ? A.in1 : A.in0;
+      y->fused_away[P.out] = 1;
+      P.out_moved = true;
+      P.out_place = y->place[A.out];
+      P.out = A.out;
+      y->steps[ai] = P;                                 // the conv takes the ADD's slot ...
+      y->steps.erase(y->steps.begin() + pick);          // ... and leaves its own (pick < ai)
+      --ai;
+    }
+  }
   for (Step& st : y->steps)
     if ((st.kind == kStepConvDirect || st.kind == kStepDepthwise) && !st.lut_host.empty()) st.post_lut_off = arena->add(st.lut_host.data(), 256);
   // ---- data dependencies between steps
@@ -706,7 +765,10 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
     const Place& pi = y->place[st.in0];
     const Place& po = st.out_moved ? st.out_place : y->place[st.out];
     const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
-    if (!conv_tc_supported(st.g, pi.tile_stride, pi.base, w)) continue;
+    if (!conv_tc_supported(st.g, pi.tile_stride, pi.base, w)) {
+      if (st.fused_add) return fail(TOD_ERR_UNSUPPORTED, "planner fused an ADD into a convolution the tensor-core path rejects");
+      continue;
+    }
     ConvTcArgs a{};
     a.g = st.g;
     a.in = reinterpret_cast<const int8_t*>(pi.base);
@@ -723,6 +785,26 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
     a.h_mult = reinterpret_cast<const int32_t*>(arena.host.data() + st.mult_off);
     a.h_shift = reinterpret_cast<const int32_t*>(arena.host.data() + st.shift_off);
     a.fast_epilogue = y->opt.conv_impl == 2 ? 0 : 1;
+    ConvTcAdd fa{};
+    if (st.fused_add) {
+      const Place& pr = y->place[st.in1];
+      fa.resid = reinterpret_cast<const int8_t*>(pr.base);
+      fa.resid_tile_stride = pr.tile_stride;
+      const AddParams& ap = st.add;
+      for (int b = 0; b < 256; ++b) {  // index = the int8 byte pattern; same literal arithmetic as ops.cu::add_kernel
+        const int v = int(int8_t(b));
+        const int32_t ta = mul_by_quant_mult((v - ap.zp_a) * (1 << 20), ap.mult_a, ap.shift_a);
+        const int32_t tb = mul_by_quant_mult((v - ap.zp_b) * (1 << 20), ap.mult_b, ap.shift_b);
+        fa.tab[b] = st.add_conv_is_a ? ta : tb;
+        fa.tab[256 + b] = st.add_conv_is_a ? tb : ta;
+      }
+      fa.mult_out = ap.mult_out;
+      fa.shift_out = ap.shift_out;
+      fa.zp_out = ap.zp_out;
+      fa.act_min = ap.act_min;
+      fa.act_max = ap.act_max;
+      a.add = &fa;
+    }
     TOD_TRY(conv_tc_create(a, &st.tc));
     st.kind = kStepConvTc;
     y->tc_layers++;
@@ -740,6 +822,7 @@ int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
     case kStepDepthwise: {
       Requant rq{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
                  st.out_zp, st.act_min, st.act_max, st.post_lut_off >= 0 ? y->d_const + st.post_lut_off : nullptr};
+      if (st.fast_off >= 0 && y->opt.conv_impl != 2) rq.fast_tab = reinterpret_cast<const int4*>(y->d_const + st.fast_off);
       const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
       const int32_t* bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(y->d_const + st.bias_off) : nullptr;
       if (st.kind == kStepDepthwise)
