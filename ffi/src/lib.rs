@@ -51,6 +51,7 @@ pub mod sys {
         pub use_cuda_graph: i32,
         pub conv_impl: i32,
         pub fusion: i32,
+        pub use_pdl: i32,
     }
 
     extern "C" {

@@ -122,9 +122,13 @@ typedef struct tod_yolact_options {
   int32_t max_dets;         /* 100 */
   int32_t use_cuda_graph;   /* 1 = capture the per-batch pipeline in a CUDA graph */
   int32_t conv_impl;        /* 0 = tcgen05 int8 implicit GEMM wherever the layer shape allows (default),
-                               1 = CUDA-core direct convolution everywhere (on-device cross-check) */
+                               1 = CUDA-core direct convolution everywhere (on-device cross-check),
+                               2 = tcgen05 with the general (literal-arithmetic) epilogue and the first-generation
+                                   depthwise kernel (cross-check of the fast requantisation forms) */
   int32_t fusion;           /* 0 = every TFLite tensor is materialised (each one can be fetched and compared),
-                               1 = PAD folded into the following convolution (default) */
+                               1 = PAD folded into the following convolution, QUANTIZE / RELU / TANH byte maps and
+                                   residual / FPN ADDs fused into the producing convolution's epilogue (default) */
+  int32_t use_pdl;          /* 1 = programmatic dependent launch between consecutive kernels of a graph branch (default) */
 } tod_yolact_options;
 
 void tod_yolact_default_options(tod_yolact_options* o);

@@ -62,6 +62,19 @@ def test_fusion_and_graph_do_not_change_bytes(tod, models):
     assert np.array_equal(a["tile_classes"], rb["tile_classes"])
 
 
+def test_pdl_does_not_change_bytes(tod, models):
+    """Programmatic dependent launch only overlaps prologues: same bytes with it on and off, over repeated replays."""
+    full, _ = models
+    tiles = synth.rgb_tiles(4, seed=34)
+    a = tod.Yolact.init(full, max_tiles=4, use_pdl=0).infer_tiles(tiles)
+    b = tod.Yolact.init(full, max_tiles=4, use_pdl=1)
+    for _ in range(3):
+        rb = b.infer_tiles(tiles)
+        for k in range(5):
+            assert np.array_equal(a["outputs"][k], rb["outputs"][k])
+        assert np.array_equal(a["tile_classes"], rb["tile_classes"])
+
+
 def test_errors(tod, models, tmp_path):
     _, small = models
     with pytest.raises(tod.TodError):

@@ -8,6 +8,11 @@ std::string& last_error() {
   return e;
 }
 
+bool& pdl_next() {
+  static thread_local bool v = false;
+  return v;
+}
+
 int select_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

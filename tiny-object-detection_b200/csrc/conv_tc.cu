@@ -190,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + size_t(kBM) * p.pitch);  // [128] global offset of each row
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_rowoff + kBM);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = p.flat ? tiles * p.HW : p.Wd;
   const int tiles_x = p.flat ? (Wd + kBM - 1) / kBM : p.tiles_x;
@@ -218,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();  // everything above touched constants only; activations (and our output buffer) are safe from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -453,6 +455,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = p.flat ? tiles * p.HW : p.Wd;
   const int tiles_x = p.flat ? (Wd + kBM - 1) / kBM : p.tiles_x;
@@ -484,6 +487,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();  // everything above touched constants only; activations (and our output buffer) are safe from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1056,10 +1060,10 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   const long long work = (long long)groups * p.tiles_y * tiles_x * p.n_tiles;
   const int grid = int(std::min<long long>(work, sm_count()));
   if (!c->fast) {
-    conv_tc_kernel<<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, p, tiles);
+    TOD_CUDA(launch_k(conv_tc_kernel, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, p, tiles));
   } else {
     switch (c->mode) {
-#define TOD_TC_CASE(M) case M: conv_tc_fast_kernel<M><<<grid, kTcThreads, c->smem_bytes, s>>>(c->map_a, c->map_b, c->map_o, p, tiles); break;
+#define TOD_TC_CASE(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M>, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); break;
       TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
       TOD_TC_CASE(12) TOD_TC_CASE(13)
       default: return fail(TOD_ERR_UNSUPPORTED, "conv_tc: no kernel for epilogue mode %u", c->mode);

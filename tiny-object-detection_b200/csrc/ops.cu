@@ -6,6 +6,8 @@
 // interpreter.invoke() (/root/reference/src/yolact.rs:163).
 #include "ops.h"
 
+#include "common.h"
+
 #include <algorithm>
 
 #include "fixedpoint.cuh"
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __r
                                                               Requant rq, int8_t* __restrict__ out, int64_t out_ts,
                                                               int tiles) {
   extern __shared__ int s_w[];  // [taps * icw][OCT] weight words, then [taps][OCT] tap sums
+  pdl_trigger();
   const int taps = g.KH * g.KW;
   const int icw = (g.IC + 3) >> 2;  // input words per tap
   int* s_ws = s_w + taps * icw * kPixOct;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __r
     s_ws[i] = (oc0 + j < g.OC) ? wsum[int64_t(oc0 + j) * taps + tap] : 0;
   }
   __syncthreads();
+  pdl_wait();
   const int pix = blockIdx.x * kPixThreads + threadIdx.x;
   const int total = tiles * g.OH * g.OW;
   if (pix >= total) return;
@@ -372,6 +376,7 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
                                                                        const int32_t* __restrict__ bias, int32_t in_zp,
                                                                        ConvGeom g, Requant rq, int8_t* __restrict__ out,
                                                                        int64_t out_ts, int rows_per_block) {
+  pdl_trigger();
   const int C = g.OC, CW = C >> 2;
   const int j = blockIdx.x * kDwThreads + threadIdx.x;
   if (j >= g.OW * CW) return;
@@ -410,6 +415,7 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
   const int oy0 = blockIdx.y * rows_per_block, oy1 = min(g.OH, oy0 + rows_per_block);
   int r0[3], r1[3], r2[3], n1[3], n2[3];
   int iy = oy0 * STRIDE - g.pad_top;
+  pdl_wait();  // filters / requantisation constants are in registers; the activations come next
   load_row(iy, r0[0], r0[1], r0[2]);
   load_row(iy + 1, r1[0], r1[1], r1[2]);
   load_row(iy + 2, r2[0], r2[1], r2[2]);
@@ -610,6 +616,8 @@ __global__ void __launch_bounds__(256) resize_kernel(const int8_t* __restrict__ 
 __global__ void __launch_bounds__(256) resize16_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
                                                       int C, int8_t* __restrict__ out, int64_t out_ts, int OH, int OW,
                                                       int hs, int ws, bool half_pixel) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.y;
   const int c16n = C >> 4;
   const int total = OH * OW * c16n;
@@ -683,9 +691,9 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
     const int total = tiles * g.OH * g.OW;
     dim3 grid(unsigned((total + kPixThreads - 1) / kPixThreads), unsigned((g.OC + kPixOct - 1) / kPixOct));
     if (g.IC == 3)
-      conv_pix_kernel<true><<<grid, kPixThreads, pix_smem, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+      launch_k(conv_pix_kernel<true>, grid, dim3(kPixThreads), pix_smem, s, in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
     else
-      conv_pix_kernel<false><<<grid, kPixThreads, pix_smem, s>>>(in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
+      launch_k(conv_pix_kernel<false>, grid, dim3(kPixThreads), pix_smem, s, in, in_ts, w, bias, wsum, in_zp, g, rq, out, out_ts, tiles);
     return;
   }
   constexpr int OCT = 8;
@@ -715,11 +723,11 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
     dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
     const bool sat = rq.act_min == -128 && rq.act_max == 127;
     if (g.stride_h == 1) {
-      if (sat) depthwise3x3_slide_kernel<1, true><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
-      else depthwise3x3_slide_kernel<1, false><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      if (sat) launch_k(depthwise3x3_slide_kernel<1, true>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      else launch_k(depthwise3x3_slide_kernel<1, false>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
     } else {
-      if (sat) depthwise3x3_slide_kernel<2, true><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
-      else depthwise3x3_slide_kernel<2, false><<<grid, kDwThreads, 0, s>>>(in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      if (sat) launch_k(depthwise3x3_slide_kernel<2, true>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      else launch_k(depthwise3x3_slide_kernel<2, false>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
     }
     return;
   }
@@ -773,7 +781,7 @@ void launch_resize_bilinear(const int8_t* in, int64_t in_ts, int IH, int IW, int
   if (align_corners && OW > 1) ws = ((1 << 10) * (IW - 1) + (OW - 1) / 2) / (OW - 1);
   if (C % 16 == 0 && aligned16(in, in_ts) && aligned16(out, out_ts) && int64_t(OH) * OW * C < (int64_t(1) << 31)) {
     dim3 grid16(grid_for(int64_t(OH) * OW * (C / 16), 256, tiles), tiles);
-    resize16_kernel<<<grid16, 256, 0, s>>>(in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
+    launch_k(resize16_kernel, grid16, dim3(256), 0, s, in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
     return;
   }
   dim3 grid(grid_for(int64_t(OH) * OW * (C / 4), 256, tiles), tiles);

@@ -1037,9 +1037,18 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, bool masks, cudaStream
       TOD_CUDA(cudaStreamWaitEvent(ls, y->fork_event, 0));
       forked[lane] = 1;
     }
+    bool waited = false;
     for (int d : st.deps)
-      if (lane_of[d] != lane) TOD_CUDA(cudaStreamWaitEvent(ls, y->step_events[d], 0));
-    TOD_TRY(run_step(y, st, n, ls));
+      if (lane_of[d] != lane) {
+        TOD_CUDA(cudaStreamWaitEvent(ls, y->step_events[d], 0));
+        waited = true;
+      }
+    // programmatic dependent launch only along an unbroken kernel -> kernel chain of this lane: the previous node of
+    // the stream must be the kernel this step waits for (event records in between are fine, event waits are not)
+    pdl_next() = y->opt.use_pdl && !waited && tail[lane] >= 0 && !st.deps.empty();  // only launch_k kernels honour it, and all of those wait
+    const int rc_step = run_step(y, st, n, ls);
+    pdl_next() = false;
+    TOD_TRY(rc_step);
     TOD_CUDA(cudaEventRecord(y->step_events[i], ls));
     lane_of[i] = lane;
     tail[lane] = int(i);
@@ -1165,6 +1174,7 @@ void tod_yolact_default_options(tod_yolact_options* o) {
   o->use_cuda_graph = 1;
   o->conv_impl = 0;
   o->fusion = 1;
+  o->use_pdl = 1;
 }
 
 int tod_model_inspect(const char* tflite_path, int32_t* num_ops, int32_t* num_tensors, int64_t* macs) {
