@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
                                                                int64_t cls_ts, const uint8_t* __restrict__ box, int64_t box_ts) {
   extern __shared__ uint8_t s_q[];  // [kDecodeThreads][C]
   __shared__ float s_exp[256];
+  __shared__ int s_cnt[256], s_base[256];
+  for (int i = threadIdx.x; i < 256; i += kDecodeThreads) s_cnt[i] = 0;
   const int t = blockIdx.y;
   const int p0 = blockIdx.x * kDecodeThreads;
   const int np = min(kDecodeThreads, c.P - p0);
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   const uint8_t* src = cls + int64_t(t) * cls_ts + int64_t(p0) * c.C;
   for (int i = threadIdx.x; i < np * c.C; i += kDecodeThreads) s_q[i] = src[i];
   __syncthreads();
-  if (threadIdx.x >= np) return;
-  const int p = p0 + threadIdx.x;
+  const bool active = threadIdx.x < np;
+  const int p = min(p0 + int(threadIdx.x), c.P - 1);
   // box_utils.decode, variances 0.1 / 0.2
   const float4 pr = reinterpret_cast<const float4*>(b.priors)[p];
   const uint8_t* l = box + int64_t(t) * box_ts + int64_t(p) * 4;
@@ -239,19 +241,35 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   const float w = __fmul_rn(pr.z, b.box_exp[l[2]]);
   const float h = __fmul_rn(pr.w, b.box_exp[l[3]]);
   const float x1 = __fsub_rn(cx, __fdiv_rn(w, 2.0f)), y1 = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
-  reinterpret_cast<float4*>(b.boxes)[int64_t(t) * c.P + p] = make_float4(x1, y1, __fadd_rn(w, x1), __fadd_rn(h, y1));
+  if (active) reinterpret_cast<float4*>(b.boxes)[int64_t(t) * c.P + p] = make_float4(x1, y1, __fadd_rn(w, x1), __fadd_rn(h, y1));
   // softmax over the u8 codes: exp(scale*(q - qmax)) from a 256-entry table, summed class 0..C-1 in order
   const uint8_t* q = s_q + threadIdx.x * c.C;
   int qmax = 0;
   for (int k = 0; k < c.C; ++k) qmax = max(qmax, int(q[k]));
   float sum = 0.f;
   for (int k = 0; k < c.C; ++k) sum = __fadd_rn(sum, s_exp[int(q[k]) - qmax + 255]);
+  // fl(e / sum) > conf_thresh, deciding without the division wherever the margin allows (see iou_exceeds)
+  const float tu = __fmul_rn(c.conf_thresh, sum);
+  const float tu_hi = __fmul_rn(tu, 1.0000004f), tu_lo = __fmul_rn(tu, 0.9999996f);
+  auto passes = [&](float e) { return c.conf_thresh > 0.f ? (e > tu_hi ? true : (e < tu_lo ? false : __fdiv_rn(e, sum) > c.conf_thresh)) : __fdiv_rn(e, sum) > c.conf_thresh; };
+  // pass 1: per-class candidate counts of this CTA (shared-memory atomics), one global reservation per class
+  if (active)
+    for (int k = 1; k < c.C; ++k)
+      if (passes(s_exp[int(q[k]) - qmax + 255])) atomicAdd(&s_cnt[k - 1], 1);
+  __syncthreads();
+  for (int k = threadIdx.x; k < c.C - 1; k += kDecodeThreads) {
+    const int cnt = s_cnt[k];
+    s_base[k] = cnt ? atomicAdd(b.cand_count + int64_t(t) * (c.C - 1) + k, cnt) : 0;
+    s_cnt[k] = 0;
+  }
+  __syncthreads();
+  if (!active) return;
   for (int k = 1; k < c.C; ++k) {
-    const float sc = __fdiv_rn(s_exp[int(q[k]) - qmax + 255], sum);
-    if (sc > c.conf_thresh) {
-      const int slot = atomicAdd(b.cand_count + int64_t(t) * (c.C - 1) + (k - 1), 1);
+    const float e = s_exp[int(q[k]) - qmax + 255];
+    if (passes(e)) {
+      const int slot = s_base[k - 1] + atomicAdd(&s_cnt[k - 1], 1);
       b.cand[(int64_t(t) * (c.C - 1) + (k - 1)) * c.P + slot] =
-          (static_cast<unsigned long long>(__float_as_uint(sc)) << 32) | (0xFFFFFFFFu - unsigned(p));
+          (static_cast<unsigned long long>(__float_as_uint(__fdiv_rn(e, sum))) << 32) | (0xFFFFFFFFu - unsigned(p));
     }
   }
 }
@@ -332,21 +350,105 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
   }
 }
 
-// merge the classes of one tile: sort survivors by score, keep max_dets
-__global__ void __launch_bounds__(1024) select_kernel(DetectCfg c, DetectBuffers b) {
-  extern __shared__ unsigned long long s_keys[];
+// merge the classes of one tile: the max_dets best survivors in key order (score, then class / rank, then prior).
+// A full sort of every survivor is wasted work when thousands survive and 100 are kept, so the kernel first bins the
+// keys by the top bits of the score (a monotone 12-bit bin), finds by a suffix sum the lowest bin the top max_dets
+// reach into, and sorts only the keys at or above that bin.  Same result as the full sort (which remains as the
+// fallback for a pathological bin population); one CTA per tile.
+constexpr int kSelThreads = 1024;
+constexpr int kSelBins = 4096;
+constexpr int kSelCap = 2048;
+
+__device__ __forceinline__ int score_bin(unsigned long long key) {
+  const int v = int(unsigned(key >> 47)) - (112 << 8);  // float bits >> 15, rebased at 2^-15: exponent low bits + 8 mantissa bits
+  return min(kSelBins - 1, max(0, v));
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(DetectCfg c, DetectBuffers b, int full_cap) {
+  extern __shared__ unsigned long long s_keys[];  // [full_cap] (fallback), then [kSelCap] short list, then int hist[kSelBins]
+  unsigned long long* s_small = s_keys + full_cap;
+  int* s_hist = reinterpret_cast<int*>(s_small + kSelCap);
+  __shared__ int s_warp[32];
+  __shared__ int s_cut, s_cnt;
   const int t = blockIdx.x;
   const int n = b.surv_count[t];
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
   const unsigned long long* src = b.surv + int64_t(t) * (c.C - 1) * c.top_k;
-  for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = i < n ? src[i] : 0ull;
-  if (n > 1) bitonic_sort_desc(s_keys, np2);
-  else __syncthreads();
   const int nd = min(n, c.max_dets);
+  unsigned long long* sorted = s_small;
+  bool done = false;
+  if (n <= kSelCap) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += kSelThreads) s_small[i] = i < n ? src[i] : 0ull;
+    if (n > 1) bitonic_sort_desc(s_small, np2);
+    else __syncthreads();
+    done = true;
+  } else {
+    for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSelThreads) atomicAdd(&s_hist[score_bin(src[i])], 1);
+    __syncthreads();
+    // suffix sums over the bins, 4 consecutive bins per thread, highest bins first
+    const int b0 = kSelBins - 4 * (threadIdx.x + 1);  // this thread owns bins b0 .. b0+3; thread 0 owns the top four
+    const int h3 = s_hist[b0 + 3], h2 = s_hist[b0 + 2], h1 = s_hist[b0 + 1], h0 = s_hist[b0];
+    const int mine = h0 + h1 + h2 + h3;
+    int incl = mine;  // inclusive scan over threads 0..tid (= bins above and including mine)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int above = incl - mine + (wid ? s_warp[wid - 1] : 0);  // keys in bins strictly above this thread's four
+    if (above < nd && above + mine >= nd) {  // the nd-th best key lies in one of my bins
+      int cut = b0 + 3, acc = above + h3;
+      if (acc < nd) { cut = b0 + 2; acc += h2; }
+      if (acc < nd) { cut = b0 + 1; acc += h1; }
+      if (acc < nd) { cut = b0; }
+      s_cut = cut;
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    for (int i = threadIdx.x; i < n; i += kSelThreads) {
+      const unsigned long long key = src[i];
+      if (score_bin(key) >= cut) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        if (slot < kSelCap) s_small[slot] = key;
+      }
+    }
+    __syncthreads();
+    const int m = s_cnt;
+    if (m <= kSelCap) {
+      int np2 = 1;
+      while (np2 < m) np2 <<= 1;
+      for (int i = m + threadIdx.x; i < np2; i += kSelThreads) s_small[i] = 0ull;
+      bitonic_sort_desc(s_small, np2);
+      done = true;
+    }
+  }
+  if (!done) {  // fallback: sort everything
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += kSelThreads) s_keys[i] = i < n ? src[i] : 0ull;
+    bitonic_sort_desc(s_keys, np2);
+    sorted = s_keys;
+  }
   if (threadIdx.x == 0) b.det_count[t] = nd;
-  for (int d = threadIdx.x; d < nd; d += blockDim.x) {
-    const unsigned long long key = s_keys[d];
+  for (int d = threadIdx.x; d < nd; d += kSelThreads) {
+    const unsigned long long key = sorted[d];
     const int prior = int(key & 0xFFFFull);
     const unsigned order = 0xFFFFu - unsigned((key >> 16) & 0xFFFFull);
     const int64_t o = int64_t(t) * c.max_dets + d;
@@ -456,7 +558,7 @@ void launch_classify_post(const uint32_t* tile_px, int n, int W, int H, const Re
   horizontal_kernel<<<unsigned((thz + 255) / 256), 256, 0, s>>>(tmp, n, sw, H, horz, 1, nullptr, tw, frames, target);
 }
 
-size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8; }
+size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8 + size_t(kSelCap) * 8 + size_t(kSelBins) * 4; }
 static size_t nms_smem(const DetectCfg& c) { return size_t(next_pow2(c.P)) * 8 + size_t(c.top_k) * 20; }
 static size_t mask_smem(const DetectCfg& c) { return size_t(c.max_dets) * (c.K + 4 + 16); }
 
@@ -471,21 +573,32 @@ int detect_setup_kernels(const DetectCfg& c) {
   return TOD_OK;
 }
 
-int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
-                  int64_t box_ts, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto, int64_t proto_ts, int tiles,
-                  bool want_masks, cudaStream_t s) {
+int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
+                        int64_t box_ts, int tiles, cudaStream_t s) {
   TOD_CUDA(cudaMemsetAsync(b.cand_count, 0, sizeof(int) * size_t(tiles) * (c.C - 1), s));
   TOD_CUDA(cudaMemsetAsync(b.surv_count, 0, sizeof(int) * size_t(tiles), s));
   dim3 g1((c.P + kDecodeThreads - 1) / kDecodeThreads, tiles);
   decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
   dim3 g2(c.C - 1, tiles);
   nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P));
-  select_kernel<<<tiles, 1024, detect_select_smem(c), s>>>(c, b);
-  if (want_masks) {
-    dim3 g4((c.ph * c.pw + kMaskThreads - 1) / kMaskThreads, tiles);
-    mask_kernel<32><<<g4, kMaskThreads, mask_smem(c), s>>>(c, b, coef, coef_ts, proto, proto_ts);
-  }
+  select_kernel<<<tiles, kSelThreads, detect_select_smem(c), s>>>(c, b, next_pow2((c.C - 1) * c.top_k));
   TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto,
+                        int64_t proto_ts, int tiles, cudaStream_t s) {
+  dim3 g4((c.ph * c.pw + kMaskThreads - 1) / kMaskThreads, tiles);
+  mask_kernel<32><<<g4, kMaskThreads, mask_smem(c), s>>>(c, b, coef, coef_ts, proto, proto_ts);
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
+                  int64_t box_ts, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto, int64_t proto_ts, int tiles,
+                  bool want_masks, cudaStream_t s) {
+  TOD_TRY(launch_detect_boxes(c, b, cls, cls_ts, box, box_ts, tiles, s));
+  if (want_masks) TOD_TRY(launch_detect_masks(c, b, coef, coef_ts, proto, proto_ts, tiles, s));
   return TOD_OK;
 }
 

@@ -179,10 +179,13 @@ struct tod_yolact {
   static constexpr int kLanes = 6;
   cudaStream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> step_events;
+  cudaEvent_t post_events[2] = {nullptr, nullptr};  // seg post-processing / detection boxes, when they run on a branch lane
+  std::vector<std::vector<int>> out_steps;        // per graph output: the steps that write it
   cudaEvent_t fork_event = nullptr;
-  // CUDA graphs, keyed by (tiles << 2 | dets << 1 | masks)
+  // CUDA graphs, keyed by (tiles << 3 | dets << 2 | mask mode); mask mode: 0 = none, 1 = binary masks only, 2 = float + binary
   std::map<int, cudaGraphExec_t> graphs;
   int last_tiles = 0;
+  int last_mask_mode = 0;
   int launches_per_call = 0;
 
   const GTensor& T(int i) const { return graph.tensors[i]; }
@@ -754,6 +757,8 @@ int plan(tod_yolact* y, ConstArena* arena) {
     d.erase(std::remove_if(d.begin(), d.end(), [&](int v) { return v >= int(i); }), d.end());
     st.deps = d;
   }
+  y->out_steps.clear();
+  for (int t : G.outputs) y->out_steps.push_back(producers(t));
   return TOD_OK;
 }
 
@@ -989,7 +994,7 @@ int setup_detection(tod_yolact* y) {
   return TOD_OK;
 }
 
-int enqueue_post(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+int enqueue_post(tod_yolact* y, int n, bool dets, int masks, cudaStream_t s) {
   if (y->seg_out >= 0) {
     const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
     const Place& ps = y->place[y->graph.outputs[y->seg_out]];
@@ -1001,14 +1006,16 @@ int enqueue_post(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
     const Place& pb = y->place[y->graph.outputs[y->o_box]];
     const Place& pf = y->place[y->graph.outputs[y->o_coef]];
     const Place& pp = y->place[y->graph.outputs[y->o_proto]];
-    TOD_TRY(launch_detect(y->dcfg, y->dbuf, pc.base, pc.tile_stride, pb.base, pb.tile_stride, pf.base, pf.tile_stride, pp.base,
-                          pp.tile_stride, n, masks, s));
+    DetectBuffers db = y->dbuf;
+    if (masks < 2) db.masks = nullptr;  // float masks only when somebody will read them
+    TOD_TRY(launch_detect(y->dcfg, db, pc.base, pc.tile_stride, pb.base, pb.tile_stride, pf.base, pf.tile_stride, pp.base,
+                          pp.tile_stride, n, masks != 0, s));
   }
   return TOD_OK;
 }
 
 // the per-batch pipeline after the input tiles are in place: graph steps + post-processing
-int enqueue_all(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+int enqueue_all(tod_yolact* y, int n, bool dets, int masks, cudaStream_t s) {
   for (const Step& st : y->steps) TOD_TRY(run_step(y, st, n, s));
   TOD_TRY(enqueue_post(y, n, dets, masks, s));
   TOD_CUDA(cudaGetLastError());
@@ -1017,7 +1024,7 @@ int enqueue_all(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
 
 // Same work as enqueue_all, spread over the handle's lane streams by data dependency.  Only used while capturing:
 // the resulting CUDA graph has one node per kernel and an edge per dependency, so independent branches overlap.
-int enqueue_all_parallel(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t origin) {
+int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_t origin) {
   const int L = tod_yolact::kLanes;
   std::vector<int> lane_of(y->steps.size(), 0), tail(L, -1);
   std::vector<char> forked(L, 0);
@@ -1053,19 +1060,67 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, bool masks, cudaStream
     lane_of[i] = lane;
     tail[lane] = int(i);
   }
+  // post-processing rides the branches: the literal segmentation pass follows the seg head on its lane; box decode /
+  // Fast-NMS / top-k follow the class and box heads on theirs and so overlap the protonet branch; only mask assembly
+  // (prototypes x coefficients of the selected detections) waits for everything.
+  auto after_outputs = [&](std::initializer_list<int> outs, int* lane_out) -> int {
+    int last = -1;
+    for (int o : outs)
+      for (int sidx : y->out_steps[o]) last = std::max(last, sidx);
+    const int lane = last >= 0 ? lane_of[last] : 0;
+    cudaStream_t ls = y->lanes[lane];
+    if (!forked[lane]) {
+      TOD_CUDA(cudaStreamWaitEvent(ls, y->fork_event, 0));
+      forked[lane] = 1;
+    }
+    for (int o : outs)
+      for (int sidx : y->out_steps[o])
+        if (lane_of[sidx] != lane || sidx != tail[lane]) TOD_CUDA(cudaStreamWaitEvent(ls, y->step_events[sidx], 0));
+    *lane_out = lane;
+    return TOD_OK;
+  };
+  bool seg_done = false, det_done = false;
+  if (y->seg_out >= 0) {
+    int lane = 0;
+    TOD_TRY(after_outputs({y->seg_out}, &lane));
+    const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
+    const Place& ps = y->place[y->graph.outputs[y->seg_out]];
+    SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
+    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, y->lanes[lane]);
+    TOD_CUDA(cudaEventRecord(y->post_events[0], y->lanes[lane]));
+    seg_done = true;
+  }
+  if (dets) {
+    int lane = 0;
+    TOD_TRY(after_outputs({y->o_cls, y->o_box}, &lane));
+    if (seg_done) TOD_CUDA(cudaStreamWaitEvent(y->lanes[lane], y->post_events[0], 0));  // harmless ordering if both share a lane
+    const Place& pc = y->place[y->graph.outputs[y->o_cls]];
+    const Place& pb = y->place[y->graph.outputs[y->o_box]];
+    TOD_TRY(launch_detect_boxes(y->dcfg, y->dbuf, pc.base, pc.tile_stride, pb.base, pb.tile_stride, n, y->lanes[lane]));
+    TOD_CUDA(cudaEventRecord(y->post_events[1], y->lanes[lane]));
+    det_done = true;
+  }
   for (int l = 0; l < L; ++l)
     if (forked[l] && tail[l] >= 0) TOD_CUDA(cudaStreamWaitEvent(origin, y->step_events[tail[l]], 0));
-  TOD_TRY(enqueue_post(y, n, dets, masks, origin));
+  if (seg_done) TOD_CUDA(cudaStreamWaitEvent(origin, y->post_events[0], 0));
+  if (det_done) TOD_CUDA(cudaStreamWaitEvent(origin, y->post_events[1], 0));
+  if (dets && masks) {
+    const Place& pf = y->place[y->graph.outputs[y->o_coef]];
+    const Place& pp = y->place[y->graph.outputs[y->o_proto]];
+    DetectBuffers db = y->dbuf;
+    if (masks < 2) db.masks = nullptr;
+    TOD_TRY(launch_detect_masks(y->dcfg, db, pf.base, pf.tile_stride, pp.base, pp.tile_stride, n, origin));
+  }
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
 }
 
-int run_pipeline(tod_yolact* y, int n, bool dets, bool masks, cudaStream_t s) {
+int run_pipeline(tod_yolact* y, int n, bool dets, int masks, cudaStream_t s) {
   if (dets && !y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
   if (dets && !y->have_priors) return fail(TOD_ERR_INVALID_ARG, "no priors for a %d-prior head: call tod_yolact_set_priors first", y->dcfg.P);
   y->last_tiles = n;
   if (!y->opt.use_cuda_graph) return enqueue_all(y, n, dets, masks, s);
-  const int key = (n << 2) | (dets ? 2 : 0) | (masks ? 1 : 0);
+  const int key = (n << 3) | (dets ? 4 : 0) | (masks & 3);
   auto it = y->graphs.find(key);
   if (it == y->graphs.end()) {
     cudaGraph_t g = nullptr;
@@ -1144,7 +1199,7 @@ int classify_device(tod_yolact* y, uint32_t* d_frames, int n, int W, int H, uint
   const Place& pin = y->place[y->graph.inputs[0]];
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), y->d_tiles_rgb, size_t(pin.bytes), size_t(pin.bytes), size_t(2 * n),
                              cudaMemcpyDeviceToDevice, s));
-  TOD_TRY(run_pipeline(y, 2 * n, false, false, s));
+  TOD_TRY(run_pipeline(y, 2 * n, false, 0, s));
   launch_classify_post(y->d_tile_classes, n, W, H, axis_of(y->post_v), axis_of(y->post_h), y->d_tmp, d_frames, d_target, tw, th, s);
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
@@ -1207,6 +1262,8 @@ void tod_yolact_destroy(tod_yolact* y) {
   for (cudaEvent_t e : y->step_events)
     if (e) cudaEventDestroy(e);
   if (y->fork_event) cudaEventDestroy(y->fork_event);
+  for (cudaEvent_t e : y->post_events)
+    if (e) cudaEventDestroy(e);
   for (Step& s : y->steps)
     if (s.tc) conv_tc_destroy(s.tc);
   for (void* p : y->det_allocs) cudaFree(p);
@@ -1269,6 +1326,8 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
   for (cudaEvent_t& e : raw->step_events)
     if ((ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
   if ((ce = cudaEventCreateWithFlags(&raw->fork_event, cudaEventDisableTiming)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
+  for (cudaEvent_t& e : raw->post_events)
+    if ((ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
   *out = raw;
   return TOD_OK;
 }
@@ -1313,7 +1372,8 @@ int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), d_rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n),
                              cudaMemcpyDeviceToDevice, s));
   const bool dets = y->det_ready && y->have_priors;
-  return run_pipeline(y, n, dets, dets, s);
+  y->last_mask_mode = dets ? 2 : 0;
+  return run_pipeline(y, n, dets, dets ? 2 : 0, s);
 }
 
 int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out) {
@@ -1383,6 +1443,8 @@ int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
   if (d->scores) TOD_CUDA(cudaMemcpyAsync(d->scores, b.det_score, nd * 4, cudaMemcpyDeviceToHost, s));
   if (d->classes) TOD_CUDA(cudaMemcpyAsync(d->classes, b.det_class, nd * 4, cudaMemcpyDeviceToHost, s));
   if (d->priors) TOD_CUDA(cudaMemcpyAsync(d->priors, b.det_prior, nd * 4, cudaMemcpyDeviceToHost, s));
+  if (d->masks && y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute float masks");
+  if (d->masks_bin && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
   if (d->masks) TOD_CUDA(cudaMemcpyAsync(d->masks, b.masks, nd * c.ph * c.pw * 4, cudaMemcpyDeviceToHost, s));
   if (d->masks_bin) TOD_CUDA(cudaMemcpyAsync(d->masks_bin, b.masks_bin, nd * c.ph * c.pw, cudaMemcpyDeviceToHost, s));
   TOD_CUDA(cudaStreamSynchronize(s));
@@ -1400,7 +1462,9 @@ int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8
   // yolact.rs:161-162 copy_from_slice into the input tensor
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n), cudaMemcpyHostToDevice, s));
   const bool want_dets = dets != nullptr;
-  TOD_TRY(run_pipeline(y, n, want_dets, want_dets && (dets->masks || dets->masks_bin), s));
+  const int mask_mode = !want_dets ? 0 : (dets->masks ? 2 : (dets->masks_bin ? 1 : 0));
+  y->last_mask_mode = mask_mode;
+  TOD_TRY(run_pipeline(y, n, want_dets, mask_mode, s));
   if (outputs_u8)
     for (size_t k = 0; k < y->graph.outputs.size(); ++k)
       if (outputs_u8[k]) TOD_TRY(fetch_strided(outputs_u8[k], y->place[y->graph.outputs[k]], n, s));
