@@ -23,6 +23,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -71,6 +73,13 @@ struct TcParams {
   uint8_t ymap[8], xmap[8];
   int wo;                      // TMA-store staging row bytes (16 / 32 / 64 / 128), 0 = manual stores
   uint32_t stage_bytes;        // shared memory reserved for output staging
+  // ---- cp.async A producer (flat 1x1 layers with short pixel rows: the TMA unit serves ~1 box row per 6-8 cycles
+  // whatever its length, so 32-byte pixels starve it; 96 threads issuing 16-byte cp.async do not care)
+  int dbg;                     // TOD_TC_DBG timing experiments: 1 = skip the output store
+  long long* trace;            // TOD_TC_TRACE: clock64 stamps of CTA 0 (epilogue warp 4 / MMA warp / producer), 16 per tile
+  int a_cp;                    // 1 = A tiles are gathered with cp.async by warps 0, 2, 3
+  const int8_t* in;            // flat [pixels][IC]
+  int IC;
   // ---- fused residual ADD (kEpiAdd): out = requant_out(tab[conv byte] + tab[256 + residual byte])
   const int8_t* resid;         // same geometry as the output
   long long resid_ts;
@@ -118,6 +127,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {  // src_bytes = 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {  // arrives once this thread's earlier cp.async have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int kCpThreads = 96;
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -423,6 +440,13 @@ struct WorkItem { int n_tile, tx, ty, g; };
 __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles_x, int tiles_y) {
   WorkItem w;
   unsigned m = unsigned(work);
+  if (n_tiles == 1 && tiles_y == 1 && m < unsigned(tiles_x)) {  // flat 1x1 layers and single-row tilings: no division at all
+    w.n_tile = 0;
+    w.tx = int(m);
+    w.ty = 0;
+    w.g = 0;
+    return w;
+  }
   if (n_tiles > 1) {
     w.n_tile = int(m % unsigned(n_tiles));
     m /= unsigned(n_tiles);
@@ -451,7 +475,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
   uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;  // 1024-aligned (both stage sizes are)
   long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + p.stage_bytes);
-  int4* s_qtab = reinterpret_cast<int4*>(s_rowoff + kBM);
+  int4* s_qtab = reinterpret_cast<int4*>(s_rowoff + 2 * kBM);
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
 
@@ -465,12 +489,12 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->full[s], p.a_cp ? kCpThreads + 1 : 1);
       mbar_init(&ctl->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], kEpiThreads / 32);
+      mbar_init(&ctl->acc_empty[s], 4);  // one epilogue group (4 warps) owns each accumulator stage
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -489,7 +513,42 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t tmem_base = ctl->tmem_base;
   pdl_wait();  // everything above touched constants only; activations (and our output buffer) are safe from here on
 
-  if (warp == 0) {
+  if (p.a_cp && (warp == 0 || warp == 2 || warp == 3)) {
+    // ===================== cp.async A producer (flat 1x1) + TMA for the weights =====================
+    const int pt = (warp == 0 ? 0 : warp - 1) * 32 + lane;  // 0 .. 95
+    const int cpr_shift = p.BK == 128 ? 3 : (p.BK == 64 ? 2 : 1);  // 16-byte chunks per row = 1 << cpr_shift
+    const int nchunks = kBM << cpr_shift;
+    const uint32_t swz_mask = p.BK == 128 ? 7u : (p.BK == 64 ? 3u : 1u);
+    if (pt == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
+      const long long row0 = (long long)w.tx * kBM;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (pt == 0) {
+          mbar_expect_tx(&ctl->full[stage], uint32_t(p.BN * p.BK));
+          tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, 0, w.n_tile * p.BN);
+        }
+        const uint32_t a_base = smem_u32(smem_a + size_t(stage) * p.a_stage);
+        for (int idx = pt; idx < nchunks; idx += kCpThreads) {
+          const int m = idx >> cpr_shift, cc = idx & ((1 << cpr_shift) - 1);
+          const int kbyte = kc * p.BK + cc * 16;
+          const bool ok = row0 + m < Wd && kbyte < p.IC;
+          const int8_t* src = p.in + (ok ? (row0 + m) * p.IC + kbyte : 0);
+          uint32_t off = uint32_t(m) * uint32_t(p.BK) + uint32_t(cc) * 16u;
+          off ^= ((off >> 7) & swz_mask) << 4;
+          cp_async16(a_base + off, src, ok ? 16u : 0u);
+        }
+        cp_async_arrive(&ctl->full[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -528,6 +587,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
+        if (p.a_cp) fence_async_smem();  // cp.async wrote A through the generic proxy; the MMA reads it through the async one
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem_a + size_t(stage) * p.a_stage);
           const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * p.b_stage);
@@ -548,10 +608,13 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Two groups of four warps (one warp per TMEM lane quarter) take alternate tiles: group g owns accumulator stage g,
+    // its own staging buffers, named barrier and bulk-store queue, so the fixed per-tile latencies of one tile (barrier
+    // waits, TMEM loads, store issue) overlap the arithmetic of the other.
     const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int half = (warp - 4) >> 2;        // which 16-column chunks of a pass this warp converts
+    const int grp = (warp - 4) >> 2;         // epilogue group == accumulator stage
     const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
-    const int et = threadIdx.x - 128;
+    const int eg = threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
     const int wx = r % p.pw;
     const int wy = (r / p.pw) % p.ph;
     const int wn = r / (p.pw * p.ph);
@@ -559,11 +622,18 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t swz_mask = p.wo == 128 ? 7u : (p.wo == 64 ? 3u : (p.wo == 32 ? 1u : 0u));
     const uint32_t row_base = (MODE & kEpiTma) ? uint32_t(r) * uint32_t(p.wo) : uint32_t(r) * uint32_t(p.pitch);
     const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.wo);
+    uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes >> 1);
+    long long* g_rowoff = s_rowoff + grp * kBM;
+    const int bar_id = 1 + grp;
     uint32_t pass_count = 0;
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      const int as = it & 1;
+      if ((it & 1) != grp) continue;
+      const int as = grp;
       const uint32_t use = uint32_t(it >> 1);
+      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 64;
+#define TOD_TR(slot) do { if (tr) p.trace[(it >> 1) * 16 + (slot)] = clock64(); } while (0)
+      TOD_TR(0);
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
       const int x = w.tx * p.pw + wx, yy = w.ty * p.ph + wy, n = w.g * p.pn + wn;
       int cls = 0;
@@ -584,7 +654,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int4* qrow = s_qtab + ocb;
       if (!(MODE & kEpiTma)) {
         const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
-        s_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
+        g_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
       }
       const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
       const int8_t* rrow = nullptr;                   // this pixel's residual bytes (kEpiAdd)
@@ -593,19 +663,22 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (valid) rrow = p.resid + (p.flat ? 0ll : (long long)n * p.resid_ts) + ((long long)yy * Wd + x) * p.OC + ocb;
       }
 
+      TOD_TR(1);
       mbar_wait(&ctl->acc_full[as], use & 1);
       tc_fence_after();
+      TOD_TR(2);
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
       for (int pass0 = 0; pass0 < ncols_tile; pass0 += p.sc) {
         const int pass_cols = min(p.sc, ncols_tile - pass0);
-        uint8_t* sbuf = stage_buf + ((MODE & kEpiTma) ? (pass_count & 1u) * buf_bytes : 0u);
+        uint8_t* sbuf = grp_buf + ((MODE & kEpiTma) ? (pass_count & 1u) * buf_bytes : 0u);
         ++pass_count;
-        for (int c0 = half * 16; c0 < pass_cols; c0 += 32) {
+        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + pass0 + c0, v);
           uint4 rres = make_uint4(0u, 0u, 0u, 0u);
           if ((MODE & kEpiAdd) && rrow) rres = *reinterpret_cast<const uint4*>(rrow + pass0 + c0);
           tmem_wait_ld();
+          TOD_TR(3);
           uint32_t packed[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -646,42 +719,47 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (MODE & kEpiTma) off ^= ((off >> 7) & swz_mask) << 4;
           *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
+        TOD_TR(4);
         if (pass0 + p.sc >= ncols_tile) {  // accumulator fully read: hand the TMEM stage back before the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
         }
         if (MODE & kEpiTma) {
-          if (et == 0) tma_store_wait_read();   // the previous pass' store has drained the *other* buffer
+          TOD_TR(5);
+          if (eg == 0) tma_store_wait_read();   // this group's previous store has drained the *other* buffer
+          TOD_TR(6);
           fence_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (et == 0) {
+          TOD_TR(7);
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          TOD_TR(8);
+          if (eg == 0 && !(p.dbg & 1)) {
             if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * kBM, 0, 0);
             else tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * p.pw, w.ty * p.ph, w.g * p.pn);
             tma_store_commit();
           }
         } else {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (p.vec_store) {
             const int cpr = pass_cols >> 4;
-            for (int idx = et; idx < kBM * cpr; idx += kEpiThreads) {
+            for (int idx = eg; idx < kBM * cpr; idx += 128) {
               const int rr = idx / cpr, ch = idx - rr * cpr;
-              const long long off = s_rowoff[rr];
+              const long long off = g_rowoff[rr];
               if (off >= 0)
                 *reinterpret_cast<uint4*>(p.out + off + ocb + pass0 + ch * 16) = *reinterpret_cast<const uint4*>(sbuf + size_t(rr) * p.pitch + ch * 16);
             }
           } else {
-            for (int idx = et; idx < kBM * pass_cols; idx += kEpiThreads) {
+            for (int idx = eg; idx < kBM * pass_cols; idx += 128) {
               const int rr = idx / pass_cols, bb = idx - rr * pass_cols;
-              const long long off = s_rowoff[rr];
+              const long long off = g_rowoff[rr];
               if (off >= 0) p.out[off + ocb + pass0 + bb] = int8_t(sbuf[size_t(rr) * p.pitch + bb]);
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
       }
     }
-    if ((MODE & kEpiTma) && et == 0) tma_store_wait_read();  // staging must outlive the last store's reads
+    if ((MODE & kEpiTma) && eg == 0) tma_store_wait_read();  // staging must outlive the last store's reads
   }
 
   tc_fence_before();
@@ -723,8 +801,11 @@ int encode(CUtensorMap* map, const void* base_c, int rank, const uint64_t* dims,
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   const CUtensorMapSwizzle sw = bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+  static const int promo_env = std::getenv("TOD_TMA_PROMO") ? std::atoi(std::getenv("TOD_TMA_PROMO")) : -1;
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (promo_env >= 0) promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, cuuint32_t(rank), base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TOD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu/%llu, box %u/%u)", int(r), rank,
                                      (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
   return TOD_OK;
@@ -798,6 +879,21 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.stride = g.stride_h;
   p.BK = (g.IC % 128 == 0) ? 128 : ((g.IC % 64 == 0) ? 64 : 32);
   p.kchunks = (g.IC + p.BK - 1) / p.BK;
+  // flat (dense 1x1) layers whose pixel rows are shorter than a 128-byte TMA row: cp.async gathers A instead, which also
+  // frees the K chunk from having to divide IC (the tail is zero-filled chunk by chunk)
+  static const int cp_env = std::getenv("TOD_TC_CP") ? std::atoi(std::getenv("TOD_TC_CP")) : -1;
+  const bool want_cp = a.fast_epilogue && a.h_mult && a.h_shift && g.KH == 1 && g.KW == 1 && g.stride_h == 1 &&
+                       a.in_tile_stride == int64_t(g.IH) * g.IW * g.IC && a.out_tile_stride == int64_t(g.OH) * g.OW * g.OC && g.IH == g.OH &&
+                       g.IW == g.OW && (cp_env >= 0 ? cp_env != 0 : g.IC % 128 != 0);
+  if (want_cp) {
+    p.BK = g.IC <= 32 ? 32 : (g.IC <= 64 ? 64 : 128);
+    p.kchunks = (g.IC + p.BK - 1) / p.BK;
+  }
+  p.a_cp = want_cp ? 1 : 0;
+  p.dbg = std::getenv("TOD_TC_DBG") ? std::atoi(std::getenv("TOD_TC_DBG")) : 0;
+  p.trace = nullptr;
+  p.in = a.in;
+  p.IC = g.IC;
   p.n_tiles = (g.OC + 255) / 256;
   // several N tiles: full 256-column tiles, so a 128-column TMA-store pass never overhangs into the next tile's
   // columns (the last tile's overhang is clipped at the tensor edge; its weight rows past OC are TMA zero fill)
@@ -898,6 +994,16 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     for (size_t i = 0; i < xmasks.size(); ++i) p.xmap[xmasks[i] & 7] = uint8_t(i);
   const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * 4 : 0;
   if (table_bytes > 40 * 1024) c->fast = 0;
+  if (p.a_cp && !c->fast) {  // the general-epilogue kernel only has the TMA producer: back to a K chunk that TMA can serve
+    p.a_cp = 0;
+    p.BK = (g.IC % 128 == 0) ? 128 : ((g.IC % 64 == 0) ? 64 : 32);
+    p.kchunks = (g.IC + p.BK - 1) / p.BK;
+    p.sbo = 8u * uint32_t(p.BK);
+    p.layout = p.BK == 128 ? 2u : (p.BK == 64 ? 4u : 6u);
+    p.a_stage = uint32_t((kBM * p.BK + 1023) / 1024 * 1024);
+    p.b_stage = uint32_t((p.BN * p.BK + 1023) / 1024 * 1024);
+    p.tx_bytes = uint32_t(p.rows * p.BK + p.BN * p.BK);
+  }
   c->mode = 0;
   if (c->fast) {
     if (a.rq.act_min == -128 && a.rq.act_max == 127) c->mode |= kEpiSat;
@@ -912,16 +1018,16 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     p.wo = width <= 16 ? 16 : (width <= 32 ? 32 : (width <= 64 ? 64 : 128));
     p.sc = p.wo;
     p.pitch = p.wo;
-    p.stage_bytes = uint32_t(2 * kBM * p.wo);
+    p.stage_bytes = uint32_t(4 * kBM * p.wo);  // two epilogue groups x double buffer
   } else {
     p.wo = 0;
     p.sc = std::min(p.BN, 128);
     int pitch16 = p.sc / 16 + 1;
     if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
     p.pitch = pitch16 * 16;
-    p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024);
+    p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024) * 2u;  // one staging tile per epilogue group
   }
-  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 8 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
+  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 16 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
   const size_t budget = 227 * 1024 - fixed;
   p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
@@ -1156,7 +1262,27 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
     a.fast_epilogue = (flags & 4) ? 0 : 1;
     rc = conv_tc_create(a, &plan);
   }
+  long long* d_trace = nullptr;
+  if (rc == TOD_OK && std::getenv("TOD_TC_TRACE")) {
+    cudaMalloc(&d_trace, 32 * 16 * 8);
+    cudaMemset(d_trace, 0, 32 * 16 * 8);
+    plan->p.trace = d_trace;
+  }
   if (rc == TOD_OK) rc = conv_tc_launch(plan, tiles, nullptr);
+  if (rc == TOD_OK && d_trace) {
+    cudaDeviceSynchronize();
+    rc = conv_tc_launch(plan, tiles, nullptr);  // warm second run is the one reported
+    cudaDeviceSynchronize();
+    long long h[32 * 16];
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int t = 0; t < 12; ++t) {
+      std::printf("tile %2d t0=%8lld :", t, h[t * 16] - h[0]);
+      for (int k = 1; k <= 8; ++k) std::printf(" %6lld", h[t * 16 + k] - h[t * 16 + k - 1]);
+      std::printf("\n");
+    }
+    plan->p.trace = nullptr;
+    cudaFree(d_trace);
+  }
   if (rc == TOD_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(TOD_ERR_CUDA, "tcgen05 conv kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc == TOD_OK) {
     cudaEventRecord(e0);
