@@ -223,18 +223,38 @@ def main():
         e2e_s = float(t.item())
     e2e = world * frames_per_step * args.steps / e2e_s
 
-    # ---- roofline of the dominant kernel (per-launch CUDA events on the launching stream)
+    # ---- roofline of the dominant kernel: conv_tc_fast_kernel (tcgen05 int8 implicit GEMM), every launch of one step.
+    # achieved = algorithmic ops of those launches (2 * MACs, SURVEY 8d: 11.24 Gop/tile over the whole graph) / the sum of
+    # their CUDA-event durations on the launching stream; peak = tcgen05 kind::i8 tensor-pipe peak measured in this
+    # process (MEASURED_PEAKS.json has no int8 entry; 2 x its bf16 burst figure is reported beside it).
     peaks = _peaks()
     ms_ops, kinds = y.profile_ops(n)
-    conv_ms = float(sum(m for m, k in zip(ms_ops, kinds) if (k & 0xFFF) == 3))
+    ms_ops2, _ = y.profile_ops(n)
+    ms_ops = np.minimum(ms_ops, ms_ops2)
+    macs_ops = y.step_macs()
+    is_tc = (kinds & 0x1000) != 0
+    tc_ms = float(ms_ops[is_tc].sum())
+    tc_macs = float(macs_ops[is_tc].sum()) * n
     total_ops_ms = float(ms_ops.sum())
-    conv_macs = st["macs_per_tile"] * n
-    int8_peak = 2.0 * peaks["bf16"]  # no measured int8 figure in MEASURED_PEAKS.json: dense int8 is nominally 2x bf16
-    achieved = 2.0 * conv_macs / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s", "frac": achieved / int8_peak, "traffic": None,
-                "kernel": "all CONV_2D/DEPTHWISE launches of one step (sum of per-launch CUDA-event times)",
-                "peak_source": "2 x %s bf16 burst (%s); int8 peak not in MEASURED_PEAKS.json" % (peaks["bf16"], peaks["src"]),
-                "conv_ms_per_step": conv_ms, "all_ops_ms_per_step": total_ops_ms, "tc_conv_layers": st["tc_conv_layers"]}
+    i8_peak = tod_b200._lib.i8_mma_peak(n_mma=20000, iters=5, device=local_rank)
+    achieved = 2.0 * tc_macs / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    big = int(np.argmax(np.where(is_tc, macs_ops, 0)))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s", "frac": achieved / i8_peak if i8_peak else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "conv_tc_fast_kernel: all %d tcgen05 conv launches of one step (per-launch CUDA events, summed)" % int(is_tc.sum()),
+                "launches": int(is_tc.sum()), "avg_launch_ms": tc_ms / max(1, int(is_tc.sum())),
+                "algorithmic_gop_per_launch": 2.0 * tc_macs / max(1, int(is_tc.sum())) / 1e9,
+                "peak_source": "tcgen05.mma.kind::i8 issue-only micro-benchmark (tod_i8_mma_peak) measured in this run; MEASURED_PEAKS.json has no int8 entry (2 x its bf16 burst = %.0f TOP/s, %s)" % (2.0 * peaks["bf16"], peaks["src"]),
+                "largest_launch": {"gop": 2.0 * float(macs_ops[big]) * n / 1e9, "ms": float(ms_ops[big]),
+                                   "top_s": 2.0 * float(macs_ops[big]) * n / (float(ms_ops[big]) * 1e-3) / 1e12 if ms_ops[big] > 0 else None},
+                "tc_ms_per_step": tc_ms, "all_ops_ms_per_step": total_ops_ms, "tc_conv_layers": st["tc_conv_layers"],
+                "hbm": {"algorithmic_bytes_per_step": 19.5e6 * n, "ms_per_step": ms / args.steps,
+                        "achieved_GBps": 19.5e6 * n / (ms / args.steps * 1e-3) / 1e9, "peak_GBps": peaks["hbm"]}}
 
     line = {
         "metric": "yolact_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

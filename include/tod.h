@@ -209,6 +209,11 @@ int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int 
  * SURVEY §8d): a plain tcgen05 kind::i8 GEMM  C[M,N] s32 = A[M,K] s8 * B[N,K]^T s8.
  * ====================================================================================== */
 int tod_i8_gemm_selftest(int device, int M, int N, int K, int iters, float* ms_per_iter, double* max_abs_err);
+/* Tensor-pipe peak of tcgen05.mma.kind::i8: every SM issues n_mma M=128 x N=256 x K=32 MMAs from resident shared
+ * memory (no loads, no epilogue); *tops = best of `iters` launches in TOP/s.  The conv roofline's denominator. */
+int tod_i8_mma_peak(int device, int n_mma, int iters, double* tops);
+/* multiply-accumulates per tile of every planned step, in tod_yolact_profile_ops order; returns the step count */
+int tod_yolact_step_macs(const tod_yolact* y, int64_t* macs, int cap);
 
 /* One KxK (K = 1 or 3), stride-1, SAME convolution [tiles,H,W,IC] -> [tiles,H,W,OC] on seeded random data through
  * both the tcgen05 implicit-GEMM kernel and the CUDA-core direct kernel: times both and counts differing bytes. */

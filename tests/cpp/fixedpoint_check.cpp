@@ -38,6 +38,26 @@ int main() {
   for (long long i = 0; i < 2000000; ++i) {  // the generic form over the full int32 range, either sign of q
     check(int32_t(rng()), int32_t(rng()), -int(rng() % 31));
   }
+  // the tabulated epilogue form (zero point and rounding term folded into the 64-bit addend)
+  auto check_tab = [&](int32_t x, int32_t qq, int rs, int zp) {
+    const int32_t want = oracle::MBQM(x, qq, -rs) + zp;
+    const int32_t got = tod::requant_tab(x, qq, rs, (1 << (rs - 1)) + zp * (1 << rs));
+    ++n;
+    if (want != got) { if (bad < 5) std::printf("tab mismatch x=%d q=%d rs=%d zp=%d: %d vs %d\n", x, qq, rs, zp, want, got); ++bad; }
+  };
+  const int32_t xe[] = {0, 1, -1, 2, -2, 3, -3, 127, -128, 1000, -1000, (1 << 20), -(1 << 20), (1 << 28), -(1 << 28), (1 << 29) - 1, -(1 << 29) + 1};
+  const int32_t qe[] = {0, 1 << 30, (1 << 30) + 1, 0x7FFFFFFF, 1518500250, 2000000000};
+  for (int32_t x : xe)
+    for (int32_t qq : qe)
+      for (int rs = 1; rs <= 22; ++rs)
+        for (int zp : {-128, -3, 0, 5, 127, 128}) check_tab(x, qq, rs, zp);
+  for (int rs = 1; rs <= 14; ++rs)  // exact .5 ties of the rounding shift, both signs
+    for (int k = -5000; k <= 5000; ++k) check_tab(k, 1 << 30, rs, -128), check_tab(2 * k + 1, 1 << 30, rs, 7), check_tab(k, (1 << 30) + (1 << 29), rs, 0);
+  for (long long i = 0; i < 10000000; ++i) {
+    const int32_t x = int32_t(rng() % (1u << 30)) - (1 << 29);
+    const int32_t qq = rng() % 64 == 0 ? int32_t(rng() % (1u << 30)) : int32_t((1u << 30) + rng() % (1u << 30));
+    check_tab(x, qq, 1 + int(rng() % 22), int(rng() % 257) - 128);
+  }
   int32_t q; int sh, q2, sh2;
   for (int i = 0; i < 200000; ++i) {
     const double m = std::ldexp(0.5 + (rng() % 1000000) / 2000000.0, -int(rng() % 40) + 3);

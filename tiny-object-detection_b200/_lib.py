@@ -25,7 +25,7 @@ SYMBOLS = [
     "tod_yolact_num_ops", "tod_yolact_tensor_info", "tod_yolact_infer_tiles", "tod_yolact_infer_tiles_device",
     "tod_yolact_fetch_output", "tod_yolact_fetch_tensor", "tod_yolact_fetch_tile_classes", "tod_yolact_fetch_detections",
     "tod_yolact_stats", "tod_yolact_profile_ops", "tod_i8_gemm_selftest", "tod_conv_selftest",
-    "tod_conv_selftest_ex",
+    "tod_conv_selftest_ex", "tod_i8_mma_peak", "tod_yolact_step_macs",
 ]
 
 
@@ -102,6 +102,8 @@ def lib():
         L.tod_i8_gemm_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.tod_conv_selftest.argtypes = [C.c_int] * 8 + [vp, vp, vp]
         L.tod_conv_selftest_ex.argtypes = [C.c_int] * 9 + [vp, vp, vp]
+        L.tod_i8_mma_peak.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+        L.tod_yolact_step_macs.argtypes = [vp, vp, C.c_int]
         _lib = L
     return _lib
 
@@ -124,3 +126,10 @@ def device_count():
     n = C.c_int(0)
     rc = lib().tod_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def i8_mma_peak(n_mma=20000, iters=5, device=0):
+    """Measured tensor-pipe peak of tcgen05.mma.kind::i8 in TOP/s (no loads, no epilogue)."""
+    v = C.c_double(0.0)
+    check(lib().tod_i8_mma_peak(device, n_mma, iters, C.byref(v)))
+    return v.value

@@ -689,7 +689,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int j = 0; j < 4; ++j) {
               const int4 k = qrow[col + j];  // {q, rs, 2^31, half + (zp << rs)}: z:w is the 64-bit addend, in place
               const int bj = j == 0 ? b4.x : (j == 1 ? b4.y : (j == 2 ? b4.z : b4.w));
-              const int x2 = int(v[4 * q4 + j]) * 2 + bj;
+              int x2;  // 2 * acc + 2 * bias on the FMA pipe (IMAD): the ALU pipe is the epilogue's bottleneck
+              asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(x2) : "r"(int(v[4 * q4 + j])), "r"(bj));
               const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
               const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
               o[j] = (t + (x2 >> 31)) >> k.y;  // sign(x2) == sign(v) wherever the rounding term can matter
@@ -1181,6 +1182,79 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
 }
 
 }  // namespace tod
+
+// ------------------------------------------------------------------ tensor-pipe peak for kind::i8
+// MEASURED_PEAKS.json records HBM and bf16 peaks only; the conv roofline needs the int8 one.  One CTA per SM keeps a
+// 128 x 128 B A tile and a 256 x 128 B B tile resident in shared memory and one thread issues `n_mma`
+// tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32) back to back into one TMEM accumulator: no loads, no epilogue.
+namespace tod {
+namespace {
+__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int n_mma, uint32_t idesc) {
+  extern __shared__ uint8_t peak_raw[];
+  uint8_t* smem = peak_raw + ((1024u - (smem_u32(peak_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u * uint32_t(i & 3);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 128 * 128);
+    for (int i = 0; i < n_mma; ++i) {
+      const int kk = i & 3;
+      umma_i8(tmem, make_desc(a_addr + kk * 32, 1024u, 2u), make_desc(b_addr + kk * 32, 1024u, 2u), idesc, i ? 1u : 0u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+}  // namespace
+}  // namespace tod
+
+extern "C" int tod_i8_mma_peak(int device, int n_mma, int iters, double* tops) {
+  using namespace tod;
+  if (n_mma < 1 || iters < 1 || !tops) return fail(TOD_ERR_INVALID_ARG, "tod_i8_mma_peak: bad argument");
+  TOD_TRY(select_device(device));
+  const size_t smem = (128 + 256) * 128 + 1024;
+  TOD_CUDA(cudaFuncSetAttribute(i8_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(256 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  const int sms = sm_count();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc);
+  TOD_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int i = 0; i < iters; ++i) {
+    cudaEventRecord(e0);
+    i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc);
+    cudaEventRecord(e1);
+    TOD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tops = 2.0 * 128 * 256 * 32 * double(n_mma) * sms / (double(best) * 1e-3) / 1e12;
+  return TOD_OK;
+}
 
 // ------------------------------------------------------------------ self tests / micro-benchmark (C ABI)
 using namespace tod;

@@ -60,6 +60,18 @@ TOD_HD int32_t mul_by_quant_mult_fast(int32_t x, int32_t q, int shift) {
   return (v + half + neg) >> right;
 }
 
+// The tabulated form the conv / depthwise epilogues run (conv_tc.cu, ops.cu; table = Requant::fast_tab):
+//   requant_tab(x, q, rs, (1 << (rs-1)) + (zp << rs))  ==  mul_by_quant_mult(x, q, -rs) + zp
+// for q >= 0, 1 <= rs <= 22, |x| < 2^29, |zp| <= 128.  hi32(2x*q + 2^31) is SRDHM's result v; the rounding term
+// and the output zero point ride in the high word of the 64-bit addend; sign(2x) stands in for sign(v): they differ
+// only where v == 0 (x < 0 with x*q > -2^30), and there (half - 1) >> rs == half >> rs == 0 anyway.
+TOD_HD int32_t requant_tab(int32_t x, int32_t q, int rs, int32_t halfp) {
+  const int32_t x2 = int32_t(uint32_t(x) * 2u);
+  const int64_t addend = int64_t((uint64_t(uint32_t(halfp)) << 32) | 0x80000000ull);
+  const int32_t t = int32_t((int64_t(x2) * int64_t(q) + addend) >> 32);
+  return (t + (x2 >> 31)) >> rs;
+}
+
 // host only: real multiplier -> (Q31 mantissa, exponent)
 inline void quantize_multiplier(double m, int32_t* q, int* shift) {
   if (m == 0.0) {

@@ -445,10 +445,7 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
     int o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int x2 = acc[q] * 2;
-      const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k[q].w)) << 32) | uint32_t(k[q].z));
-      const int t = int((static_cast<long long>(x2) * k[q].x + addend) >> 32);
-      o[q] = (t + (x2 >> 31)) >> k[q].y;
+      o[q] = requant_tab(acc[q], k[q].x, k[q].y, k[q].w);
     }
     unsigned packed;
     if (SAT) {

@@ -1506,6 +1506,16 @@ int tod_yolact_stats(const tod_yolact* y, int64_t* macs_per_tile, int32_t* launc
   return TOD_OK;
 }
 
+int tod_yolact_step_macs(const tod_yolact* y, int64_t* macs, int cap) {
+  if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_step_macs: null handle");
+  int i = 0;
+  for (const Step& st : y->steps) {
+    if (macs && i < cap) macs[i] = st.macs;
+    ++i;
+  }
+  return i;
+}
+
 int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int cap) {
   if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_profile_ops: null handle");
   if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_profile_ops: n=%d outside [1,%d]", n, y->opt.max_tiles);

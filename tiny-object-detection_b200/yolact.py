@@ -150,6 +150,12 @@ class Yolact:
         k = check(lib().tod_yolact_profile_ops(self._h, n, _ptr(ms), _ptr(kinds), cap))
         return ms[:k], kinds[:k]
 
+    def step_macs(self):
+        cap = 512
+        m = np.zeros(cap, np.int64)
+        k = check(lib().tod_yolact_step_macs(self._h, _ptr(m), cap))
+        return m[:k]
+
     # ------------------------------------------------------------------ helpers
     def _proto_hw(self):
         sp = [o["shape"] for i, o in enumerate(self.outputs) if o["shape"][1] > 1 and i != 4]
