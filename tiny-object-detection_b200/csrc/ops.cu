@@ -269,6 +269,125 @@ __global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __r
   }
 }
 
+// ------------------------------------------------------------------ stem: 3x3, stride 2, Cin = 3
+// The RGB stem is too thin for the tensor cores (K = 27) and was the slowest CUDA-core layer.  With Cin = 3 the three
+// pixels under one filter row are nine contiguous bytes, so a filter row is three (unaligned, funnel-shifted) words and
+// nine dp4a per output channel cover the whole 3x3x3 window (weights padded to 12 bytes per row with zeros).
+// Thread = one output pixel x 16 channels; the packed weights sit in shared memory and are read as warp-wide
+// broadcasts.  Out-of-image taps (TFLite SAME puts the single padding row / column at the bottom / right here) read as
+// the zero point, with the bias pre-folded as bias - zp * sum(w); requantisation is the Requant::fast_tab form.
+constexpr int kStemThreads = 128;
+constexpr int kStemOct = 16;
+
+template <bool SAT>
+__global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                                const int8_t* __restrict__ w, const int32_t* __restrict__ bias,
+                                                                int32_t in_zp, ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                                int64_t out_ts, int tiles) {
+  __shared__ int4 s_w[9 * 8 * 4];   // [filter row][word 0..2][channel group of 4 (<= 8 groups)] -> 4 channels' weight words... see fill below
+  __shared__ int s_bs[64];
+  __shared__ int4 s_k[64];
+  pdl_trigger();
+  const int OCg = g.OC;  // <= 64 here (launcher checks)
+  // s_wi[(fy*3 + k) * OC + oc] = weight bytes 4k .. 4k+3 of filter row fy (9 real bytes: 3 pixels x 3 channels), 0-padded
+  int* s_wi = reinterpret_cast<int*>(s_w);
+  for (int i = threadIdx.x; i < 9 * OCg; i += kStemThreads) {
+    const int oc = i % OCg, fk = i / OCg, fy = fk / 3, k = fk - fy * 3;
+    int word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = 4 * k + b;  // byte of the 9-byte row: pixel fx = j / 3, channel j % 3
+      if (j < 9) word |= (int(w[(int64_t(oc) * 9 + fy * 3 + j / 3) * 3 + j % 3]) & 0xFF) << (8 * b);
+    }
+    s_wi[i] = word;
+  }
+  for (int oc = threadIdx.x; oc < OCg; oc += kStemThreads) {
+    int sum = 0;
+    for (int j = 0; j < 27; ++j) sum += int(w[int64_t(oc) * 27 + j]);
+    s_bs[oc] = (bias ? bias[oc] : 0) - in_zp * sum;
+    s_k[oc] = rq.fast_tab[oc];
+  }
+  __syncthreads();
+  pdl_wait();
+  const int groups = OCg / kStemOct;
+  const int64_t idx = int64_t(blockIdx.x) * kStemThreads + threadIdx.x;
+  const int64_t total = int64_t(tiles) * g.OH * g.OW * groups;
+  if (idx >= total) return;
+  const int grp = int(idx % groups);
+  int64_t pix = idx / groups;
+  const int ox = int(pix % g.OW);
+  pix /= g.OW;
+  const int oy = int(pix % g.OH);
+  const int t = int(pix / g.OH);
+  const int oc0 = grp * kStemOct;
+  const int zp4 = (in_zp & 0xFF) * 0x01010101;
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  const int ix0 = ox * 2, iy0 = oy * 2;  // pad_top = pad_left = 0 (launcher checks)
+  int acc[kStemOct];
+#pragma unroll
+  for (int j = 0; j < kStemOct; ++j) acc[j] = s_bs[oc0 + j];
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+    int a0 = zp4, a1 = zp4, a2 = zp4;
+    const int iy = iy0 + fy;
+    if (iy < g.IH) {
+      const int64_t off = (int64_t(iy) * g.IW + ix0) * 3;          // even: 0 or 2 mod 4
+      const int* p = reinterpret_cast<const int*>(tin + (off & ~int64_t(3)));
+      const int w0 = p[0], w1 = p[1], w2 = p[2];
+      if (off & 2) {
+        a0 = __funnelshift_r(w0, w1, 16);
+        a1 = __funnelshift_r(w1, w2, 16);
+        a2 = int(unsigned(w2) >> 16);
+      } else {
+        a0 = w0;
+        a1 = w1;
+        a2 = w2;
+      }
+      // bytes of pixels to the right of the image read as the zero point (only the last output column)
+      const int valid_px = g.IW - ix0;  // 1, 2 or >= 3 pixels of this row exist
+      if (valid_px < 3) {
+        // byte j belongs to pixel j / 3: keep the bytes of pixels < valid_px (6 bytes or 3 bytes), the rest read as zp
+        const int k0 = valid_px == 2 ? int(0xFFFFFFFFu) : 0x00FFFFFF;
+        const int k1 = valid_px == 2 ? 0x0000FFFF : 0;
+        a0 = (a0 & k0) | (zp4 & ~k0);
+        a1 = (a1 & k1) | (zp4 & ~k1);
+        a2 = zp4;
+      }
+    }
+    const int4* wr0 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 0) * OCg + oc0);
+    const int4* wr1 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 1) * OCg + oc0);
+    const int4* wr2 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 2) * OCg + oc0);
+#pragma unroll
+    for (int q = 0; q < kStemOct / 4; ++q) {
+      const int4 u0 = wr0[q], u1 = wr1[q], u2 = wr2[q];
+      acc[4 * q + 0] = __dp4a(a2, u2.x, __dp4a(a1, u1.x, __dp4a(a0, u0.x, acc[4 * q + 0])));
+      acc[4 * q + 1] = __dp4a(a2, u2.y, __dp4a(a1, u1.y, __dp4a(a0, u0.y, acc[4 * q + 1])));
+      acc[4 * q + 2] = __dp4a(a2, u2.z, __dp4a(a1, u1.z, __dp4a(a0, u0.z, acc[4 * q + 2])));
+      acc[4 * q + 3] = __dp4a(a2, u2.w, __dp4a(a1, u1.w, __dp4a(a0, u0.w, acc[4 * q + 3])));
+    }
+  }
+  unsigned packed[kStemOct / 4];
+#pragma unroll
+  for (int q = 0; q < kStemOct / 4; ++q) {
+    int o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int4 k = s_k[oc0 + 4 * q + j];
+      o[j] = requant_tab(acc[4 * q + j], k.x, k.y, k.w);
+    }
+    if (SAT) {
+      unsigned hi;
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o[3]), "r"(o[2]), "r"(0u));
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(packed[q]) : "r"(o[1]), "r"(o[0]), "r"(hi));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = max(rq.act_min, min(rq.act_max, o[j]));
+      packed[q] = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + oc0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 // ------------------------------------------------------------------ depthwise, register-resident filters
 // blockDim = (channel groups of 4, pixel lanes).  A thread keeps the 3x3 taps of its 4 channels (pre-masked so a
 // dp4a isolates one channel), their bias and requantisation constants in registers and walks over output pixels;
@@ -680,6 +799,18 @@ inline int grid_for(int64_t work_items, int threads, int tiles) {
 void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const int32_t* bias, const int32_t* wsum,
                         int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles,
                         cudaStream_t s) {
+  // the RGB stem: 3x3, stride 2, no top / left padding, 16-byte-aligned 16-channel output groups
+  if (g.IC == 3 && g.KH == 3 && g.KW == 3 && g.stride_h == 2 && g.stride_w == 2 && g.dil_h == 1 && g.dil_w == 1 && g.pad_top == 0 &&
+      g.pad_left == 0 && g.OC % 16 == 0 && g.OC <= 64 && rq.fast_tab && !rq.post_lut && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (in_ts & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_ts & 15) == 0 && (g.IW * 3) % 2 == 0) {
+    const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
+    dim3 grid(unsigned((total + kStemThreads - 1) / kStemThreads));
+    if (rq.act_min == -128 && rq.act_max == 127)
+      launch_k(stem3x3s2_kernel<true>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+    else
+      launch_k(stem3x3s2_kernel<false>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+    return;
+  }
   // preferred CUDA-core path: shared-memory weight slab, one thread per pixel x 16 channels
   const int taps = g.KH * g.KW, icw = (g.IC + 3) / 4;
   const size_t pix_smem = size_t(taps) * icw * kPixOct * 4 + size_t(taps) * kPixOct * 4;
