@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kPixThreads) conv_pix_kernel(const int8_t* __r
 // the zero point, with the bias pre-folded as bias - zp * sum(w); requantisation is the Requant::fast_tab form.
 constexpr int kStemThreads = 128;
 constexpr int kStemOct = 16;
+constexpr int kStemIters = 8;
 
 template <bool SAT>
 __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* __restrict__ in, int64_t in_ts,
@@ -310,8 +311,10 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
   __syncthreads();
   pdl_wait();
   const int groups = OCg / kStemOct;
-  const int64_t idx = int64_t(blockIdx.x) * kStemThreads + threadIdx.x;
   const int64_t total = int64_t(tiles) * g.OH * g.OW * groups;
+  // kStemIters work items per thread: the packed-weight prologue above is amortised over 1024 outputs-groups per CTA
+  for (int rep = 0; rep < kStemIters; ++rep) {
+  const int64_t idx = (int64_t(blockIdx.x) * kStemIters + rep) * kStemThreads + threadIdx.x;
   if (idx >= total) return;
   const int grp = int(idx % groups);
   int64_t pix = idx / groups;
@@ -386,6 +389,7 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
     }
   }
   *reinterpret_cast<uint4*>(out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + oc0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
 }
 
 // ------------------------------------------------------------------ depthwise, register-resident filters
@@ -522,49 +526,33 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
   const int ix0 = ox * STRIDE - g.pad_left;
   const bool vx0 = ix0 >= 0 && ix0 < g.IW, vx1 = ix0 + 1 >= 0 && ix0 + 1 < g.IW, vx2 = ix0 + 2 >= 0 && ix0 + 2 < g.IW;
   const int8_t* base = in + int64_t(blockIdx.z) * in_ts + int64_t(ix0) * C + c;
+  const int64_t row_pitch = int64_t(g.IW) * C;
   auto load_row = [&](int iy, int& a0, int& a1, int& a2) {
     a0 = a1 = a2 = zp4;
     if (iy >= 0 && iy < g.IH) {
-      const int8_t* p = base + int64_t(iy) * g.IW * C;
+      const int8_t* p = base + int64_t(iy) * row_pitch;
       if (vx0) a0 = *reinterpret_cast<const int*>(p);
       if (vx1) a1 = *reinterpret_cast<const int*>(p + C);
       if (vx2) a2 = *reinterpret_cast<const int*>(p + 2 * C);
     }
   };
   const int oy0 = blockIdx.y * rows_per_block, oy1 = min(g.OH, oy0 + rows_per_block);
-  int r0[3], r1[3], r2[3], n1[3], n2[3];
   int iy = oy0 * STRIDE - g.pad_top;
-  pdl_wait();  // filters / requantisation constants are in registers; the activations come next
-  load_row(iy, r0[0], r0[1], r0[2]);
-  load_row(iy + 1, r1[0], r1[1], r1[2]);
-  load_row(iy + 2, r2[0], r2[1], r2[2]);
   int8_t* op = out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c;
-  for (int oy = oy0; oy < oy1; ++oy, iy += STRIDE, op += int64_t(g.OW) * C) {
-    // the next output row's new input rows are requested before this row's arithmetic (software pipelining)
-    if (oy + 1 < oy1) {
-      if (STRIDE == 1) {
-        load_row(iy + 3, n2[0], n2[1], n2[2]);
-      } else {
-        load_row(iy + 3, n1[0], n1[1], n1[2]);
-        load_row(iy + 4, n2[0], n2[1], n2[2]);
-      }
-    }
-    int acc[4];
+  const int64_t ostep = int64_t(g.OW) * C;
+  // one output word from three window rows
+  auto emit = [&](const int (&ra)[3], const int (&rb)[3], const int (&rc)[3], int8_t* dst) {
+    int o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       int a = bs[q];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        a = __dp4a(r0[f], wm[f][q], a);
-        a = __dp4a(r1[f], wm[3 + f][q], a);
-        a = __dp4a(r2[f], wm[6 + f][q], a);
+        a = __dp4a(ra[f], wm[f][q], a);
+        a = __dp4a(rb[f], wm[3 + f][q], a);
+        a = __dp4a(rc[f], wm[6 + f][q], a);
       }
-      acc[q] = a;
-    }
-    int o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      o[q] = requant_tab(acc[q], k[q].x, k[q].y, k[q].w);
+      o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
     }
     unsigned packed;
     if (SAT) {
@@ -576,14 +564,42 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
       for (int q = 0; q < 4; ++q) o[q] = max(rq.act_min, min(rq.act_max, o[q]));
       packed = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
     }
-    *reinterpret_cast<unsigned*>(op) = packed;
+    *reinterpret_cast<unsigned*>(dst) = packed;
+  };
+  pdl_wait();  // filters / requantisation constants are in registers; the activations come next
+  if (STRIDE == 1) {
+    // four register rows rotate through the roles (top, middle, bottom, prefetch): the loop is unrolled by four so the
+    // rotation is pure renaming, and the next row's loads are issued before the current row's arithmetic
+    int ra[3], rb[3], rc[3], rd[3];
+    load_row(iy, ra[0], ra[1], ra[2]);
+    load_row(iy + 1, rb[0], rb[1], rb[2]);
+    load_row(iy + 2, rc[0], rc[1], rc[2]);
+    for (int oy = oy0; oy < oy1; oy += 4, iy += 4, op += 4 * ostep) {
+      if (oy + 1 < oy1) load_row(iy + 3, rd[0], rd[1], rd[2]);
+      emit(ra, rb, rc, op);
+      if (oy + 1 >= oy1) break;
+      if (oy + 2 < oy1) load_row(iy + 4, ra[0], ra[1], ra[2]);
+      emit(rb, rc, rd, op + ostep);
+      if (oy + 2 >= oy1) break;
+      if (oy + 3 < oy1) load_row(iy + 5, rb[0], rb[1], rb[2]);
+      emit(rc, rd, ra, op + 2 * ostep);
+      if (oy + 3 >= oy1) break;
+      if (oy + 4 < oy1) load_row(iy + 6, rc[0], rc[1], rc[2]);
+      emit(rd, ra, rb, op + 3 * ostep);
+    }
+  } else {
+    int r0[3], r1[3], r2[3], n1[3], n2[3];
+    load_row(iy, r0[0], r0[1], r0[2]);
+    load_row(iy + 1, r1[0], r1[1], r1[2]);
+    load_row(iy + 2, r2[0], r2[1], r2[2]);
+    for (int oy = oy0; oy < oy1; ++oy, iy += STRIDE, op += ostep) {
+      if (oy + 1 < oy1) {
+        load_row(iy + 3, n1[0], n1[1], n1[2]);
+        load_row(iy + 4, n2[0], n2[1], n2[2]);
+      }
+      emit(r0, r1, r2, op);
 #pragma unroll
-    for (int f = 0; f < 3; ++f) {
-      if (STRIDE == 1) {
-        r0[f] = r1[f];
-        r1[f] = r2[f];
-        r2[f] = n2[f];
-      } else {
+      for (int f = 0; f < 3; ++f) {
         r0[f] = r2[f];
         r1[f] = n1[f];
         r2[f] = n2[f];
@@ -804,7 +820,7 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
       g.pad_left == 0 && g.OC % 16 == 0 && g.OC <= 64 && rq.fast_tab && !rq.post_lut && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (in_ts & 3) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_ts & 15) == 0 && (g.IW * 3) % 2 == 0) {
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
-    dim3 grid(unsigned((total + kStemThreads - 1) / kStemThreads));
+    dim3 grid(unsigned((total + kStemThreads * kStemIters - 1) / (kStemThreads * kStemIters)));
     if (rq.act_min == -128 && rq.act_max == 127)
       launch_k(stem3x3s2_kernel<true>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
     else
