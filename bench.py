@@ -182,7 +182,6 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -222,6 +221,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = world * frames_per_step * args.steps / e2e_s
+    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
 
     # ---- roofline of the dominant kernel: conv_tc_fast_kernel (tcgen05 int8 implicit GEMM), every launch of one step.
     # achieved = algorithmic ops of those launches (2 * MACs, SURVEY 8d: 11.24 Gop/tile over the whole graph) / the sum of

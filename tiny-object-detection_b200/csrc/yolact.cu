@@ -153,6 +153,9 @@ struct tod_yolact {
   int64_t macs_per_tile = 0;
   int tc_layers = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // early read-back of the tile class maps while detection still runs
+  cudaEvent_t seg_ready = nullptr;      // recorded (as an external event node) inside the graph right after seg_post_kernel
+  bool seg_ready_in_graph = false;
   uint8_t* d_const = nullptr;
   uint8_t* d_act = nullptr;
   size_t act_bytes = 0;
@@ -1087,6 +1090,8 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
     const Place& ps = y->place[y->graph.outputs[y->seg_out]];
     SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
     launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, y->lanes[lane]);
+    // an external event node: the host-facing call starts copying the class maps back as soon as they exist
+    TOD_CUDA(cudaEventRecordWithFlags(y->seg_ready, y->lanes[lane], cudaEventRecordExternal));
     TOD_CUDA(cudaEventRecord(y->post_events[0], y->lanes[lane]));
     seg_done = true;
   }
@@ -1274,6 +1279,8 @@ void tod_yolact_destroy(tod_yolact* y) {
   cudaFree(y->d_tile_classes); cudaFree(y->d_diverges);
   if (y->h_diverges) cudaFreeHost(y->h_diverges);
   cudaFree(y->d_const); cudaFree(y->d_act);
+  if (y->copy_stream) cudaStreamDestroy(y->copy_stream);
+  if (y->seg_ready) cudaEventDestroy(y->seg_ready);
   if (y->stream) cudaStreamDestroy(y->stream);
   delete y;
 }
@@ -1297,6 +1304,8 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
     return rc;
   };
   cudaError_t ce = cudaStreamCreateWithFlags(&raw->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&raw->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&raw->seg_ready, cudaEventDisableTiming);
   if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
   ConstArena arena;
   int rc = plan(raw, &arena);
@@ -1468,7 +1477,14 @@ int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8
   if (outputs_u8)
     for (size_t k = 0; k < y->graph.outputs.size(); ++k)
       if (outputs_u8[k]) TOD_TRY(fetch_strided(outputs_u8[k], y->place[y->graph.outputs[k]], n, s));
-  if (tile_classes) TOD_CUDA(cudaMemcpyAsync(tile_classes, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, s));
+  if (tile_classes) {
+    // the class maps are final as soon as seg_post_kernel has run (the graph records y->seg_ready right behind it):
+    // read them back on a second stream while boxes / NMS / masks are still being computed
+    cudaStream_t cs = (y->opt.use_cuda_graph && y->seg_out >= 0) ? y->copy_stream : s;
+    if (cs != s) TOD_CUDA(cudaStreamWaitEvent(cs, y->seg_ready, 0));
+    TOD_CUDA(cudaMemcpyAsync(tile_classes, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, cs));
+    if (cs != s) TOD_CUDA(cudaStreamSynchronize(cs));
+  }
   TOD_CUDA(cudaStreamSynchronize(s));
   if (want_dets) TOD_TRY(tod_yolact_fetch_detections(y, n, dets));
   return check_diverged(y, n, s);
