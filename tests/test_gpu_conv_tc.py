@@ -53,3 +53,16 @@ def test_conv_tc_stride2(tod, shape, flags):
     from tod_b200 import _lib
     ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=1, flags=flags)
     assert bad == 0, "%d bytes differ (stride 2, flags %d)" % (bad, flags)
+
+
+# CTA-pair kernel (cta_group::2): shapes with >= 64 M tiles and >= 8 K iterations; odd tile counts leave the odd CTA a dummy tile
+PAIR_SHAPES = [(16, 28, 28, 256, 256, 3), (9, 56, 56, 256, 256, 3), (33, 14, 14, 256, 256, 3), (1, 1, 20000, 1024, 256, 1),
+               (17, 28, 28, 128, 96, 3), (40, 14, 14, 256, 64, 3)]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["sat", "clamp"])
+@pytest.mark.parametrize("shape", PAIR_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_pair(tod, shape, flags):
+    from tod_b200 import _lib
+    ms_tc, ms_direct, bad = _lib.conv_selftest(*shape, iters=1, flags=flags)
+    assert bad == 0, "%d bytes differ (CTA-pair path, flags %d)" % (bad, flags)

@@ -136,6 +136,16 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {  // arrives onc
 }
 constexpr int kCpThreads = 96;
 
+__device__ __forceinline__ bool elect_one() {  // true in exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -270,6 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint64_t adesc0 = make_desc(smem_u32(smem_a), p.sbo, p.layout), bdesc0 = make_desc(smem_u32(smem_b), p.sbo, p.layout);
+    const uint32_t a_step = p.a_stage >> 4, b_step = p.b_stage >> 4;  // descriptor address field is in 16-byte units
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -282,18 +295,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem_a + size_t(stage) * p.a_stage);
-          const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * p.b_stage);
-          for (int kk = 0; kk < p.BK / 32; ++kk) {
-            const uint64_t ad = make_desc(a_addr + kk * 32, p.sbo, p.layout);
-            const uint64_t bd = make_desc(b_addr + kk * 32, p.sbo, p.layout);
-            umma_i8(tmem_d, ad, bd, p.idesc, (k | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(&ctl->empty[stage]);                     // frees the smem stage when these MMAs retire
+        // the whole warp runs this loop converged with warp-uniform values, so the descriptors live in uniform registers;
+        // only the tcgen05 instructions themselves are predicated on the elected lane
+        const uint64_t ad0 = adesc0 + uint64_t(uint32_t(stage) * a_step), bd0 = bdesc0 + uint64_t(uint32_t(stage) * b_step);
+        for (int kk = 0; kk < p.BK / 32; ++kk)
+          if (leader) umma_i8(tmem_d, ad0 + uint64_t(2 * kk), bd0 + uint64_t(2 * kk), p.idesc, (k | kk) != 0 ? 1u : 0u);
+        if (leader) {
+          umma_commit(&ctl->empty[stage]);                       // frees the smem stage when these MMAs retire
           if (k == k_iters - 1) umma_commit(&ctl->acc_full[as]);  // accumulator complete
         }
-        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -562,9 +572,13 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int fy = tap / p.KW, fx = tap - fy * p.KW;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
+            if (p.dbg & 4) {  // timing experiment: no operand traffic at all
+              mbar_arrive(&ctl->full[stage]);
+            } else {
             mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
             tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left, y0 * p.stride + fy - p.pad_top, n0);
             tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, w.n_tile * p.BN);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -575,6 +589,9 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint64_t adesc0 = make_desc(smem_u32(smem_a), p.sbo, p.layout), bdesc0 = make_desc(smem_u32(smem_b), p.sbo, p.layout);
+    const uint32_t a_step = p.a_stage >> 4, b_step = p.b_stage >> 4;  // descriptor address field is in 16-byte units
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -588,18 +605,15 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
         if (p.a_cp) fence_async_smem();  // cp.async wrote A through the generic proxy; the MMA reads it through the async one
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem_a + size_t(stage) * p.a_stage);
-          const uint32_t b_addr = smem_u32(smem_b + size_t(stage) * p.b_stage);
-          for (int kk = 0; kk < p.BK / 32; ++kk) {
-            const uint64_t ad = make_desc(a_addr + kk * 32, p.sbo, p.layout);
-            const uint64_t bd = make_desc(b_addr + kk * 32, p.sbo, p.layout);
-            umma_i8(tmem_d, ad, bd, p.idesc, (k | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(&ctl->empty[stage]);
-          if (k == k_iters - 1) umma_commit(&ctl->acc_full[as]);
+        // the whole warp runs this loop converged with warp-uniform values, so the descriptors live in uniform registers;
+        // only the tcgen05 instructions themselves are predicated on the elected lane
+        const uint64_t ad0 = adesc0 + uint64_t(uint32_t(stage) * a_step), bd0 = bdesc0 + uint64_t(uint32_t(stage) * b_step);
+        for (int kk = 0; kk < p.BK / 32; ++kk)
+          if (leader) umma_i8(tmem_d, ad0 + uint64_t(2 * kk), bd0 + uint64_t(2 * kk), p.idesc, (k | kk) != 0 ? 1u : 0u);
+        if (leader) {
+          umma_commit(&ctl->empty[stage]);                       // frees the smem stage when these MMAs retire
+          if (k == k_iters - 1) umma_commit(&ctl->acc_full[as]);  // accumulator complete
         }
-        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -668,6 +682,12 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       TOD_TR(2);
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
+      if (p.dbg & 8) {  // timing experiment: no epilogue work, hand the accumulator straight back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
+        continue;
+      }
       for (int pass0 = 0; pass0 < ncols_tile; pass0 += p.sc) {
         const int pass_cols = min(p.sc, ncols_tile - pass0);
         uint8_t* sbuf = grp_buf + ((MODE & kEpiTma) ? (pass_count & 1u) * buf_bytes : 0u);
@@ -771,6 +791,280 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// The large 3x3 layers are limited by how many operand bytes each SM can keep in flight from L2 (three 48 KB stages),
+// not by the tensor pipe (ncu: tensor 44 %, L2 31 %).  A CTA pair on one TPC shares the B operand: each CTA stages its
+// own 128 pixel rows of A and *half* of the weight rows; one tcgen05.mma.cta_group::2 (M = 256) issued by the even CTA
+// feeds both tensor cores, each accumulating its 128 x BN tile in its own TMEM.  Per SM and tile that is 295 + 295 KB
+// instead of 295 + 590 KB, and a stage shrinks to 32 KB so five fit.
+//   * both CTAs' TMA loads signal the even CTA's `full` barrier (cta_group::2 loads, peer bit cleared);
+//   * tcgen05.commit.cta_group::2 multicasts the `empty` / `acc_full` arrivals to both CTAs;
+//   * the epilogue warps of both CTAs arrive on the even CTA's `acc_empty` (count 8) through its cluster address.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address: "the even CTA's copy"
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(uint16_t(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_even_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
+template <uint32_t MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh,
+                    const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
+  uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;
+  int4* s_qtab = reinterpret_cast<int4*>(stage_buf + p.stage_bytes);
+  int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int Wd = p.flat ? tiles * p.HW : p.Wd;
+  const int tiles_x = p.flat ? (Wd + kBM - 1) / kBM : p.tiles_x;
+  const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
+  const int m_tiles = groups * p.tiles_y * tiles_x;
+  const int pair_items = ((m_tiles + 1) >> 1) * p.n_tiles;   // one item = two consecutive M tiles x one N tile
+  const int k_iters = p.taps * p.kchunks;
+  const uint32_t half_bn = uint32_t(p.BN) >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);    // used in the even CTA only
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->acc_full[s], 1);
+      mbar_init(&ctl->acc_empty[s], 8);  // four epilogue warps of each CTA (used in the even CTA only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
+  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anything signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();
+
+  // this CTA's M tile of pair item `item`
+  auto my_tile = [&](int item, int* n_tile, int* tx, int* ty, int* g) -> bool {
+    *n_tile = p.n_tiles > 1 ? item % p.n_tiles : 0;
+    const int pm = p.n_tiles > 1 ? item / p.n_tiles : item;
+    unsigned mt = unsigned(2 * pm) + rank;   // one past the end for the odd CTA of the last pair when the tile count is odd:
+    const bool real = mt < unsigned(m_tiles);  // it still runs the whole protocol on a recomputed tile, but stores nothing
+    if (!real) mt = 0;
+    *tx = int(mt % unsigned(tiles_x));
+    mt /= unsigned(tiles_x);
+    *ty = int(mt % unsigned(p.tiles_y));
+    *g = int(mt / unsigned(p.tiles_y));
+    return real;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bh)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = pair; item < pair_items; item += npairs) {
+        int n_tile, tx, ty, g;
+        my_tile(item, &n_tile, &tx, &ty, &g);
+        const int x0 = p.flat ? tx * kBM : tx * p.pw, y0 = ty * p.ph, n0 = g * p.pn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int fy = tap / p.KW, fx = tap - fy * p.KW;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&ctl->full[stage], 2u * p.tx_bytes);  // both CTAs' A tile + weight half
+            tma_load_4d_pair(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left,
+                             y0 * p.stride + fy - p.pad_top, n0);
+            tma_load_3d_pair(smem_b + size_t(stage) * p.b_stage, &map_bh, &ctl->full[stage], kc * p.BK, tap, n_tile * p.BN + int(rank * half_bn));
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (even CTA only) =====================
+    const bool leader = elect_one();
+    const uint64_t adesc0 = make_desc(smem_u32(smem_a), p.sbo, p.layout), bdesc0 = make_desc(smem_u32(smem_b), p.sbo, p.layout);
+    const uint32_t a_step = p.a_stage >> 4, b_step = p.b_stage >> 4;  // descriptor address field is in 16-byte units
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = pair; item < pair_items; item += npairs, ++it) {
+      const int as = it & 1;
+      const uint32_t use = uint32_t(it >> 1);
+      mbar_wait(&ctl->acc_empty[as], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after();
+        // the whole warp runs this loop converged with warp-uniform values, so the descriptors live in uniform registers;
+        // only the tcgen05 instructions themselves are predicated on the elected lane
+        const uint64_t ad0 = adesc0 + uint64_t(uint32_t(stage) * a_step), bd0 = bdesc0 + uint64_t(uint32_t(stage) * b_step);
+        for (int kk = 0; kk < p.BK / 32; ++kk)
+          if (leader) umma_i8_pair(tmem_d, ad0 + uint64_t(2 * kk), bd0 + uint64_t(2 * kk), p.idesc, (k | kk) != 0 ? 1u : 0u);
+        if (leader) {
+          umma_commit_pair(&ctl->empty[stage]);                       // frees the smem stage when these MMAs retire
+          if (k == k_iters - 1) umma_commit_pair(&ctl->acc_full[as]);  // accumulator complete
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs; same scheme as conv_tc_fast_kernel) =====================
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = ew * 32 + lane;
+    const int eg = threadIdx.x - 128 - grp * 128;
+    const int wx = r % p.pw;
+    const int wy = (r / p.pw) % p.ph;
+    const uint32_t swz_mask = p.wo == 128 ? 7u : (p.wo == 64 ? 3u : (p.wo == 32 ? 1u : 0u));
+    const uint32_t row_base = uint32_t(r) * uint32_t(p.wo);
+    const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.wo);
+    uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes >> 1);
+    const int bar_id = 1 + grp;
+    uint32_t pass_count = 0;
+    int it = 0;
+    for (int item = pair; item < pair_items; item += npairs, ++it) {
+      if ((it & 1) != grp) continue;
+      const int as = grp;
+      const uint32_t use = uint32_t(it >> 1);
+      int n_tile, tx, ty, g;
+      const bool real_tile = my_tile(item, &n_tile, &tx, &ty, &g);
+      const int x = tx * p.pw + wx, yy = ty * p.ph + wy;
+      int cls = 0;
+      if (p.ncls > 1) {
+        int ymask = 0, xmask = 0;
+        for (int f = 0; f < p.KH; ++f) {
+          const int iy = yy * p.stride + f - p.pad_top;
+          ymask |= (iy >= 0 && iy < p.IH) ? (1 << f) : 0;
+        }
+        for (int f = 0; f < p.KW; ++f) {
+          const int ix = x * p.stride + f - p.pad_left;
+          xmask |= (ix >= 0 && ix < p.IW) ? (1 << f) : 0;
+        }
+        cls = int(p.ymap[ymask & 7]) * p.ncls_x + int(p.xmap[xmask & 7]);
+      }
+      const int ocb = n_tile * p.BN;
+      const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
+      const int4* qrow = s_qtab + ocb;
+      const int ncols_tile = min(p.BN, p.OC - ocb);
+      mbar_wait(&ctl->acc_full[as], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
+      for (int pass0 = 0; pass0 < ncols_tile; pass0 += p.sc) {
+        const int pass_cols = min(p.sc, ncols_tile - pass0);
+        uint8_t* sbuf = grp_buf + (pass_count & 1u) * buf_bytes;
+        ++pass_count;
+        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + pass0 + c0, v);
+          tmem_wait_ld();
+          uint32_t packed[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int col = pass0 + c0 + 4 * q4;
+            const int4 b4 = b2row[col >> 2];
+            int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int4 k = qrow[col + j];
+              const int bj = j == 0 ? b4.x : (j == 1 ? b4.y : (j == 2 ? b4.z : b4.w));
+              int x2;
+              asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(x2) : "r"(int(v[4 * q4 + j])), "r"(bj));
+              const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
+              const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
+              o[j] = (t + (x2 >> 31)) >> k.y;
+            }
+            if (MODE & kEpiSat) {
+              packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = max(p.act_min, min(p.act_max, o[j]));
+              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+            }
+          }
+          uint32_t off = row_base + uint32_t(c0);
+          off ^= ((off >> 7) & swz_mask) << 4;
+          *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        if (pass0 + p.sc >= ncols_tile) {  // accumulator fully read: tell the even CTA's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_even_cta(&ctl->acc_empty[as]);
+        }
+        if (eg == 0) tma_store_wait_read();
+        fence_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (eg == 0 && real_tile) {
+          if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, tx * kBM, 0, 0);
+          else tma_store_4d(&map_o, sbuf, ocb + pass0, tx * p.pw, ty * p.ph, g * p.pn);
+          tma_store_commit();
+        }
+      }
+    }
+    if (eg == 0) tma_store_wait_read();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while its partner can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -826,7 +1120,8 @@ int sm_count() {
 }  // namespace
 
 struct ConvTc {
-  CUtensorMap map_a, map_b, map_o;
+  CUtensorMap map_a, map_b, map_o, map_bh;
+  int pair = 0;        // conv_tc_pair_kernel (cta_group::2): map_bh loads half of the weight rows per CTA
   TcParams p{};
   int32_t *d_bias_eff = nullptr, *d_mult = nullptr, *d_shift = nullptr, *d_b2 = nullptr;
   int4* d_qtab = nullptr;
@@ -1014,8 +1309,20 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   }
   if (a.add && (!c->fast || (c->mode & kEpiLut) || !p.vec_store))
     return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: a fused residual ADD needs the fast epilogue, 16-byte rows and no byte map"));
+  // CTA pairs (cta_group::2) for the MMA-heavy layers: see conv_tc_pair_kernel
+  static const int pair_env = std::getenv("TOD_TC_PAIR") ? std::atoi(std::getenv("TOD_TC_PAIR")) : -1;
+  {
+    const int groups_max = p.flat ? 1 : (a.max_tiles + p.pn - 1) / p.pn;
+    const long long m_tiles_max = p.flat ? ((long long)a.max_tiles * p.HW + kBM - 1) / kBM : (long long)groups_max * p.tiles_y * p.tiles_x;
+    c->pair = (c->fast && (c->mode & kEpiTma) && !(c->mode & (kEpiLut | kEpiAdd)) && !p.a_cp && p.BN % 32 == 0 && p.BN >= 64 &&
+               p.taps * p.kchunks >= 8 && m_tiles_max >= 64 && pair_env != 0) ? 1 : 0;
+  }
+  if (c->pair) {
+    p.b_stage = uint32_t(((p.BN / 2) * p.BK + 1023) / 1024 * 1024);
+    p.tx_bytes = uint32_t(p.rows * p.BK + (p.BN / 2) * p.BK);
+  }
   if (c->mode & kEpiTma) {
-    const int width = std::min(p.BN, 128);
+    const int width = c->pair ? std::min(p.BN, 64) : std::min(p.BN, 128);  // pairs: narrower passes buy a fifth operand stage
     p.wo = width <= 16 ? 16 : (width <= 32 ? 32 : (width <= 64 ? 64 : 128));
     p.sc = p.wo;
     p.pitch = p.wo;
@@ -1034,7 +1341,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
   c->smem_bytes = size_t(p.stages) * (p.a_stage + p.b_stage) + fixed;
   // instruction descriptor: D = s32, A = B = s8, both K-major, N, M = 128
-  p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+  p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.BN >> 3) << 17) | (uint32_t((c->pair ? 2 * kBM : kBM) >> 4) << 24);
   p.out_zp = a.rq.out_zp;
   p.act_min = a.rq.act_min;
   p.act_max = a.rq.act_max;
@@ -1121,6 +1428,14 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     rc = encode(&c->map_b, const_cast<int8_t*>(a.w), 3, dims, str, box, p.BK);
   }
   if (rc < 0) return bail(rc);
+  std::memset(&c->map_bh, 0, sizeof(c->map_bh));
+  if (c->pair) {
+    const uint64_t dims[3] = {uint64_t(g.IC), uint64_t(p.taps), uint64_t(g.OC)};
+    const uint64_t str[2] = {uint64_t(g.IC), uint64_t(p.taps) * g.IC};
+    const uint32_t box[3] = {uint32_t(p.BK), 1, uint32_t(p.BN / 2)};
+    rc = encode(&c->map_bh, a.w, 3, dims, str, box, p.BK);
+    if (rc < 0) return bail(rc);
+  }
   std::memset(&c->map_o, 0, sizeof(c->map_o));
   if (c->mode & kEpiTma) {
     // the output seen through the same patch tiling as the A operand; the box is [wo channels x patch]
@@ -1148,7 +1463,8 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
                              (const void*)conv_tc_fast_kernel<0>, (const void*)conv_tc_fast_kernel<1>, (const void*)conv_tc_fast_kernel<2>,
                              (const void*)conv_tc_fast_kernel<3>, (const void*)conv_tc_fast_kernel<4>, (const void*)conv_tc_fast_kernel<5>,
                              (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>,
-                             (const void*)conv_tc_fast_kernel<12>, (const void*)conv_tc_fast_kernel<13>};
+                             (const void*)conv_tc_fast_kernel<12>, (const void*)conv_tc_fast_kernel<13>,
+                             (const void*)conv_tc_pair_kernel<4>, (const void*)conv_tc_pair_kernel<5>};
     for (const void* k : kernels) {
       ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
@@ -1166,6 +1482,16 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
   const long long work = (long long)groups * p.tiles_y * tiles_x * p.n_tiles;
   const int grid = int(std::min<long long>(work, sm_count()));
+  if (c->pair) {
+    const long long m_tiles = (long long)groups * p.tiles_y * tiles_x;
+    const long long pair_items = ((m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = int(std::min<long long>(pair_items, sm_count() / 2));
+    if (c->mode & kEpiSat)
+      TOD_CUDA(launch_k(conv_tc_pair_kernel<5>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
+    else
+      TOD_CUDA(launch_k(conv_tc_pair_kernel<4>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
+    return TOD_OK;
+  }
   if (!c->fast) {
     TOD_CUDA(launch_k(conv_tc_kernel, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, p, tiles));
   } else {
