@@ -485,7 +485,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
   uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;  // 1024-aligned (both stage sizes are)
   long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + p.stage_bytes);
-  int4* s_qtab = reinterpret_cast<int4*>(s_rowoff + 2 * kBM);
+  int* s_runlen = reinterpret_cast<int*>(s_rowoff + 2 * kBM);   // [2 groups][128 runs]
+  int4* s_qtab = reinterpret_cast<int4*>(s_runlen + 2 * kBM);
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
 
@@ -637,7 +638,15 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t row_base = (MODE & kEpiTma) ? uint32_t(r) * uint32_t(p.wo) : uint32_t(r) * uint32_t(p.pitch);
     const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.wo);
     uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes >> 1);
-    long long* g_rowoff = s_rowoff + grp * kBM;
+    long long* g_rowoff = s_rowoff + grp * kBM;   // manual mode: global byte offset of each *run* (see below)
+    int* g_runlen = s_runlen + grp * kBM;
+    // Manual stores (rows that are not 16-byte multiples: OC = 243, 12, 81).  Pixels that are consecutive in the tile row
+    // order and in memory form a run (one patch row, or the whole tile for flat layers) whose bytes are contiguous in
+    // global memory.  A run is staged densely, shifted so that staging and global addresses are congruent mod 16, and
+    // then leaves as aligned 16-byte stores with a byte head and tail.
+    const int run_j = r / p.pw;
+    const uint32_t run_pitch = (uint32_t(p.pw) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
+    const int nruns = p.rows / p.pw;
     const int bar_id = 1 + grp;
     uint32_t pass_count = 0;
     int it = 0;
@@ -666,11 +675,20 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ocb = w.n_tile * p.BN;
       const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
       const int4* qrow = s_qtab + ocb;
-      if (!(MODE & kEpiTma)) {
-        const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
-        g_rowoff[r] = valid ? ((p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x) * p.OC) : -1ll;
-      }
       const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
+      uint32_t soff = 0;  // manual mode: this row's byte offset inside the group's staging buffer
+      if (!(MODE & kEpiTma)) {
+        const int x0 = w.tx * p.pw;
+        const bool valid_row = r < p.rows && yy < p.Hd && (p.flat || n < tiles);
+        const int nvalid = valid_row ? max(0, min(p.pw, Wd - x0)) : 0;
+        const long long g_run = (p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x0) * p.OC + ocb;
+        const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(p.out) + g_run) & 15u;
+        soff = uint32_t(run_j) * run_pitch + a + uint32_t(wx) * uint32_t(ncols_tile);
+        if (wx == 0 && r < p.rows) {
+          g_rowoff[run_j] = g_run;
+          g_runlen[run_j] = nvalid * ncols_tile;
+        }
+      }
       const int8_t* rrow = nullptr;                   // this pixel's residual bytes (kEpiAdd)
       if (MODE & kEpiAdd) {
         const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
@@ -736,9 +754,17 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
             }
           }
-          uint32_t off = row_base + uint32_t(c0);
-          if (MODE & kEpiTma) off ^= ((off >> 7) & swz_mask) << 4;
-          *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (MODE & kEpiTma) {
+            uint32_t off = row_base + uint32_t(c0);
+            off ^= ((off >> 7) & swz_mask) << 4;
+            *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          } else if (r < p.rows) {  // dense run staging: byte stores, never past this row's last real channel
+            uint8_t* dst = sbuf + soff + uint32_t(pass0 + c0);
+            const int nb = min(16, ncols_tile - pass0 - c0);
+#pragma unroll
+            for (int bi = 0; bi < 16; ++bi)
+              if (bi < nb) dst[bi] = uint8_t(packed[bi >> 2] >> (8 * (bi & 3)));
+          }
         }
         TOD_TR(4);
         if (pass0 + p.sc >= ncols_tile) {  // accumulator fully read: hand the TMEM stage back before the stores
@@ -761,20 +787,19 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         } else {
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (p.vec_store) {
-            const int cpr = pass_cols >> 4;
-            for (int idx = eg; idx < kBM * cpr; idx += 128) {
-              const int rr = idx / cpr, ch = idx - rr * cpr;
-              const long long off = g_rowoff[rr];
-              if (off >= 0)
-                *reinterpret_cast<uint4*>(p.out + off + ocb + pass0 + ch * 16) = *reinterpret_cast<const uint4*>(sbuf + size_t(rr) * p.pitch + ch * 16);
-            }
-          } else {
-            for (int idx = eg; idx < kBM * pass_cols; idx += 128) {
-              const int rr = idx / pass_cols, bb = idx - rr * pass_cols;
-              const long long off = g_rowoff[rr];
-              if (off >= 0) p.out[off + ocb + pass0 + bb] = int8_t(sbuf[size_t(rr) * p.pitch + bb]);
-            }
+          for (int j = 0; j < nruns; ++j) {
+            const int len = g_runlen[j];
+            if (len <= 0) continue;
+            int8_t* gdst = p.out + g_rowoff[j];
+            const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(gdst)) & 15u;
+            const uint8_t* ssrc = sbuf + uint32_t(j) * run_pitch + a;
+            const int head = min(len, int((16u - a) & 15u));
+            const int body = (len - head) >> 4;
+            const int tail = len - head - (body << 4);
+            for (int c = eg; c < body; c += 128)
+              *reinterpret_cast<uint4*>(gdst + head + 16 * c) = *reinterpret_cast<const uint4*>(ssrc + head + 16 * c);
+            if (eg < head) gdst[eg] = int8_t(ssrc[eg]);
+            if (eg < tail) gdst[head + 16 * body + eg] = int8_t(ssrc[head + 16 * body + eg]);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
@@ -1290,6 +1315,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     for (size_t i = 0; i < xmasks.size(); ++i) p.xmap[xmasks[i] & 7] = uint8_t(i);
   const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * 4 : 0;
   if (table_bytes > 40 * 1024) c->fast = 0;
+  if (!p.vec_store && p.n_tiles > 1) c->fast = 0;  // run staging needs whole rows (every output channel) in one tile
   if (p.a_cp && !c->fast) {  // the general-epilogue kernel only has the TMA producer: back to a K chunk that TMA can serve
     p.a_cp = 0;
     p.BK = (g.IC % 128 == 0) ? 128 : ((g.IC % 64 == 0) ? 64 : 32);
@@ -1329,13 +1355,21 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     p.stage_bytes = uint32_t(4 * kBM * p.wo);  // two epilogue groups x double buffer
   } else {
     p.wo = 0;
-    p.sc = std::min(p.BN, 128);
-    int pitch16 = p.sc / 16 + 1;
-    if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
-    p.pitch = pitch16 * 16;
-    p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024) * 2u;  // one staging tile per epilogue group
+    if (c->fast) {
+      // conv_tc_fast_kernel, manual stores: the whole tile (every column) is staged as dense runs, one buffer per group
+      p.sc = p.BN;
+      p.pitch = p.BN;
+      const uint32_t run_pitch = (uint32_t(p.pw) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
+      p.stage_bytes = uint32_t((uint32_t(p.rows / p.pw) * run_pitch + 1023u) / 1024u * 1024u) * 2u;
+    } else {
+      p.sc = std::min(p.BN, 128);
+      int pitch16 = p.sc / 16 + 1;
+      if (pitch16 % 2 == 0) ++pitch16;  // odd number of 16-byte units per row: conflict-free 16-byte row-strided stores
+      p.pitch = pitch16 * 16;
+      p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024) * 2u;
+    }
   }
-  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 16 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
+  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 24 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
   const size_t budget = 227 * 1024 - fixed;
   p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
