@@ -196,11 +196,12 @@ def main():
     det, keep = out_bufs
     keep_pinned = {}
     import ctypes as C
-    for k in ("count", "boxes", "scores", "classes", "priors", "masks_bin"):
-        tt = torch.from_numpy(keep[k]).pin_memory()
+    for k in ("count", "boxes", "scores", "classes", "priors", "masks_bits"):
+        tt = torch.from_numpy(keep[k].view(np.int32) if keep[k].dtype == np.uint32 else keep[k]).pin_memory()
         keep_pinned[k] = tt
         setattr(det, k, tt.data_ptr())
     det.masks = None
+    det.masks_bin = None  # binary masks come back bit-packed (masks_bits): an eighth of the bytes
     d2h = sum(t.numel() * t.element_size() for t in keep_pinned.values()) + tc_h.numel() * 4
     h2d = tiles_h.numel()
     lib = tod_b200.lib()
@@ -263,7 +264,7 @@ def main():
                    "tiles_per_step": n, "frames_per_step": frames_per_step, "tile": "224x224x3 u8", "model": "synthetic FRC topology (real blob missing), 5.62 GMAC/tile",
                    "parallelism": "frame-sharded x%d, no collective" % world, "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "call": "tod_yolact_infer_tiles (host tiles in, tile class maps + detections + binary masks out)"},
+                "call": "tod_yolact_infer_tiles (host tiles in; tile class maps + detections + bit-packed binary masks out)"},
         "gpu_launches": int(st["launches_per_call"] * args.steps),
         "roofline": roofline,
         "clocks": clk,

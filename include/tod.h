@@ -179,6 +179,8 @@ typedef struct tod_detections {
   int32_t* priors;        /* [n][max_dets]             prior index == NMS keep index */
   float* masks;           /* [n][max_dets][56][56]     sigmoid + crop, may be NULL */
   uint8_t* masks_bin;     /* [n][max_dets][56][56]     > 0.5, may be NULL */
+  uint32_t* masks_bits;   /* [n][max_dets][ceil(56*56/32)]  the same binary masks, 1 bit per prototype pixel (bit i of word
+                             w = pixel 32*w + i): an eighth of the read-back of masks_bin; may be NULL */
 } tod_detections;
 
 /* Runs the int8 graph on n RGB tiles u8[n][224][224][3] (== interpreter.invoke(), yolact.rs:161-163).

@@ -32,6 +32,10 @@ def _check_dets(got, want):
         inter = np.logical_and(got["masks_bin"], want["masks_bin"]).sum()
         union = np.logical_or(got["masks_bin"], want["masks_bin"]).sum()
         assert union == 0 or inter / union >= 0.999
+        if got.get("masks_bits") is not None:  # the bit-packed form is the same mask, bit i of word w = pixel 32 w + i
+            bits = np.unpackbits(got["masks_bits"].view(np.uint8), axis=-1, bitorder="little")
+            npx = got["masks_bin"].shape[-1] * got["masks_bin"].shape[-2]
+            assert np.array_equal(bits[..., :npx].reshape(got["masks_bin"].shape), got["masks_bin"])
 
 
 @pytest.mark.parametrize("id_mode", [0, 1])

@@ -499,9 +499,10 @@ __global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectB
   __syncthreads();
   const int npx = c.ph * c.pw;
   const int px = blockIdx.x * kMaskThreads + threadIdx.x;
-  if (px >= npx) return;
+  const bool in_range = px < npx;
+  const int pxc = in_range ? px : npx - 1;   // out-of-range lanes shadow the last pixel: the warp stays converged for the ballots
   unsigned int pw_[K / 4];
-  const uint8_t* pq = proto + int64_t(t) * proto_ts + int64_t(px) * K;
+  const uint8_t* pq = proto + int64_t(t) * proto_ts + int64_t(pxc) * K;
   unsigned int upsum = 0;
 #pragma unroll
   for (int w = 0; w < K / 4; ++w) {
@@ -509,8 +510,9 @@ __global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectB
     upsum = __dp4a(pw_[w], 0x01010101u, upsum);
   }
   const int psum = int(upsum);
-  const float fx = float(px % c.pw), fy = float(px / c.pw);
+  const float fx = float(pxc % c.pw), fy = float(pxc / c.pw);
   const int kzz = K * c.proto_zp * c.coef_zp;
+  const int words = (npx + 31) >> 5;
   for (int d = 0; d < nd; ++d) {
     unsigned int dot = 0;
 #pragma unroll
@@ -520,9 +522,14 @@ __global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectB
     float mval = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
     const float4 cr = s_crop[d];
     if (!(fx >= cr.x && fx < cr.y && fy >= cr.z && fy < cr.w)) mval = 0.f;
+    const bool on = in_range && mval > 0.5f;
     const int64_t o = (int64_t(t) * c.max_dets + d) * npx + px;
-    if (b.masks) b.masks[o] = mval;
-    if (b.masks_bin) b.masks_bin[o] = mval > 0.5f ? 1 : 0;
+    if (in_range && b.masks) b.masks[o] = mval;
+    if (in_range && b.masks_bin) b.masks_bin[o] = on ? 1 : 0;
+    if (b.masks_bits) {
+      const unsigned bits = __ballot_sync(0xffffffffu, on);
+      if ((threadIdx.x & 31) == 0 && (px >> 5) < words) b.masks_bits[(int64_t(t) * c.max_dets + d) * words + (px >> 5)] = bits;
+    }
   }
 }
 

@@ -63,6 +63,7 @@ struct DetectBuffers {        // all device memory, sized for max tiles
   int* det_prior;             // [tiles][max_dets]
   float* masks;               // [tiles][max_dets][ph*pw]
   uint8_t* masks_bin;         // [tiles][max_dets][ph*pw]
+  uint32_t* masks_bits;       // [tiles][max_dets][ceil(ph*pw / 32)]  bit-packed masks_bin
 };
 // cls/box/coef/proto: the model's u8 outputs, with their byte strides between tiles
 int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,

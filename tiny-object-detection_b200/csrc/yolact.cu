@@ -974,6 +974,7 @@ int setup_detection(tod_yolact* y) {
   TOD_TRY(dev_alloc(y, &b.det_prior, mt * c.max_dets));
   TOD_TRY(dev_alloc(y, &b.masks, mt * c.max_dets * c.ph * c.pw));
   TOD_TRY(dev_alloc(y, &b.masks_bin, mt * c.max_dets * c.ph * c.pw));
+  TOD_TRY(dev_alloc(y, &b.masks_bits, mt * c.max_dets * size_t((c.ph * c.pw + 31) / 32)));
   // exp() of a quantised logit is a function of the u8 code only: 256-entry tables built with the host libm
   float h_exp[256], h_deq[256], h_bexp[256];
   for (int d = 0; d < 256; ++d) h_exp[d] = std::exp(CL.scale() * float(d - 255));
@@ -1455,6 +1456,8 @@ int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
   if (d->masks && y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute float masks");
   if (d->masks_bin && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
   if (d->masks) TOD_CUDA(cudaMemcpyAsync(d->masks, b.masks, nd * c.ph * c.pw * 4, cudaMemcpyDeviceToHost, s));
+  if (d->masks_bits && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
+  if (d->masks_bits) TOD_CUDA(cudaMemcpyAsync(d->masks_bits, b.masks_bits, nd * size_t((c.ph * c.pw + 31) / 32) * 4, cudaMemcpyDeviceToHost, s));
   if (d->masks_bin) TOD_CUDA(cudaMemcpyAsync(d->masks_bin, b.masks_bin, nd * c.ph * c.pw, cudaMemcpyDeviceToHost, s));
   TOD_CUDA(cudaStreamSynchronize(s));
   return TOD_OK;
@@ -1471,7 +1474,7 @@ int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8
   // yolact.rs:161-162 copy_from_slice into the input tensor
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n), cudaMemcpyHostToDevice, s));
   const bool want_dets = dets != nullptr;
-  const int mask_mode = !want_dets ? 0 : (dets->masks ? 2 : (dets->masks_bin ? 1 : 0));
+  const int mask_mode = !want_dets ? 0 : (dets->masks ? 2 : ((dets->masks_bin || dets->masks_bits) ? 1 : 0));
   y->last_mask_mode = mask_mode;
   TOD_TRY(run_pipeline(y, n, want_dets, mask_mode, s));
   if (outputs_u8)

@@ -167,9 +167,10 @@ class Yolact:
         keep = dict(count=np.zeros(n, np.int32), boxes=np.zeros((n, md, 4), np.float32), scores=np.zeros((n, md), np.float32),
                     classes=np.zeros((n, md), np.int32), priors=np.zeros((n, md), np.int32),
                     masks=np.zeros((n, md, ph, pw), np.float32) if masks else None,
-                    masks_bin=np.zeros((n, md, ph, pw), np.uint8) if masks else None)
+                    masks_bin=np.zeros((n, md, ph, pw), np.uint8) if masks else None,
+                    masks_bits=np.zeros((n, md, (ph * pw + 31) // 32), np.uint32) if masks else None)
         det = Detections(md, *[keep[k].ctypes.data if keep[k] is not None else None
-                               for k in ("count", "boxes", "scores", "classes", "priors", "masks", "masks_bin")])
+                               for k in ("count", "boxes", "scores", "classes", "priors", "masks", "masks_bin", "masks_bits")])
         return det, keep
 
     @staticmethod
@@ -180,7 +181,8 @@ class Yolact:
             out.append(dict(n=c, box=keep["boxes"][t, :c], score=keep["scores"][t, :c], cls=keep["classes"][t, :c],
                             prior=keep["priors"][t, :c],
                             masks=keep["masks"][t, :c] if keep["masks"] is not None else None,
-                            masks_bin=keep["masks_bin"][t, :c] if keep["masks_bin"] is not None else None))
+                            masks_bin=keep["masks_bin"][t, :c] if keep["masks_bin"] is not None else None,
+                            masks_bits=keep["masks_bits"][t, :c] if keep.get("masks_bits") is not None else None))
         return out
 
 
