@@ -5,6 +5,8 @@
 // result (Rust never fuses a*b+c).
 #include "post.h"
 
+#include <algorithm>
+
 #include "common.h"
 
 namespace tod {
@@ -252,10 +254,15 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   const float tu = __fmul_rn(c.conf_thresh, sum);
   const float tu_hi = __fmul_rn(tu, 1.0000004f), tu_lo = __fmul_rn(tu, 0.9999996f);
   auto passes = [&](float e) { return c.conf_thresh > 0.f ? (e > tu_hi ? true : (e < tu_lo ? false : __fdiv_rn(e, sum) > c.conf_thresh)) : __fdiv_rn(e, sum) > c.conf_thresh; };
-  // pass 1: per-class candidate counts of this CTA (shared-memory atomics), one global reservation per class
+  // pass 1: per-class candidate counts of this CTA (shared-memory atomics); the thread remembers its candidates as a
+  // bit set (C <= 256), so the emit pass below only revisits those few classes
+  unsigned cbits[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (active)
     for (int k = 1; k < c.C; ++k)
-      if (passes(s_exp[int(q[k]) - qmax + 255])) atomicAdd(&s_cnt[k - 1], 1);
+      if (passes(s_exp[int(q[k]) - qmax + 255])) {
+        atomicAdd(&s_cnt[k - 1], 1);
+        cbits[k >> 5] |= 1u << (k & 31);
+      }
   __syncthreads();
   for (int k = threadIdx.x; k < c.C - 1; k += kDecodeThreads) {
     const int cnt = s_cnt[k];
@@ -264,9 +271,13 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   }
   __syncthreads();
   if (!active) return;
-  for (int k = 1; k < c.C; ++k) {
-    const float e = s_exp[int(q[k]) - qmax + 255];
-    if (passes(e)) {
+#pragma unroll
+  for (int wi = 0; wi < 8; ++wi) {
+    unsigned bits = cbits[wi];
+    while (bits) {
+      const int k = wi * 32 + __ffs(int(bits)) - 1;
+      bits &= bits - 1;
+      const float e = s_exp[int(q[k]) - qmax + 255];
       const int slot = s_base[k - 1] + atomicAdd(&s_cnt[k - 1], 1);
       b.cand[(int64_t(t) * (c.C - 1) + (k - 1)) * c.P + slot] =
           (static_cast<unsigned long long>(__float_as_uint(__fdiv_rn(e, sum))) << 32) | (0xFFFFFFFFu - unsigned(p));
@@ -304,15 +315,19 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const 
 // Fast-NMS for one (class, tile): sort the class' candidates, keep top_k, then each warp lane owns a
 // column j of the IoU matrix and scans the rows i < j (upper triangle); survivors are compacted with
 // ballot/popc and appended to the tile's survivor list.
+// Launched twice per batch: once sized for class lists of at most kNmsSmall candidates (8 KB of shared memory -> the whole
+// grid is resident at once) and once sized for the worst case (every prior a candidate); a CTA whose list falls in the other
+// launch's range returns immediately.  The common case no longer pays the worst case's 36 KB per CTA.
 constexpr int kNmsThreads = 256;
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap) {
+constexpr int kNmsSmall = 512;
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_lo, int n_hi) {
   extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k]
   float4* s_box = reinterpret_cast<float4*>(s_keys + sort_cap);
   float* s_area = reinterpret_cast<float*>(s_box + c.top_k);
   const int k = blockIdx.x;  // foreground class
   const int t = blockIdx.y;
   const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
-  if (n == 0) return;
+  if (n <= n_lo || n > n_hi) return;
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const unsigned long long* src = b.cand + (int64_t(t) * (c.C - 1) + k) * c.P;
@@ -566,7 +581,8 @@ void launch_classify_post(const uint32_t* tile_px, int n, int W, int H, const Re
 }
 
 size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8 + size_t(kSelCap) * 8 + size_t(kSelBins) * 4; }
-static size_t nms_smem(const DetectCfg& c) { return size_t(next_pow2(c.P)) * 8 + size_t(c.top_k) * 20; }
+static size_t nms_smem_for(const DetectCfg& c, int cap) { return size_t(cap) * 8 + size_t(c.top_k) * 20; }
+static size_t nms_smem(const DetectCfg& c) { return nms_smem_for(c, next_pow2(c.P)); }
 static size_t mask_smem(const DetectCfg& c) { return size_t(c.max_dets) * (c.K + 4 + 16); }
 
 int detect_setup_kernels(const DetectCfg& c) {
@@ -587,7 +603,9 @@ int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_
   dim3 g1((c.P + kDecodeThreads - 1) / kDecodeThreads, tiles);
   decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
   dim3 g2(c.C - 1, tiles);
-  nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P));
+  const int small_cap = std::min(kNmsSmall, next_pow2(c.P));
+  nms_kernel<<<g2, kNmsThreads, nms_smem_for(c, small_cap), s>>>(c, b, small_cap, 0, small_cap);
+  if (next_pow2(c.P) > small_cap) nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P), small_cap, c.P);
   select_kernel<<<tiles, kSelThreads, detect_select_smem(c), s>>>(c, b, next_pow2((c.C - 1) * c.top_k));
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;

@@ -1520,7 +1520,7 @@ int tod_yolact_classify(tod_yolact* y, uint32_t* frame, int width, int height) {
 int tod_yolact_stats(const tod_yolact* y, int64_t* macs_per_tile, int32_t* launches_per_call, int32_t* tc_conv_layers) {
   if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_stats: null handle");
   if (macs_per_tile) *macs_per_tile = y->macs_per_tile;
-  if (launches_per_call) *launches_per_call = y->launches_per_call + (y->seg_out >= 0 ? 1 : 0) + (y->det_ready && y->have_priors ? 4 : 0);
+  if (launches_per_call) *launches_per_call = y->launches_per_call + (y->seg_out >= 0 ? 1 : 0) + (y->det_ready && y->have_priors ? 5 : 0);
   if (tc_conv_layers) *tc_conv_layers = y->tc_layers;
   return TOD_OK;
 }
