@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--no-scene", action="store_true", help="skip the point-cloud side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0)
+    ap.add_argument("--fused", type=int, default=512, help="frames of the fused 320x240 RGB-D side measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -305,6 +306,42 @@ def main():
                          "ms_per_batch": sms, "algorithmic_GBps": nb * bytes_per_frame / (sms * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm"],
                          "frac_of_hbm": nb * bytes_per_frame / (sms * 1e-3) / 1e9 / peaks["hbm"], "stamp_ms": stamp_ms, "weights_ms": weights_ms,
                          "weights_GBps": nb * 52 * npx / (weights_ms * 1e-3) / 1e9, "stamps_per_sec": nb * npx * 400 / (stamp_ms * 1e-3)}
+
+    # ---- fused RGB-D pipeline (configs[3]): 320x240 frames, classify -> u16 target -> point cloud, all on the device
+    if args.fused and rank == 0:
+        try:
+            fb = args.fused
+            W4, H4 = 320, 240
+            y4 = tod_b200.Yolact.init(full, device=local_rank, max_tiles=2 * fb)
+            sb4 = tod_b200.SceneBuilder(device=local_rank, width=W4, height=H4, max_batch=fb)
+            fr = torch.from_numpy(np.tile(synth.rgb_frames(8, W=W4, H=H4, seed=5), (fb // 8, 1)).view(np.int32)).cuda()
+            dp = torch.from_numpy(np.tile(synth.depth_frames(8, W=W4, H=H4, seed=3), (fb // 8, 1, 1)).view(np.int16)).cuda()
+            tg = torch.zeros((fb, H4, W4), dtype=torch.int16, device="cuda")
+            o_map = torch.empty((fb, H4 * W4), dtype=torch.int32, device="cuda")
+            o_w = torch.empty((fb, H4 * W4, 4), dtype=torch.float32, device="cuda")
+            o_c0, o_c1 = torch.empty_like(o_w), torch.empty_like(o_w)
+            work = fr.clone()
+
+            def fstep():
+                work.copy_(fr)  # classify mutates the frames in place (yolact.rs:233)
+                y4.classify_device(work.data_ptr(), fb, W4, H4, tg.data_ptr(), stream)
+                sb4.append_batch_device(dp.data_ptr(), tg.data_ptr(), fb, o_map.data_ptr(), o_w.data_ptr(), o_c0.data_ptr(), o_c1.data_ptr(), None, stream)
+
+            for _ in range(2):
+                fstep()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                fstep()
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / 3
+            line["fused_rgbd"] = {"workload": "320x240 RGB-D frames: classify (2 tiles/frame) -> target -> point cloud + weights, batch %d, device-resident (configs[3])" % fb,
+                                  "frames_per_sec": fb / (fms * 1e-3), "ms_per_batch": fms}
+            del y4, sb4
+        except Exception as e:  # never let the side measurement break the headline line
+            line["fused_rgbd"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline (oracle port of the reference's CPU path), rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
