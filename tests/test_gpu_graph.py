@@ -75,6 +75,19 @@ def test_pdl_does_not_change_bytes(tod, models):
         assert np.array_equal(a["tile_classes"], rb["tile_classes"])
 
 
+@pytest.mark.parametrize("n,max_tiles", [(1, 1), (3, 3), (5, 7), (13, 16)])
+def test_tile_counts_cross_check(tod, models, n, max_tiles):
+    """Odd and partial tile counts (patch groups with tail masking, CTA pairs with a dummy tile, flat GEMMs whose last
+    M tile is ragged): the tensor-core path against the CUDA-core direct path, full model, every output and the class maps."""
+    full, _ = models
+    tiles = synth.rgb_tiles(n, seed=60 + n)
+    a = tod.Yolact.init(full, max_tiles=max_tiles, conv_impl=1).infer_tiles(tiles)
+    b = tod.Yolact.init(full, max_tiles=max_tiles, conv_impl=0).infer_tiles(tiles)
+    for k in range(5):
+        assert np.array_equal(a["outputs"][k], b["outputs"][k]), "output %d differs at n=%d" % (k, n)
+    assert np.array_equal(a["tile_classes"], b["tile_classes"])
+
+
 def test_errors(tod, models, tmp_path):
     _, small = models
     with pytest.raises(tod.TodError):
