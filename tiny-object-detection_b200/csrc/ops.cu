@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
     if (iy < g.IH) {
       const int64_t off = (int64_t(iy) * g.IW + ix0) * 3;          // even: 0 or 2 mod 4
       const int* p = reinterpret_cast<const int*>(tin + (off & ~int64_t(3)));
-      const int w0 = p[0], w1 = p[1], w2 = p[2];
+      const int xr = g.in_xor * 0x01010101;  // folded uint8 -> int8 QUANTIZE (x ^ 0x80), 0 otherwise
+      const int w0 = p[0] ^ xr, w1 = p[1] ^ xr, w2 = p[2] ^ xr;
       if (off & 2) {
         a0 = __funnelshift_r(w0, w1, 16);
         a1 = __funnelshift_r(w1, w2, 16);
@@ -812,13 +813,17 @@ inline int grid_for(int64_t work_items, int threads, int tiles) {
 
 }  // namespace
 
+bool stem_kernel_eligible(const ConvGeom& g, const Requant& rq, const void* in, int64_t in_ts, const void* out, int64_t out_ts) {
+  return g.IC == 3 && g.KH == 3 && g.KW == 3 && g.stride_h == 2 && g.stride_w == 2 && g.dil_h == 1 && g.dil_w == 1 && g.pad_top == 0 &&
+         g.pad_left == 0 && g.OC % 16 == 0 && g.OC <= 64 && rq.fast_tab && !rq.post_lut && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
+         (in_ts & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_ts & 15) == 0 && (g.IW * 3) % 2 == 0;
+}
+
 void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const int32_t* bias, const int32_t* wsum,
                         int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles,
                         cudaStream_t s) {
   // the RGB stem: 3x3, stride 2, no top / left padding, 16-byte-aligned 16-channel output groups
-  if (g.IC == 3 && g.KH == 3 && g.KW == 3 && g.stride_h == 2 && g.stride_w == 2 && g.dil_h == 1 && g.dil_w == 1 && g.pad_top == 0 &&
-      g.pad_left == 0 && g.OC % 16 == 0 && g.OC <= 64 && rq.fast_tab && !rq.post_lut && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (in_ts & 3) == 0 &&
-      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_ts & 15) == 0 && (g.IW * 3) % 2 == 0) {
+  if (stem_kernel_eligible(g, rq, in, in_ts, out, out_ts)) {
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
     dim3 grid(unsigned((total + kStemThreads * kStemIters - 1) / (kStemThreads * kStemIters)));
     if (rq.act_min == -128 && rq.act_max == 127)

@@ -13,6 +13,7 @@ struct ConvGeom {
   int KH, KW;
   int stride_h, stride_w, dil_h, dil_w;
   int pad_top, pad_left;  // taps that fall outside [0,IH)x[0,IW) are skipped (TFLite semantics)
+  int in_xor;             // stem kernel only: every input byte is XORed with this first (0x80 = the folded uint8 -> int8 QUANTIZE)
 };
 
 struct Requant {          // per-output-channel fixed point requantisation + activation clamp
@@ -30,6 +31,10 @@ struct Requant {          // per-output-channel fixed point requantisation + act
 void launch_conv_direct(const int8_t* in, int64_t in_tile_stride, const int8_t* w, const int32_t* bias,
                         const int32_t* wsum, int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out,
                         int64_t out_tile_stride, int tiles, cudaStream_t s);
+
+// true when launch_conv_direct will take the dedicated RGB-stem kernel (the only one that honours ConvGeom::in_xor)
+bool stem_kernel_eligible(const ConvGeom& g, const Requant& rq, const void* in, int64_t in_tile_stride, const void* out,
+                          int64_t out_tile_stride);
 
 // DEPTHWISE_CONV_2D, depth multiplier 1.  w: [1][KH][KW][C] int8.
 void launch_depthwise(const int8_t* in, int64_t in_tile_stride, const int8_t* w, const int32_t* bias, int32_t in_zp,

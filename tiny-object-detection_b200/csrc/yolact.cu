@@ -666,6 +666,32 @@ int plan(tod_yolact* y, ConstArena* arena) {
       }
     }
   }
+  // ---- input QUANTIZE folding: the graph starts with uint8 -> int8 (x - 128, same scale), i.e. the byte map x ^ 0x80.  When
+  // that tensor's only reader is the RGB stem kernel, the stem reads the uint8 tiles itself and flips the bit on the fly.
+  if (fuse && y->opt.conv_impl != 2) {  // conv_impl 2 runs without Requant::fast_tab, which the stem kernel needs
+    for (size_t qi = 0; qi < y->steps.size(); ++qi) {
+      const Step& Q = y->steps[qi];
+      if (Q.kind != kStepLut || Q.in0 != G.inputs[0] || consumers[Q.out] != 1) continue;
+      bool is_flip = true;
+      for (int b = 0; b < 256 && is_flip; ++b) is_flip = Q.lut_host[b] == uint8_t(b ^ 0x80);
+      if (!is_flip) continue;
+      for (size_t si = 0; si < y->steps.size(); ++si) {
+        Step& S = y->steps[si];
+        if (S.kind != kStepConvDirect || S.in0 != Q.out || !S.lut_host.empty() || S.fast_off < 0 || S.fused_add) continue;
+        const Place& pin = y->place[Q.in0];
+        const Place& pout = S.out_moved ? S.out_place : y->place[S.out];
+        Requant probe{nullptr, nullptr, S.out_zp, S.act_min, S.act_max, nullptr};
+        probe.fast_tab = reinterpret_cast<const int4*>(uintptr_t(16));  // eligibility only looks at presence
+        if (!stem_kernel_eligible(S.g, probe, pin.base, pin.tile_stride, pout.base, pout.tile_stride)) continue;
+        S.in0 = Q.in0;
+        S.g.in_xor = 0x80;
+        y->fused_away[Q.out] = 1;
+        y->steps.erase(y->steps.begin() + qi);
+        qi = y->steps.size();  // one input, one stem
+        break;
+      }
+    }
+  }
   // ---- residual / FPN ADD fusion: an ADD one of whose inputs is a tensor-core convolution's only-read output runs in
   // that convolution's epilogue (two 256-entry rescale tables + one output rescale, the arithmetic of ops.cu::add_kernel).
   // The convolution moves to the ADD's position in the step list, so the other operand is always produced before it.
