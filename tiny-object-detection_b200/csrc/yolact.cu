@@ -326,7 +326,8 @@ int plan(tod_yolact* y, ConstArena* arena) {
     total = round_up(total + root_stride[t] * mt, 1024);
   }
   y->act_bytes = size_t(total);
-  TOD_CUDA(cudaMalloc(&y->d_act, y->act_bytes ? y->act_bytes : 256));
+  // + 256 bytes: the stem kernel reads whole aligned words and may touch up to three bytes past a tensor's last pixel
+  TOD_CUDA(cudaMalloc(&y->d_act, y->act_bytes + 256));
   y->place.assign(nt, Place{});
   for (int t = 0; t < nt; ++t) {
     const GTensor& X = G.tensors[t];
@@ -792,7 +793,7 @@ int plan(tod_yolact* y, ConstArena* arena) {
 }
 
 int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
-  TOD_CUDA(cudaMalloc(&y->d_const, arena.host.size() ? arena.host.size() : 256));
+  TOD_CUDA(cudaMalloc(&y->d_const, arena.host.size() + 256));
   TOD_CUDA(cudaMemcpy(y->d_const, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice));
   for (Step& st : y->steps) {
     if (st.kind != kStepConvDirect || y->opt.conv_impl == 1) continue;  // conv_impl: 0 = tcgen05, 1 = CUDA cores only, 2 = tcgen05 with the general epilogue
