@@ -146,3 +146,18 @@ def test_detection_small_thresholds(tod, models, conf, nms):
                              res["outputs"][2][t], (o[2]["scale"], o[2]["zero_point"]), res["outputs"][3][t], (o[3]["scale"], o[3]["zero_point"]),
                              cfg=cfg, priors=pri)
         _check_dets(res["dets"][t], want)
+
+
+def test_binary_only_masks_match(tod, models):
+    """Asking for the binary masks alone takes the sign-of-the-integer-logit path (no sigmoid): same bits as thresholding
+    the float masks, in both the byte and the bit-packed form."""
+    full, _ = models
+    tiles = synth.rgb_tiles(3, seed=47)
+    y = tod.Yolact.init(full, max_tiles=3)
+    a = y.infer_tiles(tiles, outputs=False, tile_classes=False, detections=True)["dets"]
+    b = y.infer_tiles(tiles, outputs=False, tile_classes=False, detections=True, float_masks=False)["dets"]
+    for da, db in zip(a, b):
+        assert da["n"] == db["n"] and db["masks"] is None
+        assert np.array_equal(da["masks_bin"], db["masks_bin"])
+        assert np.array_equal(da["masks_bits"], db["masks_bits"])
+        assert np.array_equal(da["masks_bin"], (da["masks"] > 0.5).astype(np.uint8))

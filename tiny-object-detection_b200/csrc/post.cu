@@ -528,16 +528,28 @@ __global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectB
   const float fx = float(pxc % c.pw), fy = float(pxc / c.pw);
   const int kzz = K * c.proto_zp * c.coef_zp;
   const int words = (npx + 31) >> 5;
+  // sigmoid(l) > 0.5  <=>  l > 0  <=>  idot > 0 for a positive mask scale (|l| >= scale >> 2^-24, so exp(-l) never rounds to 1):
+  // when only the binary masks are wanted the transcendental is skipped; a pixel outside a detection's crop window is 0
+  // whatever the logit, so it skips the contraction as well
+  const bool sign_only = !b.masks && c.mask_scale >= 1e-6f;
   for (int d = 0; d < nd; ++d) {
-    unsigned int dot = 0;
-#pragma unroll
-    for (int w = 0; w < K / 4; ++w) dot = __dp4a(pw_[w], s_coef[d * (K / 4) + w], dot);
-    const int idot = int(dot) - c.coef_zp * psum - c.proto_zp * s_csum[d] + kzz;
-    const float logit = __fmul_rn(float(idot), c.mask_scale);
-    float mval = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
     const float4 cr = s_crop[d];
-    if (!(fx >= cr.x && fx < cr.y && fy >= cr.z && fy < cr.w)) mval = 0.f;
-    const bool on = in_range && mval > 0.5f;
+    const bool inside = fx >= cr.x && fx < cr.y && fy >= cr.z && fy < cr.w;
+    float mval = 0.f;
+    bool on = false;
+    if (inside) {
+      unsigned int dot = 0;
+#pragma unroll
+      for (int w = 0; w < K / 4; ++w) dot = __dp4a(pw_[w], s_coef[d * (K / 4) + w], dot);
+      const int idot = int(dot) - c.coef_zp * psum - c.proto_zp * s_csum[d] + kzz;
+      if (sign_only) {
+        on = in_range && idot > 0;
+      } else {
+        const float logit = __fmul_rn(float(idot), c.mask_scale);
+        mval = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
+        on = in_range && mval > 0.5f;
+      }
+    }
     const int64_t o = (int64_t(t) * c.max_dets + d) * npx + px;
     if (in_range && b.masks) b.masks[o] = mval;
     if (in_range && b.masks_bin) b.masks_bin[o] = on ? 1 : 0;

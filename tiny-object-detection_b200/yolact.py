@@ -91,7 +91,7 @@ class Yolact:
         check(lib().tod_yolact_classify_batch_device(self._h, d_frames_ptr, n, width, height, d_target_ptr, stream))
 
     # ------------------------------------------------------------------ batched tile inference
-    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True):
+    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True, float_masks=True):
         """tiles: u8[n, th, tw, 3].  Returns dict(outputs=[u8 arrays], tile_classes=u32[n,th,tw], dets=..., diverged=bool)."""
         tiles = np.ascontiguousarray(tiles, np.uint8)
         n, th, tw = tiles.shape[0], tiles.shape[1], tiles.shape[2]
@@ -104,6 +104,9 @@ class Yolact:
         det, keep = (None, None)
         if detections:
             det, keep = self._alloc_dets(n, masks)
+            if not float_masks:  # binary masks only: the library then skips the sigmoid (sign of the integer logit)
+                det.masks = None
+                keep["masks"] = None
         rc = check(lib().tod_yolact_infer_tiles(self._h, _ptr(tiles), n, arr if outputs else None, _ptr(tc),
                                                 C.byref(det) if det is not None else None))
         res["outputs"] = outs
