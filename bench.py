@@ -262,7 +262,7 @@ def main():
         "metric": "yolact_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": "FRC_model int8 YOLACT full graph + decode/Fast-NMS/mask assembly, synthetic RGB batch %d tiles per GPU (configs[1])" % n,
-                   "tiles_per_step": n, "frames_per_step": frames_per_step, "tile": "224x224x3 u8", "model": "synthetic FRC topology (real blob missing), 5.62 GMAC/tile",
+                   "tiles_per_step": n, "frames_per_step": frames_per_step, "tile": "224x224x3 u8", "graph": "synthetic FRC_model.tflite stand-in with the reference's operator histogram (real blob missing), 5.62 GMAC/tile",
                    "parallelism": "frame-sharded x%d, no collective" % world, "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "call": "tod_yolact_infer_tiles (host tiles in; tile class maps + detections + bit-packed binary masks out)"},
