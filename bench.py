@@ -358,6 +358,11 @@ def main():
         cpu_fps = cnt / TILES_PER_FRAME / (time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "%d tiles of the same batch through oracle/ int8 graph (reference-kernel loop nests, OpenMP %d threads), ~10 s" % (cnt, cores)}
+        # also 1 thread (per-core figure) and 4 threads (the reference's set_num_threads(4), yolact.rs:34)
+        for th in (4, 1):
+            t0 = time.perf_counter()
+            m.invoke(tl[0], threads=th)
+            line["cpu_baseline"]["frames_per_sec_%d_threads" % th] = 1.0 / TILES_PER_FRAME / (time.perf_counter() - t0)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
