@@ -1549,14 +1549,16 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
 // tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32) back to back into one TMEM accumulator: no loads, no epilogue.
 namespace tod {
 namespace {
-__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int n_mma, uint32_t idesc) {
+__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int n_mma, uint32_t idesc, int group) {
   extern __shared__ uint8_t peak_raw[];
   uint8_t* smem = peak_raw + ((1024u - (smem_u32(peak_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, ready, freed;   // `ready` / `freed` emulate the conv kernel's per-stage full / empty barriers
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u * uint32_t(i & 3);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&ready, 1);
+    mbar_init(&freed, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -1568,13 +1570,28 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int n_mma, uint32_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 0) {
-    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 128 * 128);
-    for (int i = 0; i < n_mma; ++i) {
-      const int kk = i & 3;
-      umma_i8(tmem, make_desc(a_addr + kk * 32, 1024u, 2u), make_desc(b_addr + kk * 32, 1024u, 2u), idesc, i ? 1u : 0u);
+  if (threadIdx.x < 32) {  // warp 0, converged: uniform descriptors, the elected lane issues (same scheme as the conv kernels)
+    const bool leader = elect_one();
+    const uint64_t ad0 = make_desc(smem_u32(smem), 1024u, 2u), bd0 = make_desc(smem_u32(smem + 128 * 128), 1024u, 2u);
+    uint32_t rphase = 0;
+    if (group <= 0) {
+      for (int i = 0; i < n_mma; i += 4) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (leader) umma_i8(tmem, ad0 + uint64_t(2 * kk), bd0 + uint64_t(2 * kk), idesc, (i | kk) ? 1u : 0u);
+      }
+    } else {
+      for (int i = 0; i < n_mma; i += group) {   // the conv kernel's per-stage protocol: wait `full`, fence, MMAs, commit `empty`
+        if (leader) mbar_arrive(&ready);
+        mbar_wait(&ready, rphase);
+        rphase ^= 1;
+        tc_fence_after();
+        for (int kk = 0; kk < group; ++kk)
+          if (leader) umma_i8(tmem, ad0 + uint64_t(2 * (kk & 3)), bd0 + uint64_t(2 * (kk & 3)), idesc, (i | kk) ? 1u : 0u);
+        if (leader) umma_commit(&freed);
+      }
     }
-    umma_commit(&bar);
+    if (leader) umma_commit(&bar);
     mbar_wait(&bar, 0);
   }
   tc_fence_before();
@@ -1598,12 +1615,13 @@ extern "C" int tod_i8_mma_peak(int device, int n_mma, int iters, double* tops) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc);
+  const int group = std::getenv("TOD_PEAK_GROUP") ? std::atoi(std::getenv("TOD_PEAK_GROUP")) : 0;
+  i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc, group);
   TOD_CUDA(cudaDeviceSynchronize());
   float best = 1e30f;
   for (int i = 0; i < iters; ++i) {
     cudaEventRecord(e0);
-    i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc);
+    i8_mma_peak_kernel<<<sms, 128, smem>>>(n_mma, idesc, group);
     cudaEventRecord(e1);
     TOD_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
