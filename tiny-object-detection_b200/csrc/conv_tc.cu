@@ -76,6 +76,7 @@ struct TcParams {
   // ---- cp.async A producer (flat 1x1 layers with short pixel rows: the TMA unit serves ~1 box row per 6-8 cycles
   // whatever its length, so 32-byte pixels starve it; 96 threads issuing 16-byte cp.async do not care)
   int dbg;                     // TOD_TC_DBG timing experiments: 1 = skip the output store
+  int run_w;                   // manual stores: pixels per staged run (pw, or pw * ph when the patch spans the image width)
   long long* trace;            // TOD_TC_TRACE: clock64 stamps of CTA 0 (epilogue warp 4 / MMA warp / producer), 16 per tile
   int a_cp;                    // 1 = A tiles are gathered with cp.async by warps 0, 2, 3
   const int8_t* in;            // flat [pixels][IC]
@@ -644,9 +645,9 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // order and in memory form a run (one patch row, or the whole tile for flat layers) whose bytes are contiguous in
     // global memory.  A run is staged densely, shifted so that staging and global addresses are congruent mod 16, and
     // then leaves as aligned 16-byte stores with a byte head and tail.
-    const int run_j = r / p.pw;
-    const uint32_t run_pitch = (uint32_t(p.pw) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
-    const int nruns = p.rows / p.pw;
+    const int run_j = r / p.run_w;
+    const uint32_t run_pitch = (uint32_t(p.run_w) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
+    const int nruns = p.rows / p.run_w;
     const int bar_id = 1 + grp;
     uint32_t pass_count = 0;
     int it = 0;
@@ -678,13 +679,17 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
       uint32_t soff = 0;  // manual mode: this row's byte offset inside the group's staging buffer
       if (!(MODE & kEpiTma)) {
+        // a run = one patch row; patches as wide as the image (run_w = pw * ph) are contiguous across their rows too
         const int x0 = w.tx * p.pw;
-        const bool valid_row = r < p.rows && yy < p.Hd && (p.flat || n < tiles);
-        const int nvalid = valid_row ? max(0, min(p.pw, Wd - x0)) : 0;
-        const long long g_run = (p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)yy * Wd + x0) * p.OC + ocb;
+        const bool whole = p.run_w != p.pw;
+        const int ry = whole ? w.ty * p.ph : yy;  // first image row of this pixel's run
+        const bool valid_row = r < p.rows && ry < p.Hd && (p.flat || n < tiles);
+        const int nvalid = !valid_row ? 0 : (whole ? min(p.ph, p.Hd - ry) * p.pw : max(0, min(p.pw, Wd - x0)));
+        const long long g_run = (p.flat ? 0ll : (long long)n * p.out_ts) + ((long long)ry * Wd + x0) * p.OC + ocb;
         const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(p.out) + g_run) & 15u;
-        soff = uint32_t(run_j) * run_pitch + a + uint32_t(wx) * uint32_t(ncols_tile);
-        if (wx == 0 && r < p.rows) {
+        const int pos = whole ? wy * p.pw + wx : wx;  // pixel index inside the run
+        soff = uint32_t(run_j) * run_pitch + a + uint32_t(pos) * uint32_t(ncols_tile);
+        if (pos == 0 && r < p.rows) {
           g_rowoff[run_j] = g_run;
           g_runlen[run_j] = nvalid * ncols_tile;
         }
@@ -786,8 +791,12 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tma_store_commit();
           }
         } else {
+          TOD_TR(5);
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          for (int j = 0; j < nruns; ++j) {
+          TOD_TR(6);
+          // one warp per run: the per-run address set-up is a dependent chain of shared loads, so the four warps walk
+          // different runs; lanes stride the run's aligned 16-byte chunks and the first lanes carry the head / tail bytes
+          for (int j = ew; j < nruns; j += 4) {
             const int len = g_runlen[j];
             if (len <= 0) continue;
             int8_t* gdst = p.out + g_rowoff[j];
@@ -796,12 +805,14 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int head = min(len, int((16u - a) & 15u));
             const int body = (len - head) >> 4;
             const int tail = len - head - (body << 4);
-            for (int c = eg; c < body; c += 128)
+            for (int c = lane; c < body; c += 32)
               *reinterpret_cast<uint4*>(gdst + head + 16 * c) = *reinterpret_cast<const uint4*>(ssrc + head + 16 * c);
-            if (eg < head) gdst[eg] = int8_t(ssrc[eg]);
-            if (eg < tail) gdst[head + 16 * body + eg] = int8_t(ssrc[head + 16 * body + eg]);
+            if (lane < head) gdst[lane] = int8_t(ssrc[lane]);
+            if (lane < tail) gdst[head + 16 * body + lane] = int8_t(ssrc[head + 16 * body + lane]);
           }
+          TOD_TR(7);
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          TOD_TR(8);
         }
       }
     }
@@ -1246,8 +1257,10 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
         const int groups = (a.max_tiles + pn - 1) / pn;
         const double util = double(p.Wd) * p.Hd * a.max_tiles / (double(txs) * tys * groups * kBM);
         const double halo = one ? 1.0 : double(pw + 2) * (ph + 2) / (double(pw) * ph);
-        const double score = util - 0.02 * halo;
-        if (score > best) {
+        // every (patch row, image) pair is one TMA box row per tap and K chunk and one output run: long rows are cheaper
+        // than many short ones (pw = 1 patches measured 4x slower main loops on the 7 x 7 and 14 x 14 maps)
+        const double score = util - 0.02 * halo - 0.002 * double(ph * pn);
+        if (score > best + 1e-12) {
           best = score;
           p.pw = pw;
           p.ph = ph;
@@ -1258,6 +1271,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     p.tiles_y = (p.Hd + p.ph - 1) / p.ph;
   }
   p.rows = p.pw * p.ph * p.pn;
+  p.run_w = p.pw;
   p.sbo = 8u * uint32_t(p.BK);
   p.layout = p.BK == 128 ? 2u : (p.BK == 64 ? 4u : 6u);
   p.a_stage = uint32_t((kBM * p.BK + 1023) / 1024 * 1024);
@@ -1359,8 +1373,9 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
       // conv_tc_fast_kernel, manual stores: the whole tile (every column) is staged as dense runs, one buffer per group
       p.sc = p.BN;
       p.pitch = p.BN;
-      const uint32_t run_pitch = (uint32_t(p.pw) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
-      p.stage_bytes = uint32_t((uint32_t(p.rows / p.pw) * run_pitch + 1023u) / 1024u * 1024u) * 2u;
+      p.run_w = (!p.flat && p.pw == p.Wd) ? p.pw * p.ph : p.pw;
+      const uint32_t run_pitch = (uint32_t(p.run_w) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
+      p.stage_bytes = uint32_t((uint32_t(p.rows / p.run_w) * run_pitch + 1023u) / 1024u * 1024u) * 2u;
     } else {
       p.sc = std::min(p.BN, 128);
       int pitch16 = p.sc / 16 + 1;
@@ -1504,6 +1519,13 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
       if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     }
     attr_set = true;
+  }
+  if (std::getenv("TOD_TC_PLAN")) {  // one line per planned layer, for tools/layer_table.py
+    const int groups_max = p.flat ? 1 : (a.max_tiles + p.pn - 1) / p.pn;
+    const long long m_tiles = p.flat ? ((long long)a.max_tiles * p.HW + kBM - 1) / kBM : (long long)groups_max * p.tiles_y * p.tiles_x;
+    std::fprintf(stderr, "TC_PLAN in=%dx%dx%d out=%dx%dx%d k=%d s=%d flat=%d fast=%d mode=%u pair=%d cp=%d BK=%d kchunks=%d BN=%d n_tiles=%d m_tiles=%lld patch=%dx%dx%d stages=%d wo=%d ncls=%d\n",
+                 g.IH, g.IW, g.IC, g.OH, g.OW, g.OC, g.KH, g.stride_h, p.flat, c->fast, c->mode, c->pair, p.a_cp, p.BK, p.kchunks, p.BN, p.n_tiles,
+                 m_tiles, p.pw, p.ph, p.pn, p.stages, p.wo, p.ncls);
   }
   *out = c;
   return TOD_OK;

@@ -10,6 +10,7 @@
 // TFLite integer rules, and the whole per-batch launch sequence is replayed from a CUDA graph.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -1570,15 +1571,18 @@ int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int 
   TOD_CUDA(cudaEventCreate(&e0));
   TOD_CUDA(cudaEventCreate(&e1));
   cudaStream_t s = y->stream;
+  // TOD_PROFILE_REPS > 1: back-to-back launches per event pair, which takes the event/launch gap out of short kernels
+  const int reps = std::getenv("TOD_PROFILE_REPS") ? std::max(1, std::atoi(std::getenv("TOD_PROFILE_REPS"))) : 1;
   int i = 0;
   for (const Step& st : y->steps) {
     TOD_TRY(run_step(y, st, n, s));  // warm
     TOD_CUDA(cudaEventRecord(e0, s));
-    TOD_TRY(run_step(y, st, n, s));
+    for (int r = 0; r < reps; ++r) TOD_TRY(run_step(y, st, n, s));
     TOD_CUDA(cudaEventRecord(e1, s));
     TOD_CUDA(cudaEventSynchronize(e1));
     float t = 0.f;
     TOD_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    t /= float(reps);
     if (i < cap) {
       if (ms) ms[i] = t;
       if (kinds) kinds[i] = y->graph.ops[st.op].code | (st.kind == kStepConvTc ? 0x1000 : 0) | (st.kind == kStepCopy ? 0x2000 : 0);
