@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtod_b200.so")
+LIB_PATH = os.environ.get("TOD_B200_LIB") or os.path.join(_HERE, "lib", "libtod_b200.so")  # override: A/B runs of two builds
 
 TOD_OK = 0
 TOD_WARN_REFERENCE_DIVERGES = 1

@@ -37,6 +37,9 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kTcThreads = 384;  // 4 control warps + 8 epilogue warps
+constexpr int kFastThreads = 384;  // conv_tc_fast_kernel: 4 control warps + kEpiWarps epilogue warps (16 measured 2 % slower per step)
+constexpr int kEpiWarps = kFastThreads / 32 - 4;
+constexpr int kAccStages = 2;     // accumulator stages in TMEM == epilogue groups (4 with 16 warps and BN <= 128 measured no faster)
 constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
@@ -67,7 +70,7 @@ struct TcParams {
   int sc, pitch;               // epilogue staging: columns per pass, bytes per staged row
   const uint8_t* post_lut;     // optional fused byte map (QUANTIZE / RELU / TANH chain), 256 entries
   // ---- fast epilogue (conv_tc_fast_kernel)
-  const int4* qtab;            // [OCp] {Q31 multiplier, rounding term with the output zero point folded in, right shift, 0}
+  const int4* qtab;            // [OCp] {Q31 multiplier, right shift, 2^31, rounding term with the output zero point folded in}
   const int32_t* b2tab;        // [ncls][OCp] 2 * (bias - zp * sum of in-image tap sums), compact border classes
   int ncls, ncls_x;            // compact border classes: cls = ymap[ymask] * ncls_x + xmap[xmask]
   uint8_t ymap[8], xmap[8];
@@ -76,6 +79,8 @@ struct TcParams {
   // ---- cp.async A producer (flat 1x1 layers with short pixel rows: the TMA unit serves ~1 box row per 6-8 cycles
   // whatever its length, so 32-byte pixels starve it; 96 threads issuing 16-byte cp.async do not care)
   int dbg;                     // TOD_TC_DBG timing experiments: 1 = skip the output store
+  int b_res;                   // fast kernel: the weights of the (single) N tile stay resident in shared memory, stages hold A only
+  int lin;                     // fast kernel, TMA mode: tile rows are contiguous in global memory, staged linearly, one 1-D bulk store
   int run_w;                   // manual stores: pixels per staged run (pw, or pw * ph when the patch spans the image width)
   long long* trace;            // TOD_TC_TRACE: clock64 stamps of CTA 0 (epilogue warp 4 / MMA warp / producer), 16 per tile
   int a_cp;                    // 1 = A tiles are gathered with cp.async by warps 0, 2, 3
@@ -176,6 +181,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -200,8 +210,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint
 struct SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
+  uint64_t b_full;   // resident weights have landed (TcParams::b_res)
   uint32_t tmem_base;
   uint8_t lut[256];
   int32_t add_tab[512];
@@ -477,17 +488,17 @@ __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles
 }
 
 template <uint32_t MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kFastThreads, 1)
 conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible to the compiler
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + size_t(p.stages) * p.a_stage;
-  uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;  // 1024-aligned (both stage sizes are)
+  uint8_t* stage_buf = smem_b + size_t(p.b_res ? p.kchunks : p.stages) * p.b_stage;  // 1024-aligned (both stage sizes are)
   long long* s_rowoff = reinterpret_cast<long long*>(stage_buf + p.stage_bytes);
-  int* s_runlen = reinterpret_cast<int*>(s_rowoff + 2 * kBM);   // [2 groups][128 runs]
-  int4* s_qtab = reinterpret_cast<int4*>(s_runlen + 2 * kBM);
+  int* s_runlen = reinterpret_cast<int*>(s_rowoff + 4 * kBM);   // [4 groups][128 runs]
+  int4* s_qtab = reinterpret_cast<int4*>(s_runlen + 4 * kBM);
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
 
@@ -501,20 +512,21 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&ctl->full[s], p.a_cp ? kCpThreads + 1 : 1);
+      mbar_init(&ctl->full[s], p.a_cp ? kCpThreads + (p.b_res ? 0 : 1) : 1);
       mbar_init(&ctl->empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], 4);  // one epilogue group (4 warps) owns each accumulator stage
+      mbar_init(&ctl->acc_empty[s], kEpiWarps / kAccStages);  // one epilogue group owns each accumulator stage
     }
+    mbar_init(&ctl->b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
-  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
-  if ((MODE & kEpiLut) && threadIdx.x >= 128) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
+  for (int i = threadIdx.x; i < p.OCp; i += kFastThreads) s_qtab[i] = p.qtab[i];
+  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kFastThreads) s_b2[i] = p.b2tab[i];
+  if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
   if (MODE & kEpiAdd)
-    for (int i = threadIdx.x; i < 512; i += kTcThreads) ctl->add_tab[i] = p.add_tab[i];
+    for (int i = threadIdx.x; i < 512; i += kFastThreads) ctl->add_tab[i] = p.add_tab[i];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -534,12 +546,16 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (pt == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     int stage = 0;
     uint32_t phase = 0;
+    if (p.b_res && pt == 0) {  // the whole weight matrix once: every tile of this CTA multiplies by the same N tile
+      mbar_expect_tx(&ctl->b_full, uint32_t(p.kchunks * p.BN * p.BK));
+      for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
+    }
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
       const long long row0 = (long long)w.tx * kBM;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&ctl->empty[stage], phase ^ 1);
-        if (pt == 0) {
+        if (pt == 0 && !p.b_res) {
           mbar_expect_tx(&ctl->full[stage], uint32_t(p.BN * p.BK));
           tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, 0, w.n_tile * p.BN);
         }
@@ -567,6 +583,10 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_res) {
+        mbar_expect_tx(&ctl->b_full, uint32_t(p.kchunks * p.BN * p.BK));
+        for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
+      }
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
         const int x0 = w.tx * p.pw, y0 = w.ty * p.ph, n0 = w.g * p.pn;
@@ -579,7 +599,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             } else {
             mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
             tma_load_4d(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left, y0 * p.stride + fy - p.pad_top, n0);
-            tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, w.n_tile * p.BN);
+            if (!p.b_res) tma_load_3d(smem_b + size_t(stage) * p.b_stage, &map_b, &ctl->full[stage], kc * p.BK, tap, w.n_tile * p.BN);
             }
             if (++stage == p.stages) {
               stage = 0;
@@ -594,22 +614,27 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool leader = elect_one();
     const uint64_t adesc0 = make_desc(smem_u32(smem_a), p.sbo, p.layout), bdesc0 = make_desc(smem_u32(smem_b), p.sbo, p.layout);
     const uint32_t a_step = p.a_stage >> 4, b_step = p.b_stage >> 4;  // descriptor address field is in 16-byte units
+    const uint32_t acc_stride = uint32_t(kTmemCols / kAccStages);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (p.b_res && blockIdx.x < total_work) {
+      mbar_wait(&ctl->b_full, 0);
+      tc_fence_after();
+    }
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t use = uint32_t(it >> 1);
+      const int as = it & (kAccStages - 1);
+      const uint32_t use = uint32_t(it) / uint32_t(kAccStages);
       mbar_wait(&ctl->acc_empty[as], (use & 1) ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      const uint32_t tmem_d = tmem_base + as * acc_stride;
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
         if (p.a_cp) fence_async_smem();  // cp.async wrote A through the generic proxy; the MMA reads it through the async one
         // the whole warp runs this loop converged with warp-uniform values, so the descriptors live in uniform registers;
         // only the tcgen05 instructions themselves are predicated on the elected lane
-        const uint64_t ad0 = adesc0 + uint64_t(uint32_t(stage) * a_step), bd0 = bdesc0 + uint64_t(uint32_t(stage) * b_step);
+        const uint64_t ad0 = adesc0 + uint64_t(uint32_t(stage) * a_step), bd0 = bdesc0 + uint64_t(uint32_t(p.b_res ? k : stage) * b_step);
         for (int kk = 0; kk < p.BK / 32; ++kk)
           if (leader) umma_i8(tmem_d, ad0 + uint64_t(2 * kk), bd0 + uint64_t(2 * kk), p.idesc, (k | kk) != 0 ? 1u : 0u);
         if (leader) {
@@ -624,21 +649,30 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // Two groups of four warps (one warp per TMEM lane quarter) take alternate tiles: group g owns accumulator stage g,
-    // its own staging buffers, named barrier and bulk-store queue, so the fixed per-tile latencies of one tile (barrier
-    // waits, TMEM loads, store issue) overlap the arithmetic of the other.
+    // kEpiWarps warps in acc_stages groups take tiles round-robin: group g owns accumulator stage g, its own staging
+    // buffers, named barrier and bulk-store queue, so the fixed per-tile latencies of one tile (accumulator wait, TMEM
+    // loads, barrier, store issue) overlap the arithmetic of the other.  The code is written for any multiple of four
+    // warps per group (two warps sharing a TMEM lane quarter take alternate 16-column chunks), but measured on the
+    // MobileNet expand layers the step is bound by the integer instruction count of the requantisation (about 5100
+    // warp instructions per 128 x 96 tile, IPC 0.65): 16 warps in 2 or 4 groups did not move the per-tile time.
+    constexpr int wpg = kEpiWarps / kAccStages;  // warps per group
     const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int grp = (warp - 4) >> 2;         // epilogue group == accumulator stage
+    const int grp = (warp - 4) / wpg;        // epilogue group == accumulator stage
+    const int wg = (warp - 4) % wpg;         // warp inside the group
+    const int half = wg >> 2;                // 8-warp groups: which 16-column chunks of a pass this warp takes (even / odd)
+    constexpr int cstep = 4 * wpg;           // columns between this warp's chunks (16 or 32)
+    constexpr int gthreads = 32 * wpg;
+    const uint32_t acc_stride = uint32_t(kTmemCols / kAccStages);
     const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
-    const int eg = threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
+    const int eg = threadIdx.x - 128 - grp * gthreads;  // 0..gthreads-1 inside the group
     const int wx = r % p.pw;
     const int wy = (r / p.pw) % p.ph;
     const int wn = r / (p.pw * p.ph);
     // staging: TMA mode = dense rows of p.wo bytes in the tensor map's swizzle; manual mode = padded pitch
-    const uint32_t swz_mask = p.wo == 128 ? 7u : (p.wo == 64 ? 3u : (p.wo == 32 ? 1u : 0u));
-    const uint32_t row_base = (MODE & kEpiTma) ? uint32_t(r) * uint32_t(p.wo) : uint32_t(r) * uint32_t(p.pitch);
-    const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.wo);
-    uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes >> 1);
+    const uint32_t swz_mask = p.lin ? 0u : (p.wo == 128 ? 7u : (p.wo == 64 ? 3u : (p.wo == 32 ? 1u : 0u)));
+    const uint32_t row_base = (MODE & kEpiTma) ? uint32_t(r) * uint32_t(p.lin ? p.OC : p.wo) : uint32_t(r) * uint32_t(p.pitch);
+    const uint32_t buf_bytes = uint32_t(kBM) * uint32_t(p.lin ? p.OC : p.wo);
+    uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes / uint32_t(kAccStages));
     long long* g_rowoff = s_rowoff + grp * kBM;   // manual mode: global byte offset of each *run* (see below)
     int* g_runlen = s_runlen + grp * kBM;
     // Manual stores (rows that are not 16-byte multiples: OC = 243, 12, 81).  Pixels that are consecutive in the tile row
@@ -652,11 +686,11 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t pass_count = 0;
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
+      if ((it & (kAccStages - 1)) != grp) continue;
       const int as = grp;
-      const uint32_t use = uint32_t(it >> 1);
-      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 64;
-#define TOD_TR(slot) do { if (tr) p.trace[(it >> 1) * 16 + (slot)] = clock64(); } while (0)
+      const uint32_t use = uint32_t(it) / uint32_t(kAccStages);
+      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128 && use < 32;
+#define TOD_TR(slot) do { if (tr) p.trace[use * 16 + (slot)] = clock64(); } while (0)
       TOD_TR(0);
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
       const int x = w.tx * p.pw + wx, yy = w.ty * p.ph + wy, n = w.g * p.pn + wn;
@@ -689,7 +723,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(p.out) + g_run) & 15u;
         const int pos = whole ? wy * p.pw + wx : wx;  // pixel index inside the run
         soff = uint32_t(run_j) * run_pitch + a + uint32_t(pos) * uint32_t(ncols_tile);
-        if (pos == 0 && r < p.rows) {
+        if (pos == 0 && r < p.rows && half == 0) {
           g_rowoff[run_j] = g_run;
           g_runlen[run_j] = nvalid * ncols_tile;
         }
@@ -704,7 +738,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&ctl->acc_full[as], use & 1);
       tc_fence_after();
       TOD_TR(2);
-      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * kAccStride;
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * acc_stride;
       if (p.dbg & 8) {  // timing experiment: no epilogue work, hand the accumulator straight back
         tc_fence_before();
         __syncwarp();
@@ -715,7 +749,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int pass_cols = min(p.sc, ncols_tile - pass0);
         uint8_t* sbuf = grp_buf + ((MODE & kEpiTma) ? (pass_count & 1u) * buf_bytes : 0u);
         ++pass_count;
-        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
+        for (int c0 = 16 * half; c0 < pass_cols; c0 += cstep) {
           uint32_t v[16];
           tmem_ld16(taddr + pass0 + c0, v);
           uint4 rres = make_uint4(0u, 0u, 0u, 0u);
@@ -783,20 +817,23 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           TOD_TR(6);
           fence_async_smem();
           TOD_TR(7);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
           TOD_TR(8);
           if (eg == 0 && !(p.dbg & 1)) {
-            if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * kBM, 0, 0);
+            if (p.lin) {  // the tile's rows are one contiguous block: a single 1-D bulk store instead of 128 box rows
+              const long long row0 = (long long)w.tx * kBM;
+              bulk_store_1d(p.out + row0 * p.OC, sbuf, uint32_t(min((long long)kBM, (long long)Wd - row0)) * uint32_t(p.OC));
+            } else if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * kBM, 0, 0);
             else tma_store_4d(&map_o, sbuf, ocb + pass0, w.tx * p.pw, w.ty * p.ph, w.g * p.pn);
             tma_store_commit();
           }
         } else {
           TOD_TR(5);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
           TOD_TR(6);
-          // one warp per run: the per-run address set-up is a dependent chain of shared loads, so the four warps walk
+          // one warp per run: the per-run address set-up is a dependent chain of shared loads, so the eight warps walk
           // different runs; lanes stride the run's aligned 16-byte chunks and the first lanes carry the head / tail bytes
-          for (int j = ew; j < nruns; j += 4) {
+          for (int j = wg; j < nruns; j += wpg) {
             const int len = g_runlen[j];
             if (len <= 0) continue;
             int8_t* gdst = p.out + g_rowoff[j];
@@ -811,7 +848,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (lane < tail) gdst[head + 16 * body + lane] = int8_t(ssrc[head + 16 * body + lane]);
           }
           TOD_TR(7);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
           TOD_TR(8);
         }
       }
@@ -1361,12 +1398,33 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     p.b_stage = uint32_t(((p.BN / 2) * p.BK + 1023) / 1024 * 1024);
     p.tx_bytes = uint32_t(p.rows * p.BK + (p.BN / 2) * p.BK);
   }
-  if (c->mode & kEpiTma) {
+  static const int lin_env = std::getenv("TOD_TC_LIN") ? std::atoi(std::getenv("TOD_TC_LIN")) : -1;
+  static const int bres_env = std::getenv("TOD_TC_BRES") ? std::atoi(std::getenv("TOD_TC_BRES")) : -1;
+  p.lin = 0;
+  p.b_res = 0;
+  {
+    const long long m_tiles_flat = p.flat ? ((long long)a.max_tiles * p.HW + kBM - 1) / kBM : 0;
+    // weights resident: 1x1, one N tile, several tiles per CTA to amortise over, at most 64 KB
+    if (c->fast && !c->pair && p.taps == 1 && p.n_tiles == 1 && size_t(p.kchunks) * p.b_stage <= 64 * 1024 &&
+        (p.flat ? m_tiles_flat : (long long)((a.max_tiles + p.pn - 1) / p.pn) * p.tiles_y * p.tiles_x) > sm_count() && bres_env != 0)
+      p.b_res = 1;
+    // linear staging + one bulk store per tile: flat layers whose rows are 16-byte multiples; 16-byte row-strided shared
+    // stores conflict gcd(OC / 16, 8) ways, so rows of 128 / 256 bytes keep the swizzled tensor store
+    const int u = g.OC / 16;
+    const int conflict = (u % 8 == 0) ? 8 : ((u % 4 == 0) ? 4 : ((u % 2 == 0) ? 2 : 1));
+    if (c->fast && !c->pair && (c->mode & kEpiTma) && p.flat && p.n_tiles == 1 && p.BN == g.OC && conflict <= 4 && lin_env != 0) p.lin = 1;
+  }
+  if (p.lin) {
+    p.wo = 16;  // unused by the linear path (the tensor map is still encoded, with its smallest box)
+    p.sc = p.BN;
+    p.pitch = g.OC;
+    p.stage_bytes = uint32_t((2 * kAccStages * kBM * g.OC + 1023) / 1024 * 1024);  // epilogue groups x double buffer
+  } else if (c->mode & kEpiTma) {
     const int width = c->pair ? std::min(p.BN, 64) : std::min(p.BN, 128);  // pairs: narrower passes buy a fifth operand stage
     p.wo = width <= 16 ? 16 : (width <= 32 ? 32 : (width <= 64 ? 64 : 128));
     p.sc = p.wo;
     p.pitch = p.wo;
-    p.stage_bytes = uint32_t(4 * kBM * p.wo);  // two epilogue groups x double buffer
+    p.stage_bytes = uint32_t(2 * (c->pair ? 2 : kAccStages) * kBM * p.wo);  // epilogue groups x double buffer
   } else {
     p.wo = 0;
     if (c->fast) {
@@ -1375,7 +1433,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
       p.pitch = p.BN;
       p.run_w = (!p.flat && p.pw == p.Wd) ? p.pw * p.ph : p.pw;
       const uint32_t run_pitch = (uint32_t(p.run_w) * uint32_t(p.BN) + 15u) / 16u * 16u + 32u;
-      p.stage_bytes = uint32_t((uint32_t(p.rows / p.run_w) * run_pitch + 1023u) / 1024u * 1024u) * 2u;
+      p.stage_bytes = uint32_t((uint32_t(p.rows / p.run_w) * run_pitch + 1023u) / 1024u * 1024u) * uint32_t(kAccStages);
     } else {
       p.sc = std::min(p.BN, 128);
       int pitch16 = p.sc / 16 + 1;
@@ -1384,11 +1442,16 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
       p.stage_bytes = uint32_t((kBM * p.pitch + 1023) / 1024 * 1024) * 2u;
     }
   }
-  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 24 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
+  const size_t fixed = size_t(p.stage_bytes) + size_t(kBM) * 48 + (c->fast ? table_bytes : 0) + sizeof(SmemCtl) + 1024;
   const size_t budget = 227 * 1024 - fixed;
-  p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
+  if (p.b_res) {
+    p.tx_bytes = uint32_t(p.rows * p.BK);
+    p.stages = int(std::min<size_t>(kMaxStages, (budget - size_t(p.kchunks) * p.b_stage) / p.a_stage));
+  } else {
+    p.stages = int(std::min<size_t>(kMaxStages, budget / (p.a_stage + p.b_stage)));
+  }
   if (p.stages < 2) return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory"));
-  c->smem_bytes = size_t(p.stages) * (p.a_stage + p.b_stage) + fixed;
+  c->smem_bytes = size_t(p.stages) * p.a_stage + size_t(p.b_res ? p.kchunks : p.stages) * p.b_stage + fixed;
   // instruction descriptor: D = s32, A = B = s8, both K-major, N, M = 128
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.BN >> 3) << 17) | (uint32_t((c->pair ? 2 * kBM : kBM) >> 4) << 24);
   p.out_zp = a.rq.out_zp;
@@ -1523,9 +1586,9 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   if (std::getenv("TOD_TC_PLAN")) {  // one line per planned layer, for tools/layer_table.py
     const int groups_max = p.flat ? 1 : (a.max_tiles + p.pn - 1) / p.pn;
     const long long m_tiles = p.flat ? ((long long)a.max_tiles * p.HW + kBM - 1) / kBM : (long long)groups_max * p.tiles_y * p.tiles_x;
-    std::fprintf(stderr, "TC_PLAN in=%dx%dx%d out=%dx%dx%d k=%d s=%d flat=%d fast=%d mode=%u pair=%d cp=%d BK=%d kchunks=%d BN=%d n_tiles=%d m_tiles=%lld patch=%dx%dx%d stages=%d wo=%d ncls=%d\n",
+    std::fprintf(stderr, "TC_PLAN in=%dx%dx%d out=%dx%dx%d k=%d s=%d flat=%d fast=%d mode=%u pair=%d cp=%d BK=%d kchunks=%d BN=%d n_tiles=%d m_tiles=%lld patch=%dx%dx%d stages=%d wo=%d ncls=%d bres=%d lin=%d\n",
                  g.IH, g.IW, g.IC, g.OH, g.OW, g.OC, g.KH, g.stride_h, p.flat, c->fast, c->mode, c->pair, p.a_cp, p.BK, p.kchunks, p.BN, p.n_tiles,
-                 m_tiles, p.pw, p.ph, p.pn, p.stages, p.wo, p.ncls);
+                 m_tiles, p.pw, p.ph, p.pn, p.stages, p.wo, p.ncls, p.b_res, p.lin);
   }
   *out = c;
   return TOD_OK;
@@ -1552,7 +1615,7 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
     TOD_CUDA(launch_k(conv_tc_kernel, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, p, tiles));
   } else {
     switch (c->mode) {
-#define TOD_TC_CASE(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M>, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); break;
+#define TOD_TC_CASE(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); break;
       TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
       TOD_TC_CASE(12) TOD_TC_CASE(13)
       default: return fail(TOD_ERR_UNSUPPORTED, "conv_tc: no kernel for epilogue mode %u", c->mode);
@@ -1749,7 +1812,8 @@ int conv_selftest_impl(int device, int tiles, int H, int W, int IC, int OC, int 
     cudaDeviceSynchronize();
     long long h[32 * 16];
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    for (int t = 0; t < 12; ++t) {
+    const int trace_rows = std::min(32, std::max(1, std::atoi(std::getenv("TOD_TC_TRACE"))));
+    for (int t = 0; t < trace_rows; ++t) {
       std::printf("tile %2d t0=%8lld :", t, h[t * 16] - h[0]);
       for (int k = 1; k <= 8; ++k) std::printf(" %6lld", h[t * 16 + k] - h[t * 16 + k - 1]);
       std::printf("\n");
