@@ -217,6 +217,12 @@ int tod_i8_mma_peak(int device, int n_mma, int iters, double* tops);
 /* multiply-accumulates per tile of every planned step, in tod_yolact_profile_ops order; returns the step count */
 int tod_yolact_step_macs(const tod_yolact* y, int64_t* macs, int cap);
 
+/* Diagnostics: one step enqueued on the executor's lane streams without a CUDA graph, a timing event behind every launch.
+ * end_ms[i] = end of planned step i relative to the start of the step, lanes[i] = the lane stream it ran on, kinds[i] as
+ * tod_yolact_profile_ops; the last three entries are the segmentation pass, box decode / NMS / top-k, and mask assembly.
+ * Returns the number of entries. */
+int tod_yolact_trace_steps(tod_yolact* y, int n, float* end_ms, int32_t* lanes, int32_t* kinds, int cap);
+
 /* One KxK (K = 1 or 3), stride-1, SAME convolution [tiles,H,W,IC] -> [tiles,H,W,OC] on seeded random data through
  * both the tcgen05 implicit-GEMM kernel and the CUDA-core direct kernel: times both and counts differing bytes. */
 int tod_conv_selftest(int device, int tiles, int H, int W, int IC, int OC, int K, int iters, float* ms_tc,

@@ -609,15 +609,26 @@ int detect_setup_kernels(const DetectCfg& c) {
 }
 
 int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
-                        int64_t box_ts, int tiles, cudaStream_t s) {
+                        int64_t box_ts, int tiles, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   TOD_CUDA(cudaMemsetAsync(b.cand_count, 0, sizeof(int) * size_t(tiles) * (c.C - 1), s));
   TOD_CUDA(cudaMemsetAsync(b.surv_count, 0, sizeof(int) * size_t(tiles), s));
   dim3 g1((c.P + kDecodeThreads - 1) / kDecodeThreads, tiles);
   decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
   dim3 g2(c.C - 1, tiles);
   const int small_cap = std::min(kNmsSmall, next_pow2(c.P));
+  // the two NMS launches touch disjoint (class, tile) lists; the worst-case one is a handful of long CTAs (latency-bound)
+  // while the small one fills the machine, so with a second stream they run side by side
+  const bool large = next_pow2(c.P) > small_cap;
+  const bool split = large && aux && ev_fork && ev_join;
+  if (split) {
+    TOD_CUDA(cudaEventRecord(ev_fork, s));
+    TOD_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
+    nms_kernel<<<g2, kNmsThreads, nms_smem(c), aux>>>(c, b, next_pow2(c.P), small_cap, c.P);
+    TOD_CUDA(cudaEventRecord(ev_join, aux));
+  }
   nms_kernel<<<g2, kNmsThreads, nms_smem_for(c, small_cap), s>>>(c, b, small_cap, 0, small_cap);
-  if (next_pow2(c.P) > small_cap) nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P), small_cap, c.P);
+  if (large && !split) nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P), small_cap, c.P);
+  if (split) TOD_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
   select_kernel<<<tiles, kSelThreads, detect_select_smem(c), s>>>(c, b, next_pow2((c.C - 1) * c.top_k));
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
@@ -634,7 +645,7 @@ int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_
 int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
                   int64_t box_ts, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto, int64_t proto_ts, int tiles,
                   bool want_masks, cudaStream_t s) {
-  TOD_TRY(launch_detect_boxes(c, b, cls, cls_ts, box, box_ts, tiles, s));
+  TOD_TRY(launch_detect_boxes(c, b, cls, cls_ts, box, box_ts, tiles, s, nullptr, nullptr, nullptr));
   if (want_masks) TOD_TRY(launch_detect_masks(c, b, coef, coef_ts, proto, proto_ts, tiles, s));
   return TOD_OK;
 }

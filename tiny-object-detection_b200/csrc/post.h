@@ -72,7 +72,7 @@ int launch_detect(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls
 // the two halves of launch_detect: boxes / scores / Fast-NMS / top-k need only the class and box heads, so the graph
 // executor runs them beside the protonet branch; mask assembly needs the prototypes and the selected detections
 int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_t* cls, int64_t cls_ts, const uint8_t* box,
-                        int64_t box_ts, int tiles, cudaStream_t s);
+                        int64_t box_ts, int tiles, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto,
                         int64_t proto_ts, int tiles, cudaStream_t s);
 size_t detect_select_smem(const DetectCfg& c);

@@ -155,6 +155,8 @@ struct tod_yolact {
   int tc_layers = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // early read-back of the tile class maps while detection still runs
+  cudaStream_t nms_stream = nullptr;    // the worst-case Fast-NMS launch runs beside the common-case one
+  cudaEvent_t nms_fork = nullptr, nms_join = nullptr;
   cudaEvent_t seg_ready = nullptr;      // recorded (as an external event node) inside the graph right after seg_post_kernel
   bool seg_ready_in_graph = false;
   uint8_t* d_const = nullptr;
@@ -180,12 +182,14 @@ struct tod_yolact {
   uint8_t* d_tiles_rgb = nullptr;
   // independent branches of the graph (FPN levels, the five head levels, protonet) are captured on separate
   // streams so the CUDA graph runs them concurrently
-  static constexpr int kLanes = 6;
-  cudaStream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kLanes = 16;
+  cudaStream_t lanes[kLanes] = {};
   std::vector<cudaEvent_t> step_events;
   cudaEvent_t post_events[2] = {nullptr, nullptr};  // seg post-processing / detection boxes, when they run on a branch lane
   std::vector<std::vector<int>> out_steps;        // per graph output: the steps that write it
   cudaEvent_t fork_event = nullptr;
+  std::vector<int> trace_lanes;
+  std::vector<cudaEvent_t> trace_events;  // tod_yolact_trace_steps: timing events, one per step + 4 (start, seg post, boxes, masks)
   // CUDA graphs, keyed by (tiles << 3 | dets << 2 | mask mode); mask mode: 0 = none, 1 = binary masks only, 2 = float + binary
   std::map<int, cudaGraphExec_t> graphs;
   int last_tiles = 0;
@@ -1060,16 +1064,32 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
   const int L = tod_yolact::kLanes;
   std::vector<int> lane_of(y->steps.size(), 0), tail(L, -1);
   std::vector<char> forked(L, 0);
+  std::vector<std::vector<char>> ancestors(y->steps.size());
+  if (!y->trace_events.empty()) TOD_CUDA(cudaEventRecord(y->trace_events[y->steps.size()], origin));
   TOD_CUDA(cudaEventRecord(y->fork_event, origin));
   for (size_t i = 0; i < y->steps.size(); ++i) {
     const Step& st = y->steps[i];
+    // Stream order becomes a graph edge, so a step only joins a lane whose tail it depends on anyway: first the lane
+    // of a direct producer that is still a tail (a kernel -> kernel chain, PDL-eligible), else a lane whose tail is one
+    // of its ancestors, else an unused lane; the captured graph then holds the true dependencies only (with six
+    // round-robin lanes the small pyramid levels' heads queued behind unrelated layers and held detection back ~250 us).
+    std::vector<char>& anc = ancestors[i];
+    anc.assign(y->steps.size(), 0);
+    for (int d : st.deps) {
+      anc[d] = 1;
+      for (size_t k = 0; k < y->steps.size(); ++k) anc[k] |= ancestors[d][k];
+    }
     int lane = -1;
     for (auto it = st.deps.rbegin(); it != st.deps.rend() && lane < 0; ++it)
-      if (tail[lane_of[*it]] == *it) lane = lane_of[*it];  // continue the chain of a producer that is still a lane tail
+      if (tail[lane_of[*it]] == *it) lane = lane_of[*it];
+    for (int l = 0; l < L && lane < 0; ++l)
+      if (tail[l] >= 0 && anc[tail[l]]) lane = l;
+    for (int l = 0; l < L && lane < 0; ++l)
+      if (tail[l] < 0) lane = l;
     if (lane < 0) {
       lane = 0;
       for (int l = 1; l < L; ++l)
-        if (tail[l] < tail[lane]) lane = l;  // least recently used lane
+        if (tail[l] < tail[lane]) lane = l;  // out of lanes: least recently used
     }
     cudaStream_t ls = y->lanes[lane];
     if (!forked[lane]) {
@@ -1089,6 +1109,10 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
     pdl_next() = false;
     TOD_TRY(rc_step);
     TOD_CUDA(cudaEventRecord(y->step_events[i], ls));
+    if (!y->trace_events.empty()) {
+      TOD_CUDA(cudaEventRecord(y->trace_events[i], ls));
+      y->trace_lanes[i] = lane;
+    }
     lane_of[i] = lane;
     tail[lane] = int(i);
   }
@@ -1120,18 +1144,20 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
     SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
     launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, y->lanes[lane]);
     // an external event node: the host-facing call starts copying the class maps back as soon as they exist
-    TOD_CUDA(cudaEventRecordWithFlags(y->seg_ready, y->lanes[lane], cudaEventRecordExternal));
+    if (y->trace_events.empty()) TOD_CUDA(cudaEventRecordWithFlags(y->seg_ready, y->lanes[lane], cudaEventRecordExternal));
+    else TOD_CUDA(cudaEventRecord(y->seg_ready, y->lanes[lane]));  // tod_yolact_trace_steps runs outside a capture
     TOD_CUDA(cudaEventRecord(y->post_events[0], y->lanes[lane]));
+    if (!y->trace_events.empty()) TOD_CUDA(cudaEventRecord(y->trace_events[y->steps.size() + 1], y->lanes[lane]));
     seg_done = true;
   }
   if (dets) {
     int lane = 0;
     TOD_TRY(after_outputs({y->o_cls, y->o_box}, &lane));
-    if (seg_done) TOD_CUDA(cudaStreamWaitEvent(y->lanes[lane], y->post_events[0], 0));  // harmless ordering if both share a lane
     const Place& pc = y->place[y->graph.outputs[y->o_cls]];
     const Place& pb = y->place[y->graph.outputs[y->o_box]];
-    TOD_TRY(launch_detect_boxes(y->dcfg, y->dbuf, pc.base, pc.tile_stride, pb.base, pb.tile_stride, n, y->lanes[lane]));
+    TOD_TRY(launch_detect_boxes(y->dcfg, y->dbuf, pc.base, pc.tile_stride, pb.base, pb.tile_stride, n, y->lanes[lane], y->nms_stream, y->nms_fork, y->nms_join));
     TOD_CUDA(cudaEventRecord(y->post_events[1], y->lanes[lane]));
+    if (!y->trace_events.empty()) TOD_CUDA(cudaEventRecord(y->trace_events[y->steps.size() + 2], y->lanes[lane]));
     det_done = true;
   }
   for (int l = 0; l < L; ++l)
@@ -1145,6 +1171,7 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
     if (masks < 2) db.masks = nullptr;
     TOD_TRY(launch_detect_masks(y->dcfg, db, pf.base, pf.tile_stride, pp.base, pp.tile_stride, n, origin));
   }
+  if (!y->trace_events.empty()) TOD_CUDA(cudaEventRecord(y->trace_events[y->steps.size() + 3], origin));
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
 }
@@ -1310,6 +1337,9 @@ void tod_yolact_destroy(tod_yolact* y) {
   cudaFree(y->d_const); cudaFree(y->d_act);
   if (y->copy_stream) cudaStreamDestroy(y->copy_stream);
   if (y->seg_ready) cudaEventDestroy(y->seg_ready);
+  if (y->nms_fork) cudaEventDestroy(y->nms_fork);
+  if (y->nms_join) cudaEventDestroy(y->nms_join);
+  if (y->nms_stream) cudaStreamDestroy(y->nms_stream);
   if (y->stream) cudaStreamDestroy(y->stream);
   delete y;
 }
@@ -1335,6 +1365,9 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
   cudaError_t ce = cudaStreamCreateWithFlags(&raw->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&raw->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&raw->seg_ready, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&raw->nms_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&raw->nms_fork, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&raw->nms_join, cudaEventDisableTiming);
   if (ce != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)));
   ConstArena arena;
   int rc = plan(raw, &arena);
@@ -1561,6 +1594,44 @@ int tod_yolact_step_macs(const tod_yolact* y, int64_t* macs, int cap) {
     ++i;
   }
   return i;
+}
+
+// One step enqueued on the lane streams directly (no graph) with a timing event behind every launch: end time of each
+// step relative to the start of the step, and the lane it ran on.  Entries [steps .. steps+2] are the literal
+// segmentation pass, the box decode / NMS / top-k and the mask assembly (the step's end).
+int tod_yolact_trace_steps(tod_yolact* y, int n, float* end_ms, int32_t* lanes, int32_t* kinds, int cap) {
+  if (!y) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_trace_steps: null handle");
+  if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_trace_steps: n=%d outside [1,%d]", n, y->opt.max_tiles);
+  TOD_CUDA(cudaSetDevice(y->device));
+  const size_t ns = y->steps.size();
+  const bool dets = y->det_ready && y->have_priors;
+  y->trace_events.assign(ns + 4, nullptr);
+  y->trace_lanes.assign(ns, 0);
+  for (cudaEvent_t& e : y->trace_events) TOD_CUDA(cudaEventCreate(&e));
+  int rc = TOD_OK;
+  for (int rep = 0; rep < 3 && rc == TOD_OK; ++rep) {  // the last repetition is the one read back
+    rc = enqueue_all_parallel(y, n, dets, dets ? 1 : 0, y->stream);
+    if (rc == TOD_OK && cudaStreamSynchronize(y->stream) != cudaSuccess) rc = fail(TOD_ERR_CUDA, "trace run failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  int count = 0;
+  if (rc == TOD_OK) {
+    for (size_t i = 0; i < ns + 3; ++i) {
+      const size_t ev = i < ns ? i : i + 1;
+      float t = -1.f;
+      if (cudaEventQuery(y->trace_events[ev]) == cudaSuccess) cudaEventElapsedTime(&t, y->trace_events[ns], y->trace_events[ev]);
+      (void)cudaGetLastError();
+      if (int(i) < cap) {
+        if (end_ms) end_ms[i] = t;
+        if (lanes) lanes[i] = i < ns ? y->trace_lanes[i] : -1;
+        if (kinds) kinds[i] = i < ns ? (y->graph.ops[y->steps[i].op].code | (y->steps[i].kind == kStepConvTc ? 0x1000 : 0) | (y->steps[i].kind == kStepCopy ? 0x2000 : 0)) : -1;
+      }
+      ++count;
+    }
+  }
+  for (cudaEvent_t e : y->trace_events) cudaEventDestroy(e);
+  y->trace_events.clear();
+  y->last_tiles = n;
+  return rc < 0 ? rc : count;
 }
 
 int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int cap) {

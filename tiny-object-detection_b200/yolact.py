@@ -153,6 +153,14 @@ class Yolact:
         k = check(lib().tod_yolact_profile_ops(self._h, n, _ptr(ms), _ptr(kinds), cap))
         return ms[:k], kinds[:k]
 
+    def trace_steps(self, n):
+        cap = 600
+        ms = np.zeros(cap, np.float32)
+        lanes = np.zeros(cap, np.int32)
+        kinds = np.zeros(cap, np.int32)
+        k = check(lib().tod_yolact_trace_steps(self._h, n, _ptr(ms), _ptr(lanes), _ptr(kinds), cap))
+        return ms[:k], lanes[:k], kinds[:k]
+
     def step_macs(self):
         cap = 512
         m = np.zeros(cap, np.int64)
