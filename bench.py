@@ -124,6 +124,8 @@ def main():
     ap.add_argument("--no-scene", action="store_true", help="skip the point-cloud side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0)
+    ap.add_argument("--pipeline", type=int, default=3,
+                    help="batches in flight: handles that take alternate steps on their own streams (1 = one handle, steps back to back)")
     ap.add_argument("--fused", type=int, default=512, help="frames of the fused 320x240 RGB-D side measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -223,7 +225,84 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = world * frames_per_step * args.steps / e2e_s
-    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
+    single = {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e}
+
+    # ---- two (or more) batches in flight: the frame loop's double buffering.  Every step is still one full batch through one
+    # handle; consecutive steps go to alternate handles on their own streams, so the latency-bound tail of one batch (small
+    # pyramid levels, Fast-NMS, mask assembly) overlaps the backbone of the next, and in the end-to-end leg one batch's copies
+    # overlap the other's kernels (one host thread per handle: the C-ABI call blocks, ctypes drops the GIL).
+    depth = max(1, args.pipeline)
+    if depth > 1:
+        import threading
+        ys = [y] + [tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl) for _ in range(depth - 1)]
+        pstreams = [torch.cuda.Stream() for _ in range(depth)]
+        ptiles = [tiles_d] + [torch.from_numpy(synth.rgb_tiles(n, seed=100 + 7 * k + rank)).cuda() for k in range(1, depth)]
+
+        def pstep(k):
+            h = k % depth
+            ys[h].infer_tiles_device(ptiles[h].data_ptr(), n, pstreams[h].cuda_stream)
+
+        for k in range(2 * depth + max(args.warmup, 3)):
+            pstep(k)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()  # on tstream; every pipeline stream starts behind it and tstream ends behind all of them
+        for ps in pstreams:
+            ps.wait_event(p0)
+        for k in range(args.steps):
+            pstep(k)
+        for ps in pstreams:
+            tstream.wait_stream(ps)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1)
+        if dist is not None:
+            t = torch.tensor([pms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = float(t.item())
+        barrier()
+        ms = pms
+        value = world * frames_per_step * args.steps / (pms * 1e-3)
+
+        # end to end: one host thread per handle, each with its own pinned buffers
+        ctx = []
+        for h in range(depth):
+            d_h, keep_h = ys[h]._alloc_dets(n, True)
+            pin = {}
+            for kk in ("count", "boxes", "scores", "classes", "priors", "masks_bits"):
+                tt = torch.from_numpy(keep_h[kk].view(np.int32) if keep_h[kk].dtype == np.uint32 else keep_h[kk]).pin_memory()
+                pin[kk] = tt
+                setattr(d_h, kk, tt.data_ptr())
+            d_h.masks = None
+            d_h.masks_bin = None
+            ctx.append((ys[h], d_h, pin, torch.empty((n, 224, 224), dtype=torch.int32).pin_memory(), (tiles_h if h == 0 else ptiles[h].cpu().pin_memory())))
+        counts = [args.steps // depth + (1 if h < args.steps % depth else 0) for h in range(depth)]
+
+        def worker(h, reps):
+            torch.cuda.set_device(local_rank)
+            yy, d_h, _, tc_p, th = ctx[h]
+            for _ in range(reps):
+                tod_b200._lib.check(lib.tod_yolact_infer_tiles(yy._h, th.data_ptr(), n, None, tc_p.data_ptr(), C.byref(d_h)))
+
+        def run_threads(cs):
+            ths = [threading.Thread(target=worker, args=(h, cs[h])) for h in range(depth)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+
+        run_threads([2] * depth)
+        barrier()
+        t0 = time.perf_counter()
+        run_threads(counts)
+        torch.cuda.synchronize()
+        pe2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([pe2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pe2e_s = float(t.item())
+        e2e = world * frames_per_step * args.steps / pe2e_s
+    clk = clocks.stop() if rank == 0 else None  # sampled over the timed regions (device-resident and end-to-end)
 
     # ---- roofline of the dominant kernel: conv_tc_fast_kernel (tcgen05 int8 implicit GEMM), every launch of one step.
     # achieved = algorithmic ops of those launches (2 * MACs, SURVEY 8d: 11.24 Gop/tile over the whole graph) / the sum of
@@ -263,9 +342,12 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": "FRC_model int8 YOLACT full graph + decode/Fast-NMS/mask assembly, synthetic RGB batch %d tiles per GPU (configs[1])" % n,
                    "tiles_per_step": n, "frames_per_step": frames_per_step, "tile": "224x224x3 u8", "graph": "synthetic FRC_model.tflite stand-in with the reference's operator histogram (real blob missing), 5.62 GMAC/tile",
-                   "parallelism": "frame-sharded x%d, no collective" % world, "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)},
+                   "parallelism": "frame-sharded x%d, no collective" % world,
+                   "pipeline": ("%d batches in flight: %d handles take alternate %d-tile steps on their own streams (frame-loop double buffering); "
+                                "single_stream = one handle, steps back to back" % (depth, depth, n)) if depth > 1 else "1 (one handle, steps back to back)", "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "call": "tod_yolact_infer_tiles (host tiles in; tile class maps + detections + bit-packed binary masks out)"},
+        "single_stream": {"value": single["value"], "ms_per_step": single["ms_per_step"], "e2e_value": single["e2e"], "unit": "frames/s"},
         "gpu_launches": int(st["launches_per_call"] * args.steps),
         "roofline": roofline,
         "clocks": clk,

@@ -99,3 +99,24 @@ def test_errors(tod, models, tmp_path):
     y = tod.Yolact.init(small, max_tiles=2)
     with pytest.raises(tod.TodError):
         y.infer_tiles(synth.rgb_tiles(3, S=64))
+
+
+def test_pool_matches_single_handle(tod, models):
+    """Batches through a pool of three handles (alternate handles, one host thread each) give exactly what one handle gives."""
+    full, _ = models
+    batches = [synth.rgb_tiles(4, seed=300 + k) for k in range(7)]
+    y = tod.Yolact.init(full, max_tiles=4)
+    want = [y.infer_tiles(b, detections=True, float_masks=False) for b in batches]
+    y.close()
+    pool = tod.YolactPool(full, depth=3, max_tiles=4)
+    got = pool.map(batches, detections=True, float_masks=False)
+    pool.close()
+    for g, w in zip(got, want):
+        assert np.array_equal(g["tile_classes"], w["tile_classes"])
+        for a, b in zip(g["outputs"], w["outputs"]):
+            assert np.array_equal(a, b)
+        for dg, dw in zip(g["dets"], w["dets"]):
+            assert dg["n"] == dw["n"]
+            assert np.array_equal(dg["prior"], dw["prior"]) and np.array_equal(dg["cls"], dw["cls"])
+            assert np.array_equal(dg["score"].view(np.uint32), dw["score"].view(np.uint32))
+            assert np.array_equal(dg["masks_bits"], dw["masks_bits"])

@@ -197,6 +197,38 @@ class Yolact:
         return out
 
 
+class YolactPool:
+    """`depth` handles that take alternate batches, each from its own host thread: the frame loop's double / triple
+    buffering.  One batch's host<->device copies and latency-bound tail (small pyramid levels, Fast-NMS, mask assembly)
+    overlap the next batch's backbone.  Every batch still goes through one handle exactly as `Yolact.infer_tiles` would run
+    it (same results); the C-ABI call blocks and ctypes drops the GIL, so plain threads are enough."""
+
+    def __init__(self, model_path=DEFAULT_MODEL, device=0, depth=3, **options):
+        from concurrent.futures import ThreadPoolExecutor
+        self.handles = [Yolact(model_path, device, **options) for _ in range(max(1, depth))]
+        self._workers = [ThreadPoolExecutor(1) for _ in self.handles]  # one thread per handle: a handle runs one batch at a time
+        self._next = 0
+
+    def set_priors(self, priors):
+        for h in self.handles:
+            h.set_priors(priors)
+
+    def submit(self, tiles, **kw):
+        """Queues one batch; returns a future of `Yolact.infer_tiles(tiles, **kw)`."""
+        k = self._next % len(self.handles)
+        self._next += 1
+        return self._workers[k].submit(self.handles[k].infer_tiles, tiles, **kw)
+
+    def map(self, batches, **kw):
+        return [f.result() for f in [self.submit(b, **kw) for b in batches]]
+
+    def close(self):
+        for w in self._workers:
+            w.shutdown(wait=True)
+        for h in self.handles:
+            h.close()
+
+
 def model_inspect(path):
     no, nt, m = C.c_int32(), C.c_int32(), C.c_int64()
     check(lib().tod_model_inspect(str(path).encode(), C.byref(no), C.byref(nt), C.byref(m)))
