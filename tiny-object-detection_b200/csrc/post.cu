@@ -320,6 +320,7 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const 
 // launch's range returns immediately.  The common case no longer pays the worst case's 36 KB per CTA.
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmall = 512;
+constexpr int kNmsRank = 256;   // lists up to this long are rank-sorted (needs top_k <= sort_cap / 2, checked per launch)
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_lo, int n_hi) {
   extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k]
   float4* s_box = reinterpret_cast<float4*>(s_keys + sort_cap);
@@ -331,9 +332,28 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const unsigned long long* src = b.cand + (int64_t(t) * (c.C - 1) + k) * c.P;
-  for (int i = threadIdx.x; i < np2; i += kNmsThreads) s_keys[i] = i < n ? src[i] : 0ull;
-  bitonic_sort_desc(s_keys, np2);
   const int m = min(n, c.top_k);
+  if (n <= kNmsRank && n <= sort_cap / 2) {
+    // short lists: rank sort.  Keys are unique (the prior index is part of the key), so a key's position in the descending
+    // order is the number of larger keys: one pass over the list per thread, one barrier, against 28..36 barrier-separated
+    // compare-exchange rounds of the bitonic network.  Only the top_k ranks are written (into the upper half of s_keys).
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) s_keys[i] = src[i];
+    __syncthreads();
+    unsigned long long* s_sorted = s_keys + sort_cap / 2;
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+      const unsigned long long key = s_keys[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int q = 0; q < n; ++q) rank += s_keys[q] > key ? 1 : 0;
+      if (rank < m) s_sorted[rank] = key;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += kNmsThreads) s_keys[i] = s_sorted[i];
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < np2; i += kNmsThreads) s_keys[i] = i < n ? src[i] : 0ull;
+    bitonic_sort_desc(s_keys, np2);
+  }
   for (int i = threadIdx.x; i < m; i += kNmsThreads) {
     const int prior = int(0xFFFFFFFFu - unsigned(s_keys[i] & 0xFFFFFFFFull));
     const float4 bx = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
