@@ -487,11 +487,14 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
 
 // ------------------------------------------------------------------ depthwise 3x3, sliding window
 // Thread = one 4-channel word of one output column, walking down a run of output rows.  The (column, channel word)
-// pair is a flattened index along the NHWC row, so consecutive lanes read consecutive words whatever C is.  The
-// 3x3 input window lives in nine registers and slides vertically: a stride-1 row costs three new words (two rows of
-// three for stride 2) instead of nine.  Out-of-image taps read as the input zero point, which makes their
-// (in - zp) * w term vanish with the bias pre-folded as bias - zp * sum(w): no branches in the arithmetic.
-// Requantisation is the 4-instruction form of Requant::fast_tab.
+// pair is a flattened index along the NHWC row, so consecutive lanes read consecutive words whatever C is.
+// A depthwise tap multiplies channel by channel, so a dp4a over a loaded word (4 channels of ONE tap) wastes three of
+// its four products.  Each input row's three words (columns x-1, x, x+1) are therefore transposed with six PRMT into
+// four words holding the three taps of ONE channel (fourth byte multiplied by a zero weight): a filter row then costs
+// one dp4a per channel, 12 per output word instead of 36 (ncu on the 36-dp4a form: fmaheavy 54 %, issue 54 %, 95
+// registers).  The transposed rows slide vertically: a stride-1 output row costs one new input row (3 loads, 6 PRMT),
+// a stride-2 row two.  Out-of-image taps read as the input zero point, which makes their (in - zp) * w term vanish
+// with the bias pre-folded as bias - zp * sum(w): no branches in the arithmetic.  Requantisation: Requant::fast_tab.
 constexpr int kDwThreads = 128;
 
 template <int STRIDE, bool SAT>
@@ -505,16 +508,29 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
   const int j = blockIdx.x * kDwThreads + threadIdx.x;
   if (j >= g.OW * CW) return;
   const int ox = j / CW, c = (j - ox * CW) * 4;
-  int wm[9][4];
+  // three input words (taps fx = 0, 1, 2; four channels each) -> four words (channel q; bytes = taps 0, 1, 2, don't care)
+  auto transpose = [](unsigned a0, unsigned a1, unsigned a2, unsigned (&t)[4]) {
+    const unsigned lo = __byte_perm(a0, a1, 0x5140);  // a0.b0 a1.b0 a0.b1 a1.b1
+    const unsigned hi = __byte_perm(a0, a1, 0x7362);  // a0.b2 a1.b2 a0.b3 a1.b3
+    t[0] = __byte_perm(lo, a2, 0x4410);
+    t[1] = __byte_perm(lo, a2, 0x5532);
+    t[2] = __byte_perm(hi, a2, 0x6610);
+    t[3] = __byte_perm(hi, a2, 0x7732);
+  };
+  unsigned wt[3][4];  // wt[fy][q] = {w(fy,0,q), w(fy,1,q), w(fy,2,q), 0}
   int wall[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp) {
-    const int wv = __ldg(reinterpret_cast<const int*>(w + int64_t(tp) * C + c));
+  for (int fy = 0; fy < 3; ++fy) {
+    unsigned wv[3];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      wm[tp][q] = wv & (0xFF << (8 * q));
-      wall[q] += (wv << (24 - 8 * q)) >> 24;
+    for (int fx = 0; fx < 3; ++fx) {
+      wv[fx] = unsigned(__ldg(reinterpret_cast<const int*>(w + int64_t(fy * 3 + fx) * C + c)));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wall[q] += int(wv[fx] << (24 - 8 * q)) >> 24;
     }
+    transpose(wv[0], wv[1], wv[2], wt[fy]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wt[fy][q] &= 0x00FFFFFFu;
   }
   int4 k[4];
   int bs[4];
@@ -523,36 +539,37 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
     k[q] = __ldg(rq.fast_tab + c + q);
     bs[q] = (bias ? __ldg(bias + c + q) : 0) - in_zp * wall[q];
   }
-  const int zp4 = (in_zp & 0xFF) * 0x01010101;
+  const unsigned zp4 = unsigned(in_zp & 0xFF) * 0x01010101u;
   const int ix0 = ox * STRIDE - g.pad_left;
   const bool vx0 = ix0 >= 0 && ix0 < g.IW, vx1 = ix0 + 1 >= 0 && ix0 + 1 < g.IW, vx2 = ix0 + 2 >= 0 && ix0 + 2 < g.IW;
   const int8_t* base = in + int64_t(blockIdx.z) * in_ts + int64_t(ix0) * C + c;
   const int64_t row_pitch = int64_t(g.IW) * C;
-  auto load_row = [&](int iy, int& a0, int& a1, int& a2) {
-    a0 = a1 = a2 = zp4;
+  auto load_raw = [&](int iy, unsigned (&a)[3]) {
+    a[0] = a[1] = a[2] = zp4;
     if (iy >= 0 && iy < g.IH) {
       const int8_t* p = base + int64_t(iy) * row_pitch;
-      if (vx0) a0 = *reinterpret_cast<const int*>(p);
-      if (vx1) a1 = *reinterpret_cast<const int*>(p + C);
-      if (vx2) a2 = *reinterpret_cast<const int*>(p + 2 * C);
+      if (vx0) a[0] = *reinterpret_cast<const unsigned*>(p);
+      if (vx1) a[1] = *reinterpret_cast<const unsigned*>(p + C);
+      if (vx2) a[2] = *reinterpret_cast<const unsigned*>(p + 2 * C);
     }
+  };
+  auto load_row = [&](int iy, unsigned (&t)[4]) {
+    unsigned a[3];
+    load_raw(iy, a);
+    transpose(a[0], a[1], a[2], t);
   };
   const int oy0 = blockIdx.y * rows_per_block, oy1 = min(g.OH, oy0 + rows_per_block);
   int iy = oy0 * STRIDE - g.pad_top;
   int8_t* op = out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c;
   const int64_t ostep = int64_t(g.OW) * C;
-  // one output word from three window rows
-  auto emit = [&](const int (&ra)[3], const int (&rb)[3], const int (&rc)[3], int8_t* dst) {
+  // one output word from three transposed window rows
+  auto emit = [&](const unsigned (&ra)[4], const unsigned (&rb)[4], const unsigned (&rc)[4], int8_t* dst) {
     int o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      int a = bs[q];
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        a = __dp4a(ra[f], wm[f][q], a);
-        a = __dp4a(rb[f], wm[3 + f][q], a);
-        a = __dp4a(rc[f], wm[6 + f][q], a);
-      }
+      int a = __dp4a(int(ra[q]), int(wt[0][q]), bs[q]);
+      a = __dp4a(int(rb[q]), int(wt[1][q]), a);
+      a = __dp4a(int(rc[q]), int(wt[2][q]), a);
       o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
     }
     unsigned packed;
@@ -569,41 +586,46 @@ __global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const in
   };
   pdl_wait();  // filters / requantisation constants are in registers; the activations come next
   if (STRIDE == 1) {
-    // four register rows rotate through the roles (top, middle, bottom, prefetch): the loop is unrolled by four so the
-    // rotation is pure renaming, and the next row's loads are issued before the current row's arithmetic
-    int ra[3], rb[3], rc[3], rd[3];
-    load_row(iy, ra[0], ra[1], ra[2]);
-    load_row(iy + 1, rb[0], rb[1], rb[2]);
-    load_row(iy + 2, rc[0], rc[1], rc[2]);
+    // four register rows rotate through the roles (top, middle, bottom, incoming): the loop is unrolled by four so the
+    // rotation is pure renaming; the next row's loads are issued before the current row's arithmetic and transposed after
+    unsigned ra[4], rb[4], rc[4], rd[4], nx[3];
+    load_row(iy, ra);
+    load_row(iy + 1, rb);
+    load_row(iy + 2, rc);
     for (int oy = oy0; oy < oy1; oy += 4, iy += 4, op += 4 * ostep) {
-      if (oy + 1 < oy1) load_row(iy + 3, rd[0], rd[1], rd[2]);
+      if (oy + 1 < oy1) load_raw(iy + 3, nx);
       emit(ra, rb, rc, op);
       if (oy + 1 >= oy1) break;
-      if (oy + 2 < oy1) load_row(iy + 4, ra[0], ra[1], ra[2]);
+      transpose(nx[0], nx[1], nx[2], rd);
+      if (oy + 2 < oy1) load_raw(iy + 4, nx);
       emit(rb, rc, rd, op + ostep);
       if (oy + 2 >= oy1) break;
-      if (oy + 3 < oy1) load_row(iy + 5, rb[0], rb[1], rb[2]);
+      transpose(nx[0], nx[1], nx[2], ra);
+      if (oy + 3 < oy1) load_raw(iy + 5, nx);
       emit(rc, rd, ra, op + 2 * ostep);
       if (oy + 3 >= oy1) break;
-      if (oy + 4 < oy1) load_row(iy + 6, rc[0], rc[1], rc[2]);
+      transpose(nx[0], nx[1], nx[2], rb);
+      if (oy + 4 < oy1) load_raw(iy + 6, nx);
       emit(rd, ra, rb, op + 3 * ostep);
+      if (oy + 4 < oy1) transpose(nx[0], nx[1], nx[2], rc);
     }
   } else {
-    int r0[3], r1[3], r2[3], n1[3], n2[3];
-    load_row(iy, r0[0], r0[1], r0[2]);
-    load_row(iy + 1, r1[0], r1[1], r1[2]);
-    load_row(iy + 2, r2[0], r2[1], r2[2]);
+    unsigned r0[4], r1[4], r2[4], n1[3], n2[3];
+    load_row(iy, r0);
+    load_row(iy + 1, r1);
+    load_row(iy + 2, r2);
     for (int oy = oy0; oy < oy1; ++oy, iy += STRIDE, op += ostep) {
-      if (oy + 1 < oy1) {
-        load_row(iy + 3, n1[0], n1[1], n1[2]);
-        load_row(iy + 4, n2[0], n2[1], n2[2]);
+      const bool more = oy + 1 < oy1;
+      if (more) {
+        load_raw(iy + 3, n1);
+        load_raw(iy + 4, n2);
       }
       emit(r0, r1, r2, op);
+      if (more) {
 #pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        r0[f] = r2[f];
-        r1[f] = n1[f];
-        r2[f] = n2[f];
+        for (int q = 0; q < 4; ++q) r0[q] = r2[q];
+        transpose(n1[0], n1[1], n1[2], r1);
+        transpose(n2[0], n2[1], n2[2], r2);
       }
     }
   }
