@@ -784,27 +784,39 @@ __global__ void __launch_bounds__(256) resize16_kernel(const int8_t* __restrict_
     int iy, y0, y1, ix, x0, x1;
     resize_axis(y, hs, IH, half_pixel, &iy, &y0, &y1);
     resize_axis(x, ws, IW, half_pixel, &ix, &x0, &x1);
-    // the four weights are < 2^20 and |pixel| <= 128, so the 4-term sum fits comfortably in int32
+    // o20 = sum of the four corners x (wy * wx), weights < 2^20, |pixel| <= 128: fits int32.  Factored exactly as
+    // wy0 * (wx0 a + wx1 d) + wy1 * (wx0 b + wx1 e); the inner sums are dp2a over (a, d) / (b, e) byte pairs interleaved
+    // with one PRMT per two channels - 9 instructions per channel instead of 16 byte-extract / IMAD ones.
     const int wy1 = iy - (1 << 10) * y0, wy0 = (1 << 10) - wy1;
     const int wx1 = ix - (1 << 10) * x0, wx0 = (1 << 10) - wx1;
-    const int w00 = wy0 * wx0, w10 = wy1 * wx0, w01 = wy0 * wx1, w11 = wy1 * wx1;
-    const int4 p00 = *reinterpret_cast<const int4*>(tin + (int64_t(y0) * IW + x0) * C + c);
-    const int4 p10 = *reinterpret_cast<const int4*>(tin + (int64_t(y1) * IW + x0) * C + c);
-    const int4 p01 = *reinterpret_cast<const int4*>(tin + (int64_t(y0) * IW + x1) * C + c);
-    const int4 p11 = *reinterpret_cast<const int4*>(tin + (int64_t(y1) * IW + x1) * C + c);
-    const int8_t* a = reinterpret_cast<const int8_t*>(&p00);
-    const int8_t* b = reinterpret_cast<const int8_t*>(&p10);
-    const int8_t* d = reinterpret_cast<const int8_t*>(&p01);
-    const int8_t* e = reinterpret_cast<const int8_t*>(&p11);
-    int4 o;
-    int8_t* ob = reinterpret_cast<int8_t*>(&o);
+    const unsigned wx = (unsigned(wx1) << 16) | unsigned(wx0);  // two 16-bit weights (<= 1024)
+    const uint4 p00 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0) * IW + x0) * C + c);
+    const uint4 p10 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1) * IW + x0) * C + c);
+    const uint4 p01 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0) * IW + x1) * C + c);
+    const uint4 p11 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1) * IW + x1) * C + c);
+    const unsigned ta[4] = {p00.x, p00.y, p00.z, p00.w}, td[4] = {p01.x, p01.y, p01.z, p01.w};
+    const unsigned tb[4] = {p10.x, p10.y, p10.z, p10.w}, te[4] = {p11.x, p11.y, p11.z, p11.w};
+    unsigned ow[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int o20 = int(a[j]) * w00 + int(b[j]) * w10 + int(d[j]) * w01 + int(e[j]) * w11;
-      const int rnd = o20 > 0 ? (1 << 19) : -(1 << 19);
-      ob[j] = int8_t((o20 + rnd) / (1 << 20));
+    for (int wd = 0; wd < 4; ++wd) {
+      int q[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const unsigned sel = hf ? 0x7362u : 0x5140u;            // bytes {a_j, d_j, a_j+1, d_j+1} of channels 2 hf, 2 hf + 1
+        const unsigned ad = __byte_perm(ta[wd], td[wd], sel), be = __byte_perm(tb[wd], te[wd], sel);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ht = u ? __dp2a_hi(int(wx), int(ad), 0) : __dp2a_lo(int(wx), int(ad), 0);
+          const int hb = u ? __dp2a_hi(int(wx), int(be), 0) : __dp2a_lo(int(wx), int(be), 0);
+          const int o20 = wy0 * ht + wy1 * hb;
+          // (o20 + (o20 > 0 ? 2^19 : -2^19)) / 2^20 truncating == floor((o20 + 2^19 + (o20 < 0 ? -1 : 0)) / 2^20)
+          q[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+        }
+      }
+      ow[wd] = (unsigned(q[0]) & 0xFFu) | ((unsigned(q[1]) & 0xFFu) << 8) | ((unsigned(q[2]) & 0xFFu) << 16) | (unsigned(q[3]) << 24);
     }
-    *reinterpret_cast<int4*>(out + int64_t(t) * out_ts + (int64_t(y) * OW + x) * C + c) = o;
+    const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    *reinterpret_cast<uint4*>(out + int64_t(t) * out_ts + (int64_t(y) * OW + x) * C + c) = o;
   }
 }
 
