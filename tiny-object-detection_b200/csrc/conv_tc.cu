@@ -993,9 +993,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int fy = tap / p.KW, fx = tap - fy * p.KW;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
-            if (rank == 0) mbar_expect_tx(&ctl->full[stage], 2u * p.tx_bytes);  // both CTAs' A tile + weight half
+            const bool skip_b = (p.dbg & 64) != 0, skip_a = (p.dbg & 128) != 0;  // timing experiments: operand traffic of one side only
+            if (rank == 0) mbar_expect_tx(&ctl->full[stage], 2u * (p.tx_bytes - (skip_b ? half_bn * uint32_t(p.BK) : 0u) - (skip_a ? uint32_t(p.rows * p.BK) : 0u)));  // both CTAs' A tile + weight half
+            if (!skip_a)
             tma_load_4d_pair(smem_a + size_t(stage) * p.a_stage, &map_a, &ctl->full[stage], kc * p.BK, x0 * p.stride + fx - p.pad_left,
                              y0 * p.stride + fy - p.pad_top, n0);
+            if (!skip_b)
             tma_load_3d_pair(smem_b + size_t(stage) * p.b_stage, &map_bh, &ctl->full[stage], kc * p.BK, tap, n_tile * p.BN + int(rank * half_bn));
             if (++stage == p.stages) {
               stage = 0;
