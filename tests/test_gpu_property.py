@@ -66,3 +66,53 @@ def test_scene_random_frames(tod, w, h, n, seed, weights_mode, sample_shift):
         assert np.array_equal(got["conn1"][f].view(np.uint32), c1.view(np.uint32))
         assert np.array_equal(got["conn0"][f].view(np.uint32), c0.view(np.uint32))
         np.testing.assert_allclose(got["balls"][f], balls, rtol=1e-5, atol=0)
+
+
+def _micro_graph(S, c0, expand, dw_stride, oc, seed):
+    """input -> QUANTIZE -> 3x3 s2 stem -> 1x1 expand -> (PAD +) depthwise -> 1x1 project -> RESIZE 2x -> 3x3 conv: the CUDA-core
+    kernels (stem, depthwise, resize) and the tcgen05 convolutions around them on shapes the FRC graph does not have."""
+    from oracle import synth_model as sm
+    calib = sm.calib_images()[:, :S, :S]
+    g = sm.Graph(seed, calib)
+    x = g.input_u8([1, S, S, 3], float(sm.f32(1.0 / 128.0)), 128)
+    x = g.quantize(x, float(sm.f32(1.0 / 128.0)), 0, sm.T_INT8, "input_int8")
+    x = g.pad(x, ((0, 1), (0, 1)), "stem_pad")
+    x = g.conv(x, c0, 3, 2, sm.PAD_VALID, sm.ACT_RELU6, "stem", gain=1.6)
+    h = g.conv(x, c0 * expand, 1, 1, sm.PAD_SAME, sm.ACT_RELU6, "expand", gain=1.6)
+    if dw_stride == 2:
+        h = g.pad(h, ((0, 1), (0, 1)), "dw_pad")
+        h = g.conv(h, 0, 3, 2, sm.PAD_VALID, sm.ACT_RELU6, "dw", gain=1.8, depthwise=True)
+    else:
+        h = g.conv(h, 0, 3, 1, sm.PAD_SAME, sm.ACT_RELU6, "dw", gain=1.8, depthwise=True)
+    h = g.conv(h, oc, 1, 1, sm.PAD_SAME, sm.ACT_NONE, "project", gain=0.9)
+    h = g.resize2x(h, "up")
+    h = g.conv(h, oc, 3, 1, sm.PAD_SAME, sm.ACT_RELU, "smooth", gain=1.4)
+    out = g.quantize(h, h.scale, h.zp + 128, sm.T_UINT8, "out")
+    return g.serialize([g.tensors[0]], [out], "tod-b200 property-test micro graph")
+
+
+@settings(max_examples=12, **COMMON)
+@given(S=st.sampled_from([16, 24, 30, 40, 58]), c0=st.sampled_from([8, 16, 32]), expand=st.sampled_from([1, 3, 6]), dw_stride=st.sampled_from([1, 2]),
+       oc=st.sampled_from([16, 32, 48]), seed=st.integers(1, 1000), fusion=st.sampled_from([0, 1]))
+def test_micro_graph_every_tensor(tod, tmp_path_factory, S, c0, expand, dw_stride, oc, seed, fusion):
+    blob = _micro_graph(S, c0, expand, dw_stride, oc, seed)
+    path = tmp_path_factory.mktemp("micro") / "g.tflite"
+    path.write_bytes(blob)
+    from tests import synth
+    tiles = synth.rgb_tiles(3, S=S, seed=seed)
+    y = tod.Yolact.init(str(path), max_tiles=3, fusion=fusion, use_cuda_graph=fusion)
+    res = y.infer_tiles(tiles, tile_classes=False, detections=False)
+    for t in range(3):
+        m = oracle.Model(str(path))
+        m.invoke(tiles[t], threads=4)
+        if fusion:
+            want = m.tensor(m.outputs[0])
+            assert np.array_equal(res["outputs"][0][t].reshape(-1), want.reshape(-1))
+        else:
+            for op in range(m.num_ops):
+                ti = m.op_output(op)
+                want = m.tensor(ti)
+                got = y.fetch_tensor(ti, 3)[t]
+                assert np.array_equal(got.reshape(-1), want.reshape(-1)), "tile %d op %d (code %d) differs in %d of %d" % (
+                    t, op, m.op_code(op), (got.reshape(-1) != want.reshape(-1)).sum(), want.size)
+    y.close()
