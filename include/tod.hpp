@@ -8,9 +8,13 @@
 //   tod::Yolact::classify(frame)       <- Yolact::classify(&mut [u32])        src/yolact.rs:39-41
 //   tod::append_scene(queues, scene)   <- append_scene(...)                   src/scene.rs:147-331
 //   tod::Scene                         <- struct Scene                        src/scene.rs:122-143
+//   tod::YolactPool                    (no counterpart: several batches in flight over the same C ABI)
 #pragma once
 #include <array>
 #include <cstdint>
+#include <future>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -56,6 +60,46 @@ class Yolact {
  private:
   Yolact() = default;
   tod_yolact* h_ = nullptr;
+};
+
+// Several batches in flight (the frame loop's double / triple buffering; the Python mirror is tod_b200.YolactPool): `depth`
+// handles take alternate batches, each call on its own host thread, so one batch's copies and latency-bound tail overlap the
+// next batch's backbone.  Every batch runs through one handle exactly as tod_yolact_infer_tiles would run it alone.
+class YolactPool {
+ public:
+  YolactPool(const char* model, int device, int max_tiles, int depth = 3) {
+    tod_yolact_options o;
+    tod_yolact_default_options(&o);
+    o.max_tiles = max_tiles;
+    for (int i = 0; i < (depth < 1 ? 1 : depth); ++i) {
+      slots_.emplace_back(new Slot());
+      expect(tod_yolact_create(model, device, &o, &slots_.back()->h), "YolactPool");
+    }
+  }
+  YolactPool(const YolactPool&) = delete;
+  ~YolactPool() {
+    for (auto& s : slots_) {
+      std::lock_guard<std::mutex> g(s->busy);  // wait for the batch in flight
+      tod_yolact_destroy(s->h);
+    }
+  }
+  // queues one batch of u8[n][th][tw][3] tiles; the future yields tod_yolact_infer_tiles' return code (throws tod::Error on failure)
+  std::future<int> submit(const uint8_t* rgb_tiles, int n, uint32_t* tile_classes, tod_detections* dets) {
+    Slot* s = slots_[next_++ % slots_.size()].get();
+    return std::async(std::launch::async, [=] {
+      std::lock_guard<std::mutex> g(s->busy);  // a handle runs one batch at a time
+      return expect(tod_yolact_infer_tiles(s->h, rgb_tiles, n, nullptr, tile_classes, dets), "YolactPool::submit");
+    });
+  }
+  size_t depth() const { return slots_.size(); }
+
+ private:
+  struct Slot {
+    tod_yolact* h = nullptr;
+    std::mutex busy;
+  };
+  std::vector<std::unique_ptr<Slot>> slots_;
+  size_t next_ = 0;
 };
 
 struct Scene {  // scene.rs:122-132
