@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
 constexpr int kDwThreads = 128;
 
 template <int STRIDE, bool SAT>
-__global__ void __launch_bounds__(kDwThreads) depthwise3x3_slide_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+__global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const int8_t* __restrict__ in, int64_t in_ts,
                                                                        const int8_t* __restrict__ w,
                                                                        const int32_t* __restrict__ bias, int32_t in_zp,
                                                                        ConvGeom g, Requant rq, int8_t* __restrict__ out,
