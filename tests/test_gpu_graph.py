@@ -120,3 +120,23 @@ def test_pool_matches_single_handle(tod, models):
             assert np.array_equal(dg["prior"], dw["prior"]) and np.array_equal(dg["cls"], dw["cls"])
             assert np.array_equal(dg["score"].view(np.uint32), dw["score"].view(np.uint32))
             assert np.array_equal(dg["masks_bits"], dw["masks_bits"])
+
+
+def test_trace_steps(tod, models):
+    """The diagnostics entry point: one entry per planned step plus the three post-processing stages, end times
+    non-negative and bounded by the step end, lanes inside the executor's lane range."""
+    _, small = models
+    tiles = synth.rgb_tiles(2, S=64, seed=5)
+    y = tod.Yolact.init(small, max_tiles=2)
+    y.infer_tiles(tiles, detections=False)
+    iso, kinds = y.profile_ops(2)
+    end, lanes, kinds2 = y.trace_steps(2)
+    assert len(end) == len(iso) + 3
+    assert np.array_equal(kinds, kinds2[:len(iso)])
+    assert (end[:len(iso)] > 0).all() and (lanes[:len(iso)] >= 0).all() and (lanes[:len(iso)] < 16).all()
+    assert end[len(iso)] > 0  # segmentation pass ran
+    # the class maps of a later normal call are unaffected by the traced (graph-less) run
+    a = y.infer_tiles(tiles, detections=False)["tile_classes"]
+    y2 = tod.Yolact.init(small, max_tiles=2)
+    b = y2.infer_tiles(tiles, detections=False)["tile_classes"]
+    assert np.array_equal(a, b)
