@@ -15,10 +15,13 @@ import oracle  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
+import os  # noqa: E402
+
+SCALE = max(1, int(os.environ.get("TOD_PROP_SCALE", "1")))  # TOD_PROP_SCALE=10: a ten times longer soak of the same properties
 COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow], derandomize=True)
 
 
-@settings(max_examples=40, **COMMON)
+@settings(max_examples=40 * SCALE, **COMMON)
 @given(tiles=st.integers(1, 9), h=st.integers(1, 30), w=st.integers(1, 30), ic16=st.integers(1, 20), oc=st.integers(1, 300),
        k=st.sampled_from([1, 3]), flags=st.sampled_from([0, 1, 2, 3, 4, 16]))
 def test_conv_random_shapes(tod, tiles, h, w, ic16, oc, k, flags):
@@ -27,7 +30,7 @@ def test_conv_random_shapes(tod, tiles, h, w, ic16, oc, k, flags):
     assert bad == 0
 
 
-@settings(max_examples=15, **COMMON)
+@settings(max_examples=15 * SCALE, **COMMON)
 @given(tiles=st.integers(1, 40), hw=st.integers(2, 40), ic16=st.integers(1, 16), oc=st.integers(1, 260), flags=st.sampled_from([32, 33, 36]))
 def test_conv_stride2_random_shapes(tod, tiles, hw, ic16, oc, flags):
     from tod_b200 import _lib
@@ -35,7 +38,7 @@ def test_conv_stride2_random_shapes(tod, tiles, hw, ic16, oc, flags):
     assert bad == 0
 
 
-@settings(max_examples=10, **COMMON)
+@settings(max_examples=10 * SCALE, **COMMON)
 @given(tiles=st.integers(8, 40), hw=st.sampled_from([14, 20, 28]), ic128=st.integers(1, 3), oc32=st.integers(2, 8), flags=st.sampled_from([0, 1]))
 def test_conv_pair_random_shapes(tod, tiles, hw, ic128, oc32, flags):
     """Shapes inside the CTA-pair kernel's range (>= 8 K iterations; the M-tile count decides per case)."""
@@ -44,7 +47,17 @@ def test_conv_pair_random_shapes(tod, tiles, hw, ic128, oc32, flags):
     assert bad == 0
 
 
-@settings(max_examples=12, **COMMON)
+@settings(max_examples=16 * SCALE, **COMMON)
+@given(tiles=st.integers(40, 64), hw=st.integers(24, 60), ic16=st.integers(1, 16), oc=st.integers(1, 200), flags=st.sampled_from([0, 1, 2, 3]))
+def test_conv_flat_many_tiles(tod, tiles, hw, ic16, oc, flags):
+    """Dense 1x1 layers with more M tiles than SMs: the resident-weights path, the cp.async A producer (IC % 128 != 0), the
+    linear staging + 1-D bulk store (16-byte rows) and the run-staged stores (other rows), with ragged last tiles."""
+    from tod_b200 import _lib
+    ms_tc, ms_direct, bad = _lib.conv_selftest(tiles, hw, hw, 16 * ic16, oc, 1, iters=1, flags=flags)
+    assert bad == 0
+
+
+@settings(max_examples=12 * SCALE, **COMMON)
 @given(w=st.integers(34, 130), h=st.integers(24, 90), n=st.integers(1, 3), seed=st.integers(0, 10_000), weights_mode=st.sampled_from([0, 1]),
        sample_shift=st.sampled_from([0, 1]))
 def test_scene_random_frames(tod, w, h, n, seed, weights_mode, sample_shift):
@@ -91,7 +104,7 @@ def _micro_graph(S, c0, expand, dw_stride, oc, seed):
     return g.serialize([g.tensors[0]], [out], "tod-b200 property-test micro graph")
 
 
-@settings(max_examples=12, **COMMON)
+@settings(max_examples=12 * SCALE, **COMMON)
 @given(S=st.sampled_from([16, 24, 30, 40, 58]), c0=st.sampled_from([8, 16, 32]), expand=st.sampled_from([1, 3, 6]), dw_stride=st.sampled_from([1, 2]),
        oc=st.sampled_from([16, 32, 48]), seed=st.integers(1, 1000), fusion=st.sampled_from([0, 1]))
 def test_micro_graph_every_tensor(tod, tmp_path_factory, S, c0, expand, dw_stride, oc, seed, fusion):
