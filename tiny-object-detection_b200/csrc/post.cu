@@ -231,7 +231,14 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   const int np = min(kDecodeThreads, c.P - p0);
   for (int i = threadIdx.x; i < 256; i += kDecodeThreads) s_exp[i] = b.exp_diff[i];
   const uint8_t* src = cls + int64_t(t) * cls_ts + int64_t(p0) * c.C;
-  for (int i = threadIdx.x; i < np * c.C; i += kDecodeThreads) s_q[i] = src[i];
+  const int nbytes = np * c.C;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(s_q)) & 15) == 0) {  // the CTA's class bytes are one contiguous block
+    const int n16 = nbytes >> 4;
+    for (int i = threadIdx.x; i < n16; i += kDecodeThreads) reinterpret_cast<uint4*>(s_q)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (int i = (n16 << 4) + threadIdx.x; i < nbytes; i += kDecodeThreads) s_q[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += kDecodeThreads) s_q[i] = src[i];
+  }
   __syncthreads();
   const bool active = threadIdx.x < np;
   const int p = min(p0 + int(threadIdx.x), c.P - 1);
@@ -256,10 +263,19 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, Det
   auto passes = [&](float e) { return c.conf_thresh > 0.f ? (e > tu_hi ? true : (e < tu_lo ? false : __fdiv_rn(e, sum) > c.conf_thresh)) : __fdiv_rn(e, sum) > c.conf_thresh; };
   // pass 1: per-class candidate counts of this CTA (shared-memory atomics); the thread remembers its candidates as a
   // bit set (C <= 256), so the emit pass below only revisits those few classes
+  // `passes` is monotone in e and the table is monotone in its index, so the per-class test is a byte compare against the
+  // smallest passing table index (binary search, 8 probes) instead of 80 table look-ups and float tests
+  int lo = 0, hi = 256;  // smallest i in [0, 256) with passes(s_exp[i]); 256 if none
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (passes(s_exp[mid])) hi = mid;
+    else lo = mid + 1;
+  }
+  const int q_thr = lo + qmax - 255;  // class k is a candidate  <=>  q[k] >= q_thr
   unsigned cbits[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   if (active)
     for (int k = 1; k < c.C; ++k)
-      if (passes(s_exp[int(q[k]) - qmax + 255])) {
+      if (int(q[k]) >= q_thr) {
         atomicAdd(&s_cnt[k - 1], 1);
         cbits[k >> 5] |= 1u << (k & 31);
       }
