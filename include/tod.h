@@ -181,6 +181,9 @@ typedef struct tod_detections {
   uint8_t* masks_bin;     /* [n][max_dets][56][56]     > 0.5, may be NULL */
   uint32_t* masks_bits;   /* [n][max_dets][ceil(56*56/32)]  the same binary masks, 1 bit per prototype pixel (bit i of word
                              w = pixel 32*w + i): an eighth of the read-back of masks_bin; may be NULL */
+  uint32_t* masks_tile_bits; /* [n][max_dets][ceil(224*224/32)]  YOLACT postprocess: the cropped float masks resized to the tile
+                             (bilinear, align_corners = false) and thresholded at 0.5, 1 bit per tile pixel; may be NULL.
+                             Implies the float-mask computation; rows of detections >= count[tile] are zero. */
 } tod_detections;
 
 /* Runs the int8 graph on n RGB tiles u8[n][224][224][3] (== interpreter.invoke(), yolact.rs:161-163).

@@ -230,6 +230,33 @@ def detect(cls_q, cls_qp, box_q, box_qp, coef_q, coef_qp, proto_q, proto_qp, cfg
 
 
 # ------------------------------------------------------------------ tflite graph
+def upsample_masks(masks, out_h, out_w):
+    """YOLACT `postprocess` (layers/output_utils.py, not in the reference; north-star row 9): the cropped prototype-resolution
+    masks are resized to the tile with `F.interpolate(mode='bilinear', align_corners=False)` and thresholded at 0.5.
+    float32 arithmetic in PyTorch's order: src = max(scale * (dst + 0.5) - 0.5, 0), i0 = int(src), i1 = i0 + (i0 < in - 1),
+    l1 = src - i0, l0 = 1 - l1; v = h0 * (w0 * m[y0, x0] + w1 * m[y0, x1]) + h1 * (w0 * m[y1, x0] + w1 * m[y1, x1]).
+    Returns (float32 [N, out_h, out_w], uint8 same shape)."""
+    m = np.ascontiguousarray(masks, np.float32)
+    n, ih, iw = m.shape
+    f = np.float32
+
+    def axis(out, inn):
+        scale = f(inn) / f(out)
+        src = np.maximum(scale * (np.arange(out, dtype=np.float32) + f(0.5)) - f(0.5), f(0))
+        i0 = src.astype(np.int32)
+        i1 = i0 + (i0 < inn - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        l0 = (f(1) - l1).astype(np.float32)
+        return i0, i1, l0, l1
+
+    y0, y1, h0, h1 = axis(out_h, ih)
+    x0, x1, w0, w1 = axis(out_w, iw)
+    top = (w0[None, None, :] * m[:, y0][:, :, x0] + w1[None, None, :] * m[:, y0][:, :, x1]).astype(np.float32)
+    bot = (w0[None, None, :] * m[:, y1][:, :, x0] + w1[None, None, :] * m[:, y1][:, :, x1]).astype(np.float32)
+    up = (h0[None, :, None] * top + h1[None, :, None] * bot).astype(np.float32)
+    return up, (up > f(0.5)).astype(np.uint8)
+
+
 class Model:
     def __init__(self, path):
         self._h = lib().tod_oracle_model_load(os.fsencode(path))

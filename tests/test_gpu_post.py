@@ -130,6 +130,35 @@ def test_detection_full_vs_oracle(tod, models):
     assert total > 0, "synthetic model produced no detections; the test would be vacuous"
 
 
+def test_tile_resolution_masks(tod, models):
+    """Row 9's last step (YOLACT postprocess): cropped float masks resized to the tile (bilinear, align_corners = false) and
+    thresholded.  Resizing the library's own float masks with the oracle must give the identical bits (same float32 operation
+    order); against the oracle's masks the bar is the binary-mask one (IoU >= 0.999)."""
+    full, _ = models
+    tiles = synth.rgb_tiles(2, seed=44)
+    y = tod.Yolact.init(full, max_tiles=2)
+    res = y.infer_tiles(tiles, detections=True, tile_masks=True)
+    o = y.outputs
+    seen = 0
+    for t in range(2):
+        d = res["dets"][t]
+        if d["n"] == 0:
+            continue
+        got = np.unpackbits(d["masks_tile_bits"].view(np.uint8), axis=-1, bitorder="little")[:, :224 * 224].reshape(d["n"], 224, 224)
+        up, bits = oracle.upsample_masks(d["masks"], 224, 224)
+        assert np.array_equal(got, bits), "%d of %d tile pixels differ from the oracle resize of the same float masks" % ((got != bits).sum(), bits.size)
+        want = oracle.detect(res["outputs"][1][t], (o[1]["scale"], o[1]["zero_point"]), res["outputs"][0][t], (o[0]["scale"], o[0]["zero_point"]),
+                             res["outputs"][2][t], (o[2]["scale"], o[2]["zero_point"]), res["outputs"][3][t], (o[3]["scale"], o[3]["zero_point"]))
+        _, wbits = oracle.upsample_masks(want["masks"], 224, 224)
+        inter, union = np.logical_and(got, wbits).sum(), np.logical_or(got, wbits).sum()
+        assert union == 0 or inter / union >= 0.999
+        seen += d["n"]
+    assert seen > 0
+    # unused rows are zero; a binary-only call cannot deliver them
+    full_bits = y.infer_tiles(tiles, outputs=False, tile_classes=False, detections=True, tile_masks=True)
+    assert full_bits["dets"][0]["masks_tile_bits"].shape[1] == 224 * 224 // 32
+
+
 @pytest.mark.parametrize("conf,nms", [(0.05, 0.5), (0.01, 0.3), (0.2, 0.9)])
 def test_detection_small_thresholds(tod, models, conf, nms):
     _, small = models

@@ -1,4 +1,5 @@
 """Known answers for the detection oracle (YOLACT decode / Fast-NMS / masks; not in the reference: parity unpinned)."""
+import pytest
 import numpy as np
 
 import oracle
@@ -61,3 +62,18 @@ def test_thresholds_and_masks():
     ys, xs = np.nonzero(m)
     assert xs.min() == max(0, int(np.ceil(x1 - 1))) and ys.min() == max(0, int(np.ceil(y1 - 1)))
     assert m.sum() > 0 and (d["masks"][0][m == 1] > 0.5).all() and (d["masks"][0][m == 0] == 0).all()
+
+
+def test_upsample_masks_is_torch_interpolate():
+    """oracle.upsample_masks pins itself on the library YOLACT calls: F.interpolate(bilinear, align_corners=False) on CPU."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    m = rng.random((6, 56, 56)).astype(np.float32)
+    m[:, :10] = 0.0  # cropped regions are exact zeros
+    up, bits = oracle.upsample_masks(m, 224, 224)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(m)[None], (224, 224), mode="bilinear", align_corners=False)[0].numpy()
+    np.testing.assert_allclose(up, ref, rtol=0, atol=2.5e-7)
+    clear = np.abs(ref - 0.5) > 1e-6
+    assert np.array_equal(bits[clear], (ref > 0.5)[clear].astype(np.uint8))
+    up2, _ = oracle.upsample_masks(m[:, :7, :7], 7, 7)  # identity size: the source pixels come back exactly
+    assert np.array_equal(up2, m[:, :7, :7])

@@ -50,7 +50,8 @@ class YolactOptions(C.Structure):
 
 class Detections(C.Structure):
     _fields_ = [("max_dets", C.c_int32), ("count", C.c_void_p), ("boxes", C.c_void_p), ("scores", C.c_void_p),
-                ("classes", C.c_void_p), ("priors", C.c_void_p), ("masks", C.c_void_p), ("masks_bin", C.c_void_p), ("masks_bits", C.c_void_p)]
+                ("classes", C.c_void_p), ("priors", C.c_void_p), ("masks", C.c_void_p), ("masks_bin", C.c_void_p), ("masks_bits", C.c_void_p),
+                ("masks_tile_bits", C.c_void_p)]
 
 
 def build(force=False):

@@ -596,6 +596,35 @@ __global__ void __launch_bounds__(kMaskThreads) mask_kernel(DetectCfg c, DetectB
   }
 }
 
+// YOLACT `postprocess` (layers/output_utils.py; north-star row 9): the cropped prototype-resolution masks resized to the tile
+// with F.interpolate(mode='bilinear', align_corners=False) and thresholded at 0.5.  One thread per tile pixel, one ballot per 32
+// pixels -> bit-packed [tile][det][th*tw/32].  PyTorch's arithmetic order, no contraction: src = max(scale*(dst+0.5)-0.5, 0).
+__global__ void __launch_bounds__(256) mask_upsample_kernel(const float* __restrict__ masks, const int* __restrict__ det_count,
+                                                           int max_dets, int ph, int pw, int th, int tw,
+                                                           uint32_t* __restrict__ out_bits) {
+  const int t = blockIdx.z, d = blockIdx.y;
+  const int words = (th * tw + 31) >> 5;
+  const int px = blockIdx.x * 256 + threadIdx.x;
+  const bool in_range = px < th * tw;
+  bool on = false;
+  if (d < det_count[t] && in_range) {
+    const int y = px / tw, x = px - y * tw;
+    const float sy = __fdiv_rn(float(ph), float(th)), sx = __fdiv_rn(float(pw), float(tw));
+    const float fy = fmaxf(__fsub_rn(__fmul_rn(sy, __fadd_rn(float(y), 0.5f)), 0.5f), 0.f);
+    const float fx = fmaxf(__fsub_rn(__fmul_rn(sx, __fadd_rn(float(x), 0.5f)), 0.5f), 0.f);
+    const int y0 = int(fy), x0 = int(fx);
+    const int y1 = y0 + (y0 < ph - 1 ? 1 : 0), x1 = x0 + (x0 < pw - 1 ? 1 : 0);
+    const float h1 = __fsub_rn(fy, float(y0)), h0 = __fsub_rn(1.f, h1);
+    const float w1 = __fsub_rn(fx, float(x0)), w0 = __fsub_rn(1.f, w1);
+    const float* m = masks + (int64_t(t) * max_dets + d) * ph * pw;
+    const float top = __fadd_rn(__fmul_rn(w0, m[y0 * pw + x0]), __fmul_rn(w1, m[y0 * pw + x1]));
+    const float bot = __fadd_rn(__fmul_rn(w0, m[y1 * pw + x0]), __fmul_rn(w1, m[y1 * pw + x1]));
+    on = __fadd_rn(__fmul_rn(h0, top), __fmul_rn(h1, bot)) > 0.5f;
+  }
+  const unsigned bits = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && (px >> 5) < words) out_bits[(int64_t(t) * max_dets + d) * words + (px >> 5)] = bits;
+}
+
 inline int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -674,6 +703,13 @@ int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_
                         int64_t proto_ts, int tiles, cudaStream_t s) {
   dim3 g4((c.ph * c.pw + kMaskThreads - 1) / kMaskThreads, tiles);
   mask_kernel<32><<<g4, kMaskThreads, mask_smem(c), s>>>(c, b, coef, coef_ts, proto, proto_ts);
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+int launch_mask_upsample(const DetectCfg& c, const DetectBuffers& b, int tiles, int th, int tw, uint32_t* out_bits, cudaStream_t s) {
+  dim3 g((th * tw + 255) / 256, c.max_dets, tiles);
+  mask_upsample_kernel<<<g, 256, 0, s>>>(b.masks, b.det_count, c.max_dets, c.ph, c.pw, th, tw, out_bits);
   TOD_CUDA(cudaGetLastError());
   return TOD_OK;
 }

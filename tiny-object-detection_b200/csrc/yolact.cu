@@ -155,6 +155,7 @@ struct tod_yolact {
   int tc_layers = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // early read-back of the tile class maps while detection still runs
+  uint32_t* d_tile_bits = nullptr;      // [max_tiles][max_dets][th*tw/32], allocated on the first request for tile-resolution masks
   cudaStream_t nms_stream = nullptr;    // the worst-case Fast-NMS launch runs beside the common-case one
   cudaEvent_t nms_fork = nullptr, nms_join = nullptr;
   cudaEvent_t seg_ready = nullptr;      // recorded (as an external event node) inside the graph right after seg_post_kernel
@@ -1332,7 +1333,7 @@ void tod_yolact_destroy(tod_yolact* y) {
     cudaFree(t->d_left); cudaFree(t->d_count); cudaFree(t->d_weight);
   }
   cudaFree(y->d_tmp); cudaFree(y->d_frames); cudaFree(y->d_tiles_rgb);
-  cudaFree(y->d_tile_classes); cudaFree(y->d_diverges);
+  cudaFree(y->d_tile_classes); cudaFree(y->d_diverges); cudaFree(y->d_tile_bits);
   if (y->h_diverges) cudaFreeHost(y->h_diverges);
   cudaFree(y->d_const); cudaFree(y->d_act);
   if (y->copy_stream) cudaStreamDestroy(y->copy_stream);
@@ -1520,6 +1521,13 @@ int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
   if (d->masks_bits && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
   if (d->masks_bits) TOD_CUDA(cudaMemcpyAsync(d->masks_bits, b.masks_bits, nd * size_t((c.ph * c.pw + 31) / 32) * 4, cudaMemcpyDeviceToHost, s));
   if (d->masks_bin) TOD_CUDA(cudaMemcpyAsync(d->masks_bin, b.masks_bin, nd * c.ph * c.pw, cudaMemcpyDeviceToHost, s));
+  if (d->masks_tile_bits) {
+    if (y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: tile-resolution masks need the float masks of the last call");
+    const size_t words = size_t(y->tile_h() * y->tile_w() + 31) / 32;
+    if (!y->d_tile_bits) TOD_CUDA(cudaMalloc(&y->d_tile_bits, size_t(y->opt.max_tiles) * c.max_dets * words * 4));
+    TOD_TRY(launch_mask_upsample(c, b, n, y->tile_h(), y->tile_w(), y->d_tile_bits, s));
+    TOD_CUDA(cudaMemcpyAsync(d->masks_tile_bits, y->d_tile_bits, nd * words * 4, cudaMemcpyDeviceToHost, s));
+  }
   TOD_CUDA(cudaStreamSynchronize(s));
   return TOD_OK;
 }
@@ -1535,7 +1543,7 @@ int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8
   // yolact.rs:161-162 copy_from_slice into the input tensor
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n), cudaMemcpyHostToDevice, s));
   const bool want_dets = dets != nullptr;
-  const int mask_mode = !want_dets ? 0 : (dets->masks ? 2 : ((dets->masks_bin || dets->masks_bits) ? 1 : 0));
+  const int mask_mode = !want_dets ? 0 : ((dets->masks || dets->masks_tile_bits) ? 2 : ((dets->masks_bin || dets->masks_bits) ? 1 : 0));
   y->last_mask_mode = mask_mode;
   TOD_TRY(run_pipeline(y, n, want_dets, mask_mode, s));
   if (outputs_u8)

@@ -91,7 +91,7 @@ class Yolact:
         check(lib().tod_yolact_classify_batch_device(self._h, d_frames_ptr, n, width, height, d_target_ptr, stream))
 
     # ------------------------------------------------------------------ batched tile inference
-    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True, float_masks=True):
+    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True, float_masks=True, tile_masks=False):
         """tiles: u8[n, th, tw, 3].  Returns dict(outputs=[u8 arrays], tile_classes=u32[n,th,tw], dets=..., diverged=bool)."""
         tiles = np.ascontiguousarray(tiles, np.uint8)
         n, th, tw = tiles.shape[0], tiles.shape[1], tiles.shape[2]
@@ -103,7 +103,7 @@ class Yolact:
         tc = np.zeros((n, th, tw), np.uint32) if tile_classes else None
         det, keep = (None, None)
         if detections:
-            det, keep = self._alloc_dets(n, masks)
+            det, keep = self._alloc_dets(n, masks, tile_hw=(th, tw) if tile_masks else None)
             if not float_masks:  # binary masks only: the library then skips the sigmoid (sign of the integer logit)
                 det.masks = None
                 keep["masks"] = None
@@ -172,16 +172,17 @@ class Yolact:
         sp = [o["shape"] for i, o in enumerate(self.outputs) if o["shape"][1] > 1 and i != 4]
         return (sp[0][1], sp[0][2]) if sp else (56, 56)
 
-    def _alloc_dets(self, n, masks):
+    def _alloc_dets(self, n, masks, tile_hw=None):
         md = self.options.max_dets
         ph, pw = self._proto_hw()
         keep = dict(count=np.zeros(n, np.int32), boxes=np.zeros((n, md, 4), np.float32), scores=np.zeros((n, md), np.float32),
                     classes=np.zeros((n, md), np.int32), priors=np.zeros((n, md), np.int32),
                     masks=np.zeros((n, md, ph, pw), np.float32) if masks else None,
                     masks_bin=np.zeros((n, md, ph, pw), np.uint8) if masks else None,
-                    masks_bits=np.zeros((n, md, (ph * pw + 31) // 32), np.uint32) if masks else None)
+                    masks_bits=np.zeros((n, md, (ph * pw + 31) // 32), np.uint32) if masks else None,
+                    masks_tile_bits=np.zeros((n, md, (tile_hw[0] * tile_hw[1] + 31) // 32), np.uint32) if (masks and tile_hw) else None)
         det = Detections(md, *[keep[k].ctypes.data if keep[k] is not None else None
-                               for k in ("count", "boxes", "scores", "classes", "priors", "masks", "masks_bin", "masks_bits")])
+                               for k in ("count", "boxes", "scores", "classes", "priors", "masks", "masks_bin", "masks_bits", "masks_tile_bits")])
         return det, keep
 
     @staticmethod
@@ -193,7 +194,8 @@ class Yolact:
                             prior=keep["priors"][t, :c],
                             masks=keep["masks"][t, :c] if keep["masks"] is not None else None,
                             masks_bin=keep["masks_bin"][t, :c] if keep["masks_bin"] is not None else None,
-                            masks_bits=keep["masks_bits"][t, :c] if keep.get("masks_bits") is not None else None))
+                            masks_bits=keep["masks_bits"][t, :c] if keep.get("masks_bits") is not None else None,
+                            masks_tile_bits=keep["masks_tile_bits"][t, :c] if keep.get("masks_tile_bits") is not None else None))
         return out
 
 
