@@ -194,6 +194,10 @@ typedef struct tod_detections {
 int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8,
                            uint32_t* tile_classes, tod_detections* dets);
 
+/* Output k of the last call dequantised on the GPU exactly as the reference does for its `results: Vec<Vec<f32>>`
+ * (yolact.rs:169-188): out[t][e] = scale * ((u8 as i32 - zero_point) as f32), f32[n][elems_k]. */
+int tod_yolact_fetch_output_f32(tod_yolact* y, int index, int n, float* out);
+
 /* Device-resident form used by the fused RGB-D pipeline and the benchmark: input tiles already on the GPU;
  * results stay on the GPU (fetch with tod_yolact_fetch_*).  Asynchronous on `stream`. */
 int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int n, void* stream);

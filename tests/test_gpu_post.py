@@ -190,3 +190,15 @@ def test_binary_only_masks_match(tod, models):
         assert np.array_equal(da["masks_bin"], db["masks_bin"])
         assert np.array_equal(da["masks_bits"], db["masks_bits"])
         assert np.array_equal(da["masks_bin"], (da["masks"] > 0.5).astype(np.uint8))
+
+
+def test_output_dequantisation(tod, models):
+    """SURVEY 8a row 6 (yolact.rs:169-188): every output dequantised as scale * ((u8 - zp) as f32), bit for bit."""
+    full, _ = models
+    tiles = synth.rgb_tiles(2, seed=46)
+    y = tod.Yolact.init(full, max_tiles=2)
+    res = y.infer_tiles(tiles, detections=False)
+    for k, info in enumerate(y.outputs):
+        got = y.fetch_output_f32(k, 2)
+        want = oracle.dequant_u8(res["outputs"][k], info["scale"], info["zero_point"])
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), "output %d" % k

@@ -25,7 +25,7 @@ SYMBOLS = [
     "tod_yolact_num_ops", "tod_yolact_tensor_info", "tod_yolact_infer_tiles", "tod_yolact_infer_tiles_device",
     "tod_yolact_fetch_output", "tod_yolact_fetch_tensor", "tod_yolact_fetch_tile_classes", "tod_yolact_fetch_detections",
     "tod_yolact_stats", "tod_yolact_profile_ops", "tod_i8_gemm_selftest", "tod_conv_selftest",
-    "tod_conv_selftest_ex", "tod_i8_mma_peak", "tod_yolact_step_macs", "tod_yolact_trace_steps",
+    "tod_conv_selftest_ex", "tod_i8_mma_peak", "tod_yolact_step_macs", "tod_yolact_trace_steps", "tod_yolact_fetch_output_f32",
 ]
 
 
@@ -106,6 +106,7 @@ def lib():
         L.tod_i8_mma_peak.argtypes = [C.c_int, C.c_int, C.c_int, vp]
         L.tod_yolact_step_macs.argtypes = [vp, vp, C.c_int]
         L.tod_yolact_trace_steps.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
+        L.tod_yolact_fetch_output_f32.argtypes = [vp, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 

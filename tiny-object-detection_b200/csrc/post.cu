@@ -707,6 +707,28 @@ int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_
   return TOD_OK;
 }
 
+namespace {
+// yolact.rs:179-186: f32 = scale * ((u8 as i32 - zero_point) as f32), element by element (c_store > c: channel-padded storage)
+__global__ void __launch_bounds__(256) dequant_u8_kernel(const uint8_t* __restrict__ in, int64_t tile_stride, int c, int c_store,
+                                                        int64_t elems, float scale, int zp, float* __restrict__ out) {
+  const uint8_t* tin = in + int64_t(blockIdx.y) * tile_stride;
+  float* tout = out + int64_t(blockIdx.y) * elems;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < elems; i += int64_t(gridDim.x) * 256) {
+    const int64_t px = i / c;
+    const int ch = int(i - px * c);
+    tout[i] = __fmul_rn(scale, float(int(tin[px * c_store + ch]) - zp));
+  }
+}
+}  // namespace
+
+int launch_dequant_u8(const uint8_t* in, int64_t tile_stride, int c, int c_store, int64_t elems, int tiles, float scale, int zp,
+                      float* out, cudaStream_t s) {
+  dim3 g(unsigned(std::min<int64_t>((elems + 255) / 256, 1024)), tiles);
+  dequant_u8_kernel<<<g, 256, 0, s>>>(in, tile_stride, c, c_store, elems, scale, zp, out);
+  TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
 int launch_mask_upsample(const DetectCfg& c, const DetectBuffers& b, int tiles, int th, int tw, uint32_t* out_bits, cudaStream_t s) {
   dim3 g((th * tw + 255) / 256, c.max_dets, tiles);
   mask_upsample_kernel<<<g, 256, 0, s>>>(b.masks, b.det_count, c.max_dets, c.ph, c.pw, th, tw, out_bits);

@@ -75,6 +75,9 @@ int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_
                         int64_t box_ts, int tiles, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto,
                         int64_t proto_ts, int tiles, cudaStream_t s);
+// output dequantisation (yolact.rs:179-186) of `tiles` u8 tensors of `elems` elements each into float [tiles][elems]
+int launch_dequant_u8(const uint8_t* in, int64_t tile_stride, int c, int c_store, int64_t elems, int tiles, float scale, int zp,
+                      float* out, cudaStream_t s);
 // bilinear resize (PyTorch align_corners = false) of the cropped float masks to th x tw, > 0.5, bit-packed [tiles][max_dets][th*tw/32]
 int launch_mask_upsample(const DetectCfg& c, const DetectBuffers& b, int tiles, int th, int tw, uint32_t* out_bits, cudaStream_t s);
 size_t detect_select_smem(const DetectCfg& c);

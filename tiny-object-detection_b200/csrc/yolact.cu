@@ -1457,6 +1457,24 @@ int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out) {
   return TOD_OK;
 }
 
+int tod_yolact_fetch_output_f32(tod_yolact* y, int index, int n, float* out) {
+  if (!y || !out || index < 0 || index >= int(y->graph.outputs.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_output_f32: bad argument");
+  if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_output_f32: n=%d but the last call ran %d tiles", n, y->last_tiles);
+  const GTensor& T = y->T(y->graph.outputs[index]);
+  if (T.type != kU8) return fail(TOD_ERR_UNSUPPORTED, "tod_yolact_fetch_output_f32: output %d is not uint8", index);
+  const Place& p = y->place[y->graph.outputs[index]];
+  const int c = p.c_store > 0 ? p.c : 1, c_store = p.c_store > 0 ? p.c_store : 1;
+  const int64_t elems = p.c_store > 0 ? p.bytes / p.c_store * p.c : p.bytes;
+  TOD_CUDA(cudaSetDevice(y->device));
+  float* d_f = nullptr;
+  TOD_CUDA(cudaMalloc(&d_f, size_t(n) * elems * 4));
+  int rc = launch_dequant_u8(p.base, p.tile_stride, c, c_store, elems, n, T.scale(), T.zp(), d_f, y->stream);
+  if (rc == TOD_OK && cudaMemcpyAsync(out, d_f, size_t(n) * elems * 4, cudaMemcpyDeviceToHost, y->stream) != cudaSuccess) rc = fail(TOD_ERR_CUDA, "tod_yolact_fetch_output_f32: copy failed");
+  if (cudaStreamSynchronize(y->stream) != cudaSuccess && rc == TOD_OK) rc = fail(TOD_ERR_CUDA, "tod_yolact_fetch_output_f32: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_f);
+  return rc;
+}
+
 int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t out_bytes) {
   if (!y || !out || tensor < 0 || tensor >= int(y->graph.tensors.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: bad argument");
   if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_tensor: n=%d but the last call ran %d tiles", n, y->last_tiles);

@@ -124,6 +124,12 @@ class Yolact:
         check(lib().tod_yolact_fetch_output(self._h, index, n, _ptr(out)))
         return out
 
+    def fetch_output_f32(self, index, n):
+        """The reference's dequantised `results[index]` (yolact.rs:169-188), computed on the GPU."""
+        out = np.zeros((n,) + self.outputs[index]["shape"][1:], np.float32)
+        check(lib().tod_yolact_fetch_output_f32(self._h, index, n, _ptr(out)))
+        return out
+
     def fetch_tensor(self, t, n):
         info = self.tensor_info(t)
         dt = {0: np.float32, 2: np.int32, 3: np.uint8, 9: np.int8}[info["type"]]
