@@ -445,6 +445,17 @@ def main():
             t0 = time.perf_counter()
             m.invoke(tl[0], threads=th)
             line["cpu_baseline"]["frames_per_sec_%d_threads" % th] = 1.0 / TILES_PER_FRAME / (time.perf_counter() - t0)
+        # the point-cloud half of the path (pt_cloud.comp + pt_cloud_weights.comp restated in oracle/, one thread): SURVEY 8d
+        if "scene" in line and "error" not in line["scene"]:
+            dfr = synth.depth_frames(3, seed=3)
+            tfr = np.zeros_like(dfr)
+            op = oracle.scene_params()
+            t0 = time.perf_counter()
+            for f in range(3):
+                mp, _ = oracle.pt_cloud(dfr[f], tfr[f], op)
+                oracle.pt_cloud_weights(mp, op)
+            line["scene"]["cpu_baseline_frames_per_sec"] = 3.0 / (time.perf_counter() - t0)
+            line["scene"]["cpu_baseline_note"] = "oracle port of both shaders, 640x480, 1 host thread, 3 frames"
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
