@@ -354,6 +354,19 @@ def main():
         "tiles_per_sec": value * TILES_PER_FRAME,
     }
 
+    # ---- detection tail (decode / Fast-NMS / top-k / mask assembly): HBM-side figure of BASELINE's metric.  Timed on the lane
+    # streams without the graph (tod_yolact_trace_steps): from the end of the last graph layer to the end of mask assembly.
+    try:
+        t_end, _, _ = y.trace_steps(n)
+        ns_steps = len(ms_ops)
+        tail_ms = float(t_end[-1] - t_end[:ns_steps].max())
+        det_bytes = n * (3147 * (81 + 4 + 32) + 56 * 56 * 32) + n * 100 * 56 * 56 * (4 + 1) + n * 100 * (56 * 56 // 8)  # heads + prototypes in; float + byte + bit masks out
+        line["detection_tail"] = {"ms": tail_ms, "algorithmic_bytes": int(det_bytes), "GBps": det_bytes / (tail_ms * 1e-3) / 1e9,
+                                  "frac_of_hbm": det_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm"],
+                                  "note": "decode + Fast-NMS + top-k + mask assembly after the last graph layer, stream-ordered (no graph); instruction-bound, see DESIGN 5.3"}
+    except Exception as e:
+        line["detection_tail"] = {"error": str(e)[:200]}
+
     # ---- scene path (configs[2]): depth -> point cloud + weights, HBM-bound streaming + shared-memory stamp
     if not args.no_scene and rank == 0:
         nb = SCENE_BATCH
