@@ -490,7 +490,9 @@ __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles
   return w;
 }
 
-template <uint32_t MODE>
+// DIAG = true compiles in the clock64 stamps (TOD_TC_TRACE) and the timing-experiment switches (TOD_TC_DBG); the production
+// instantiations carry neither (predicated-off stamps inside the chunk loop alone were measurable).
+template <uint32_t MODE, bool DIAG = false>
 __global__ void __launch_bounds__(kFastThreads, 1)
 conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
@@ -607,7 +609,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int fy = tap / p.KW, fx = tap - fy * p.KW;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
-            if (p.dbg & 4) {  // timing experiment: no operand traffic at all
+            if (DIAG && (p.dbg & 4)) {  // timing experiment: no operand traffic at all
               mbar_arrive(&ctl->full[stage]);
             } else {
             mbar_expect_tx(&ctl->full[stage], p.tx_bytes);
@@ -702,8 +704,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if ((it & (kAccStages - 1)) != grp) continue;
       const int as = grp;
       const uint32_t use = uint32_t(it) / uint32_t(kAccStages);
-      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128 && use < 32;
-#define TOD_TR(slot) do { if (tr) p.trace[use * 16 + (slot)] = clock64(); } while (0)
+      const bool tr = DIAG && p.trace && blockIdx.x == 0 && threadIdx.x == 128 && use < 32;
+#define TOD_TR(slot) do { if (DIAG && tr) p.trace[use * 16 + (slot)] = clock64(); } while (0)
       TOD_TR(0);
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
       const int x = w.tx * p.pw + wx, yy = w.ty * p.ph + wy, n = w.g * p.pn + wn;
@@ -752,7 +754,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       TOD_TR(2);
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * acc_stride;
-      if (p.dbg & 8) {  // timing experiment: no epilogue work, hand the accumulator straight back
+      if (DIAG && (p.dbg & 8)) {  // timing experiment: no epilogue work, hand the accumulator straight back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
@@ -833,7 +835,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           TOD_TR(7);
           asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
           TOD_TR(8);
-          if (eg == 0 && !(p.dbg & 1)) {
+          if (eg == 0 && !(DIAG && (p.dbg & 1))) {
             if (p.lin) {  // the tile's rows are one contiguous block: a single 1-D bulk store instead of 128 box rows
               const long long row0 = (long long)w.tx * kBM;
               bulk_store_1d(p.out + row0 * p.OC, sbuf, uint32_t(min((long long)kBM, (long long)Wd - row0)) * uint32_t(p.OC));
@@ -1594,6 +1596,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
                              (const void*)conv_tc_fast_kernel<3>, (const void*)conv_tc_fast_kernel<4>, (const void*)conv_tc_fast_kernel<5>,
                              (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>,
                              (const void*)conv_tc_fast_kernel<12>, (const void*)conv_tc_fast_kernel<13>,
+                             (const void*)conv_tc_fast_kernel<3, true>, (const void*)conv_tc_fast_kernel<5, true>,
                              (const void*)conv_tc_pair_kernel<4>, (const void*)conv_tc_pair_kernel<5>};
     for (const void* k : kernels) {
       ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1632,6 +1635,12 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   if (!c->fast) {
     TOD_CUDA(launch_k(conv_tc_kernel, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, p, tiles));
   } else {
+    if ((p.trace || p.dbg) && (c->mode == 3 || c->mode == 5)) {  // diagnostics builds of the two most common epilogues
+      if (c->mode == 3) TOD_CUDA(launch_k(conv_tc_fast_kernel<3, true>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles));
+      else TOD_CUDA(launch_k(conv_tc_fast_kernel<5, true>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles));
+      TOD_CUDA(cudaGetLastError());
+      return TOD_OK;
+    }
     switch (c->mode) {
 #define TOD_TC_CASE(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); break;
       TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
