@@ -316,12 +316,15 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
   for (int rep = 0; rep < kStemIters; ++rep) {
   const int64_t idx = (int64_t(blockIdx.x) * kStemIters + rep) * kStemThreads + threadIdx.x;
   if (idx >= total) return;
-  const int grp = int(idx % groups);
-  int64_t pix = idx / groups;
-  const int ox = int(pix % g.OW);
-  pix /= g.OW;
-  const int oy = int(pix % g.OH);
-  const int t = int(pix / g.OH);
+  // 32-bit index arithmetic (the launcher guarantees total < 2^31): four 64-bit divisions per work item were as many
+  // instructions as the 144 dp4a they fed
+  const unsigned idx32 = unsigned(idx);
+  unsigned pix = idx32 / unsigned(groups);
+  const int grp = int(idx32 - pix * unsigned(groups));
+  unsigned row = pix / unsigned(g.OW);
+  const int ox = int(pix - row * unsigned(g.OW));
+  const int t = int(row / unsigned(g.OH));
+  const int oy = int(row - unsigned(t) * unsigned(g.OH));
   const int oc0 = grp * kStemOct;
   const int zp4 = (in_zp & 0xFF) * 0x01010101;
   const int8_t* tin = in + int64_t(t) * in_ts;
@@ -857,7 +860,7 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
                         int32_t in_zp, const ConvGeom& g, const Requant& rq, int8_t* out, int64_t out_ts, int tiles,
                         cudaStream_t s) {
   // the RGB stem: 3x3, stride 2, no top / left padding, 16-byte-aligned 16-channel output groups
-  if (stem_kernel_eligible(g, rq, in, in_ts, out, out_ts)) {
+  if (stem_kernel_eligible(g, rq, in, in_ts, out, out_ts) && int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct) < (int64_t(1) << 31)) {
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
     dim3 grid(unsigned((total + kStemThreads * kStemIters - 1) / (kStemThreads * kStemIters)));
     if (rq.act_min == -128 && rq.act_max == 127)
