@@ -142,9 +142,17 @@ __global__ void __launch_bounds__(256) vertical_kernel(Src src, int n, int sw, R
   const int64_t total = int64_t(n) * A.out_size * sw;
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int x = int(idx % sw);
-  const int oy = int((idx / sw) % A.out_size);
-  const int f = int(idx / (int64_t(sw) * A.out_size));
+  int x, oy, f;
+  if (total < (int64_t(1) << 31)) {  // 32-bit index arithmetic whenever it fits: the 64-bit divisions outweighed the taps
+    const unsigned i32 = unsigned(idx), r = i32 / unsigned(sw);
+    x = int(i32 - r * unsigned(sw));
+    f = int(r / unsigned(A.out_size));
+    oy = int(r - unsigned(f) * unsigned(A.out_size));
+  } else {
+    x = int(idx % sw);
+    oy = int((idx / sw) % A.out_size);
+    f = int(idx / (int64_t(sw) * A.out_size));
+  }
   const int left = A.left[oy], cnt = A.count[oy];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   for (int i = 0; i < cnt; ++i) {
@@ -172,9 +180,17 @@ __global__ void __launch_bounds__(256) horizontal_kernel(const float* __restrict
   const int64_t total = int64_t(n) * rows * A.out_size;
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ox = int(idx % A.out_size);
-  const int y = int((idx / A.out_size) % rows);
-  const int f = int(idx / (int64_t(A.out_size) * rows));
+  int ox, y, f;
+  if (total < (int64_t(1) << 31)) {
+    const unsigned i32 = unsigned(idx), r = i32 / unsigned(A.out_size);
+    ox = int(i32 - r * unsigned(A.out_size));
+    f = int(r / unsigned(rows));
+    y = int(r - unsigned(f) * unsigned(rows));
+  } else {
+    ox = int(idx % A.out_size);
+    y = int((idx / A.out_size) % rows);
+    f = int(idx / (int64_t(A.out_size) * rows));
+  }
   const int left = A.left[ox], cnt = A.count[ox];
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   const float* row = tmp + (int64_t(f) * rows + y) * sw * 3;
