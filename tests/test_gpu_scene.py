@@ -95,3 +95,65 @@ def test_batch_independence_and_capacity(tod):
         assert np.array_equal(a[k], b[k][::-1]), k  # a frame's bytes do not depend on its position in the batch
     with pytest.raises(tod.TodError):
         tod.SceneBuilder(width=320, height=240, max_batch=2).append_batch(depth, target)
+
+
+def test_stamp_kernels_agree(tod, monkeypatch):
+    """TOD_STAMP_IMPL: 0 = pruned (default), 1 = shared-atomic, 2 = packed, 3 = generic - identical bytes, with robots and balls."""
+    depth = synth.depth_frames(3, seed=31)
+    target = synth.target_frames(3, seed=32, blobs=9)
+    maps = []
+    for impl in (0, 1, 2, 3):
+        monkeypatch.setenv("TOD_STAMP_IMPL", str(impl))
+        sb = tod.SceneBuilder(max_batch=3)
+        maps.append(sb.append_batch(depth, target)["map"])
+    m0, _ = oracle.pt_cloud(depth[0], target[0])
+    assert np.array_equal(maps[0][0], m0)
+    for k in (1, 2, 3):
+        assert np.array_equal(maps[0], maps[k]), "stamp kernel %d differs from the pruned kernel" % k
+
+
+def test_wide_terrain_bump_takes_the_generic_kernel(tod):
+    """terrain_norm_const > 16 needs more than the 64 source columns the eight-warp atomic kernel stages (and a wider
+    pattern than the pruned kernel's): the handle must fall back to the generic kernel and still match the oracle."""
+    depth = synth.depth_frames(1, W=200, H=150, seed=33)
+    target = synth.target_frames(1, W=200, H=150, seed=34)
+    _compare(tod, depth, target, terrain_norm_const=17, bot_norm_const=20)
+    _compare(tod, depth, target, terrain_norm_const=12, bot_norm_const=24)
+
+
+def test_handles_of_different_sizes_coexist(tod, monkeypatch):
+    """Opt-in shared memory is a per-function attribute: creating a smaller handle must not break an existing larger one."""
+    depth = synth.depth_frames(1, seed=35)
+    target = synth.target_frames(1, seed=36)
+    small_d = synth.depth_frames(1, W=320, H=240, seed=37)
+    for impl in ("1", "2", "3"):
+        monkeypatch.setenv("TOD_STAMP_IMPL", impl)
+        big = tod.SceneBuilder(max_batch=1)
+        small = tod.SceneBuilder(width=320, height=240, max_batch=1)
+        small.append_batch(small_d, np.zeros_like(small_d))
+        got = big.append_batch(depth, target)
+        m, _ = oracle.pt_cloud(depth[0], target[0])
+        assert np.array_equal(got["map"][0], m)
+
+
+def test_bench_size_batch_sampled_against_oracle(tod):
+    """BASELINE config 3 at its size: 256 frames of 640x480 in one call; sampled frames against the oracle, and every
+    frame against the same frame run alone (bytes do not depend on the batch)."""
+    depth = synth.depth_frames(256, seed=3)
+    target = synth.target_frames(256, seed=4)
+    sb = tod.SceneBuilder(max_batch=256)
+    got = sb.append_batch(depth, target, want=("map", "balls"))
+    for f in (0, 1, 63, 128, 255):
+        m, balls = oracle.pt_cloud(depth[f], target[f])
+        assert np.array_equal(got["map"][f], m), "frame %d" % f
+        np.testing.assert_allclose(got["balls"][f], balls, rtol=1e-5, atol=0)
+    one = tod.SceneBuilder(max_batch=1)
+    for f in (5, 77, 200):
+        a = one.append_batch(depth[f:f + 1], target[f:f + 1])
+        assert np.array_equal(a["map"][0], got["map"][f])
+    full = sb.append_batch(depth[:8], target[:8])
+    for f in (0, 7):
+        world, c0, c1 = oracle.pt_cloud_weights(got["map"][f])
+        assert np.array_equal(full["world"][f].view(np.uint32), world.view(np.uint32))
+        assert np.array_equal(full["conn0"][f].view(np.uint32), c0.view(np.uint32))
+        assert np.array_equal(full["conn1"][f].view(np.uint32), c1.view(np.uint32))

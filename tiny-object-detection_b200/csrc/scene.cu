@@ -37,54 +37,69 @@ struct SceneDev {
 };
 
 // ------------------------------------------------------------------ land: where does each pixel stamp?
-// pt_cloud.comp:84-114.  Output: land u16 = kind<<14 | (py + py_bias), plus ball sums and a per-row
-// "row holds a robot pixel" flag so the stamp kernel can skip the 40x40 pass on robot-free rows.
+// pt_cloud.comp:84-114.  One warp = one source row of one 32-column strip.  Output: land u16 = kind<<14 | (py + py_bias),
+// ball sums, a per-row "row holds a robot pixel" flag (the single-warp stamp kernels skip the 40x40 pass on robot-free
+// rows) and, per (strip, source row), the range of encoded landing rows of its terrain / robot pixels (lo | hi<<16,
+// lo > hi when there is none): the pruned stamp kernel only visits the source rows that can land in its band.
 __global__ void __launch_bounds__(256) land_kernel(const uint16_t* __restrict__ depth,
                                                   const uint16_t* __restrict__ target, const float* __restrict__ cy_tab,
                                                   const float* __restrict__ cx_tab, SceneDev P,
                                                   uint16_t* __restrict__ land, unsigned int* __restrict__ row_robot,
-                                                  unsigned long long* __restrict__ ball_sums, int frames) {
+                                                  unsigned long long* __restrict__ ball_sums,
+                                                  uint32_t* __restrict__ rowinfo_t, uint32_t* __restrict__ rowinfo_b) {
+  const int lane = threadIdx.x;
+  const int x = blockIdx.x * kStripW + lane;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (y >= P.H) return;  // whole warp
+  const bool valid = x < P.W;
   const int64_t npx = int64_t(P.W) * P.H;
-  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= npx * frames) return;
-  const int f = int(idx / npx);
-  const int p = int(idx - int64_t(f) * npx);
-  const int y = p / P.W, x = p - y * P.W;
-  // nearest texture() fetch; SURVEY §9.4: texel (x - shift, y - shift) with Repeat addressing
-  int sx = x - P.sample_shift, sy = y - P.sample_shift;
-  if (sx < 0) sx += P.W;
-  if (sy < 0) sy += P.H;
-  const int64_t src = int64_t(f) * npx + int64_t(sy) * P.W + sx;
-  const unsigned d = depth[src];
-  const unsigned tg = target[src];
-  const int cls = tg & 0xFF, id = tg >> 8;  // R8G8 little-endian upload (scene.rs:198)
-  // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
-  const float de = __fmul_rn(__fmul_rn(float(d), cy_tab[y]), cx_tab[x]);
-  // :98  int(float(height) * depth / max_depth_in)
-  const int dz = int(__fdiv_rn(__fmul_rn(float(P.H), de), P.max_depth));
-  const int py = P.H - dz;  // :114
-  int action = cls;
-  if (action > 1) action -= 1;  // :108-111
-  int kind;
-  if (action == 0) kind = kKindTerrain;
-  else if (action == 2) kind = kKindBall;
-  else kind = kKindRobot;
-  if (kind == kKindBall) {
-    if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
-      unsigned long long* b = ball_sums + (int64_t(f) * kMaxBalls + id) * 3;
-      atomicAdd(b + 0, (unsigned long long)(long long)x);
-      atomicAdd(b + 1, (unsigned long long)(long long)py);
-      atomicAdd(b + 2, 1ull);
+  int kind = kKindNone, enc = 0;
+  if (valid) {
+    // nearest texture() fetch; SURVEY §9.4: texel (x - shift, y - shift) with Repeat addressing
+    int sx = x - P.sample_shift, sy = y - P.sample_shift;
+    if (sx < 0) sx += P.W;
+    if (sy < 0) sy += P.H;
+    const int64_t src = int64_t(f) * npx + int64_t(sy) * P.W + sx;
+    const unsigned d = depth[src];
+    const unsigned tg = target[src];
+    const int cls = tg & 0xFF, id = tg >> 8;  // R8G8 little-endian upload (scene.rs:198)
+    // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
+    const float de = __fmul_rn(__fmul_rn(float(d), cy_tab[y]), cx_tab[x]);
+    // :98  int(float(height) * depth / max_depth_in)
+    const int dz = int(__fdiv_rn(__fmul_rn(float(P.H), de), P.max_depth));
+    const int py = P.H - dz;  // :114
+    int action = cls;
+    if (action > 1) action -= 1;  // :108-111
+    if (action == 0) kind = kKindTerrain;
+    else if (action == 2) kind = kKindBall;
+    else kind = kKindRobot;
+    if (kind == kKindBall) {
+      if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
+        unsigned long long* b = ball_sums + (int64_t(f) * kMaxBalls + id) * 3;
+        atomicAdd(b + 0, (unsigned long long)(long long)x);
+        atomicAdd(b + 1, (unsigned long long)(long long)py);
+        atomicAdd(b + 2, 1ull);
+      }
+    } else {
+      const int s = kind == kKindTerrain ? P.s_t : P.s_b;
+      // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
+      if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
     }
-  } else {
-    const int s = kind == kKindTerrain ? P.s_t : P.s_b;
-    // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
-    if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
-    else if (kind == kKindRobot) atomicOr(row_robot + int64_t(f) * P.H + y, 1u);
+    enc = max(0, min(py + P.py_bias, 0x3FFF));
+    land[int64_t(f) * npx + int64_t(y) * P.W + x] = uint16_t((kind << 14) | enc);
   }
-  int enc = py + P.py_bias;
-  enc = max(0, min(enc, 0x3FFF));
-  land[idx] = uint16_t((kind << 14) | enc);
+  const unsigned full = 0xffffffffu;
+  const unsigned t_lo = __reduce_min_sync(full, kind == kKindTerrain ? unsigned(enc) : 0xFFFFu);
+  const unsigned t_hi = __reduce_max_sync(full, kind == kKindTerrain ? unsigned(enc) : 0u);
+  const unsigned b_lo = __reduce_min_sync(full, kind == kKindRobot ? unsigned(enc) : 0xFFFFu);
+  const unsigned b_hi = __reduce_max_sync(full, kind == kKindRobot ? unsigned(enc) : 0u);
+  if (lane == 0) {
+    const int64_t ri = (int64_t(f) * gridDim.x + blockIdx.x) * P.H + y;
+    rowinfo_t[ri] = t_lo | (t_hi << 16);
+    rowinfo_b[ri] = b_lo | (b_hi << 16);
+    if (b_lo <= b_hi) atomicOr(row_robot + int64_t(f) * P.H + y, 1u);
+  }
 }
 
 __global__ void balls_kernel(const unsigned long long* __restrict__ sums, float* __restrict__ balls4, int n) {
@@ -371,6 +386,185 @@ __global__ void __launch_bounds__(32) stamp_packed_kernel(const uint16_t* __rest
   }
 }
 
+// ------------------------------------------------------------------ stamp, pruned (default)
+// What the shader does per source pixel - 400 imageAtomicMax (pt_cloud.comp:64-75) - is mostly redundant:
+//  * the terrain bump uint(y_add) is non-decreasing in val = source row y for every stamp offset (checked element-wise
+//    on the host table at create time), so of all terrain pixels of a column that land on the same map row only the
+//    one with the largest y can win: 307 200 stamps per 640x480 frame become ~110 000 (column, landing row) entries;
+//  * the bump depends on the offset only through d2 = dx*dx + dy*dy and is zero beyond d2 = 80 (also checked), so an
+//    entry carries 36 table values, not 400.
+// One warp owns one (32-column strip, 64-landing-row band) of one frame and a private shared-memory tile of the map
+// around it (16-cell halo, two map rows per 32-bit word).  Phase A: walk the source rows from the bottom up (only the
+// rows whose landing range meets the band, via land_kernel's row ranges); the first terrain pixel of a column that lands
+// on a row is the dominant one and is appended to that lane's list.  Phase B: lane = source column; every lane walks its
+// own list and applies the stamp - the generated, fully unrolled csrc/stamp_pattern.inc: 137 packed read / vmaxu2 /
+// write triples with immediate offsets, no atomics.  A tile row is 64 words, so bank = (lane + dx) mod 32: conflict-free,
+// and two lanes touch the same word only in different dx groups, which are separated by __syncwarp.  Robot pixels
+// (constant value, 33 x 33 table) go through the same lists with a generic loop.  The tile leaves as one 12 KB block;
+// merge_kernel takes the maximum of the (at most four) tiles that cover a map cell.
+constexpr int kPrBand = 64, kPrHalo = 16, kPrTileW = 64;
+constexpr int kPrPairs = (kPrBand + 2 * kPrHalo) / 2;   // 48 word rows
+constexpr int kPrTileWords = kPrPairs * kPrTileW;        // 3072 words = 12 KB
+constexpr int kPrRadius = 8, kPrD2Max = 80, kPrClasses = 36, kPrRowWords = 20;  // table row: 36 u16, padded to 80 bytes
+constexpr int kPrBotCols = 2 * kPrHalo + 1, kPrBotWords = kPrHalo + 1;          // robot table: [2][33][17] words
+
+struct PrunedDev {
+  int r_min, nbands, nstrips;   // band b holds the landing rows [r_min + 64 b, r_min + 64 b + 64)
+};
+
+__device__ __forceinline__ void pr_append(unsigned v, int y, int want_kind, int enc_lo, unsigned long long& seen, int& cnt,
+                                          uint16_t* list, int lane) {
+  const int rel = int(v & 0x3FFF) - enc_lo;
+  if (int(v >> 14) == want_kind && unsigned(rel) < unsigned(kPrBand)) {
+    const unsigned long long bit = 1ull << rel;
+    if (!(seen & bit)) {
+      seen |= bit;
+      list[cnt * 32 + lane] = uint16_t((rel << 10) | y);
+      ++cnt;
+    }
+  }
+}
+
+// Phase A for one pixel kind: per lane, the (landing row, largest source row) entries of its column inside the band
+__device__ __forceinline__ int pr_collect(const uint16_t* __restrict__ L, const uint32_t* __restrict__ RI, const SceneDev& P, int x, int lane,
+                                          int want_kind, int y_min, int enc_lo, uint16_t* list) {
+  int cnt = 0;
+  unsigned long long seen = 0ull;
+  const unsigned enc_hi = unsigned(enc_lo + kPrBand - 1);
+  for (int y_top = P.H - 1; y_top >= y_min; y_top -= 32) {
+    const int yl = y_top - lane;
+    bool hit = false;
+    if (yl >= y_min) {
+      const uint32_t info = __ldg(RI + yl);
+      hit = int(info & 0xFFFFu) <= int(enc_hi) && int(info >> 16) >= enc_lo;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    while (m) {  // descending y, four rows in flight
+      int ys[4];
+      unsigned vs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ys[j] = -1;
+        if (m) {
+          ys[j] = y_top - (__ffs(m) - 1);
+          m &= m - 1;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vs[j] = (ys[j] >= 0 && x < P.W) ? unsigned(L[int64_t(ys[j]) * P.W + x]) : unsigned(kKindNone << 14);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pr_append(vs[j], ys[j], want_kind, enc_lo, seen, cnt, list, lane);
+    }
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __restrict__ land, const uint32_t* __restrict__ rowinfo_t,
+                                                         const uint32_t* __restrict__ rowinfo_b, const uint4* __restrict__ ttab,  // [H][5]
+                                                         const uint32_t* __restrict__ btab,    // [2 parities][33][17] packed robot stamp
+                                                         const uint32_t* __restrict__ bspan,   // [33] klo | khi << 8
+                                                         SceneDev P, PrunedDev Q, uint32_t* __restrict__ staging) {
+  __shared__ __align__(16) uint32_t tile[kPrTileWords];
+  __shared__ uint16_t list[kPrBand * 32];
+  const int lane = threadIdx.x;
+  const int strip = blockIdx.x / Q.nbands, band = blockIdx.x - strip * Q.nbands;
+  const int f = blockIdx.y;
+  const int x = strip * kStripW + lane;
+  const int enc_lo = Q.r_min + band * kPrBand + P.py_bias;  // encoded landing row of the band's first row
+  for (int i = lane; i < kPrTileWords / 4; i += 32) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  const uint16_t* L = land + int64_t(f) * P.W * P.H;
+  const int64_t ri = (int64_t(f) * Q.nstrips + strip) * P.H;
+  // ---- terrain (val = source row; row 0 stamps nothing: val = 0 makes every y_add NaN -> 0)
+  {
+    const int cnt = pr_collect(L, rowinfo_t + ri, P, x, lane, kKindTerrain, 1, enc_lo, list);
+    const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
+#pragma unroll 1
+    for (int i = 0; i < maxcnt; ++i) {
+      const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
+      if (i < cnt) {
+        const unsigned e = list[i * 32 + lane];
+        const int row0 = int(e >> 10) + (kPrHalo - kPrRadius);   // tile row of dy = -8
+        uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane + kPrHalo;
+        const unsigned sel = (row0 & 1) ? 0x5432u : 0x7654u;
+        const uint4* tr = ttab + int64_t(e & 1023u) * (kPrRowWords / 4);
+        uint32_t t[kPrRowWords];
+#pragma unroll
+        for (int q = 0; q < kPrRowWords / 4; ++q) {
+          const uint4 v = __ldg(tr + q);
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+#define PR_PRMT(a, b, s) __byte_perm(a, b, s)
+#define PR_RMW(off, w) base[off] = __vmaxu2(base[off], w)
+#define PR_SYNC() __syncwarp(active)
+#include "stamp_pattern.inc"
+#undef PR_PRMT
+#undef PR_RMW
+#undef PR_SYNC
+      }
+    }
+  }
+  // ---- robot (constant val: one stamp per (column, landing row) is enough)
+  {
+    __syncwarp();
+    const int cnt = pr_collect(L, rowinfo_b + ri, P, x, lane, kKindRobot, 0, enc_lo, list);
+    const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
+#pragma unroll 1
+    for (int i = 0; i < maxcnt; ++i) {
+      const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
+      if (i < cnt) {
+        const int row0 = int(list[i * 32 + lane] >> 10);   // tile row of dy = -16
+        uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane;   // column of dx = -16
+        const uint32_t* tp = btab + (row0 & 1) * (kPrBotCols * kPrBotWords);
+        for (int c = 0; c < kPrBotCols; ++c) {
+          const unsigned sp = __ldg(bspan + c);
+          const int klo = int(sp & 0xFFu), khi = int(sp >> 8);
+          for (int k = klo; k < khi; ++k) {
+            uint32_t* q = base + k * kPrTileW + c;
+            *q = __vmaxu2(*q, __ldg(tp + c * kPrBotWords + k));
+          }
+          __syncwarp(active);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  uint4* out = reinterpret_cast<uint4*>(staging + (int64_t(f) * gridDim.x + blockIdx.x) * kPrTileWords);
+  for (int i = lane; i < kPrTileWords / 4; i += 32) out[i] = reinterpret_cast<const uint4*>(tile)[i];
+}
+
+// map cell = max over the tiles that cover it (two strips x one or two bands); pt_cloud.comp:67 border rule
+__global__ void __launch_bounds__(256) merge_kernel(const uint32_t* __restrict__ staging, SceneDev P, PrunedDev Q,
+                                                   uint32_t* __restrict__ map, int frames) {
+  const int64_t npx = int64_t(P.W) * P.H;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= npx * frames) return;
+  const int f = int(idx / npx);
+  const int p = int(idx - int64_t(f) * npx);
+  const int y = p / P.W, x = p - y * P.W;
+  uint32_t v = 0u;
+  if (x > 0 && x < P.W - 1 && y > 0 && y < P.H - 1) {
+    const int s1 = (x + kPrHalo) / kStripW;          // tile columns: x - 32 s + 16 in [0, 64)
+    const int b1 = (y - Q.r_min + kPrHalo) / kPrBand;   // tile rows:    y - r_min - 64 b + 16 in [0, 96)
+    const uint16_t* S = reinterpret_cast<const uint16_t*>(staging) + int64_t(f) * Q.nstrips * Q.nbands * (2 * kPrTileWords);
+#pragma unroll
+    for (int ds = 0; ds < 2; ++ds) {
+      const int s = s1 - ds;
+      if (s < 0 || s >= Q.nstrips) continue;
+      const int c = x - s * kStripW + kPrHalo;
+#pragma unroll
+      for (int db = 0; db < 2; ++db) {
+        const int b = b1 - db;
+        const int r = y - Q.r_min - b * kPrBand + kPrHalo;
+        if (b < 0 || b >= Q.nbands || r >= kPrBand + 2 * kPrHalo) continue;
+        const uint32_t t = S[(int64_t(s) * Q.nbands + b) * (2 * kPrTileWords) + ((r >> 1) * kPrTileW + c) * 2 + (r & 1)];
+        v = t > v ? t : v;
+      }
+    }
+  }
+  map[idx] = v;
+}
+
 // ------------------------------------------------------------------ weights
 // pt_cloud_weights.comp:49-123 as one streaming pass: every thread recomputes the (at most 8)
 // distances it needs from the 3x3 map neighbourhood instead of exchanging them through images, which
@@ -380,42 +574,60 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
   return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 
-__global__ void __launch_bounds__(256) weights_kernel(const uint32_t* __restrict__ map, SceneDev P,
-                                                     float4* __restrict__ world, float4* __restrict__ conn0,
-                                                     float4* __restrict__ conn1, int frames) {
+// One block = a 32 x 8 pixel tile.  In literal mode (pack() == 0, so every neighbour decodes to world[0,0])
+// all eight link weights of a pixel are values of one field D[a] = |world[a] - world[0,0]| at the pixel and four of its
+// neighbours: the tile (+ 1-pixel halo) of D is computed once into shared memory - 1.3 square roots per pixel instead of
+// 5 - and the 48 output bytes per pixel leave as streaming 16-byte stores (nothing reads them back on the device).
+constexpr int kWtX = 32, kWtY = 8;
+
+__global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __restrict__ map, SceneDev P,
+                                                             float4* __restrict__ world, float4* __restrict__ conn0,
+                                                             float4* __restrict__ conn1) {
+  __shared__ float fld[kWtY + 2][kWtX + 2];   // literal: D[a]; intent: h[a]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x0 = blockIdx.x * kWtX, y0 = blockIdx.y * kWtY;
+  const int f = blockIdx.z;
   const int64_t npx = int64_t(P.W) * P.H;
-  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= npx * frames) return;
-  const int f = int(idx / npx);
-  const int p = int(idx - int64_t(f) * npx);
-  const int y = p / P.W, x = p - y * P.W;
   const uint32_t* M = map + int64_t(f) * npx;
   const bool literal = P.weights_mode == 0;
-  auto h = [&](int xx, int yy) { return float(M[int64_t(yy) * P.W + xx]); };
   const float h00 = literal ? float(M[0]) : 0.f;
-  // distance between pixel a (the "pos" of the shader invocation) and its neighbour b
-  auto link = [&](int ax, int ay, int bx, int by) {
-    const float wx = float(ax), wy = h(ax, ay), wz = float(ay);
-    if (literal) return dist3(wx, wy, wz, 0.f, h00, 0.f);  // pack() == 0 -> unpack loads world[0,0]
-    return dist3(wx, wy, wz, float(bx), h(bx, by), float(by));
+  for (int i = ty * kWtX + tx; i < (kWtY + 2) * (kWtX + 2); i += kWtX * kWtY) {
+    const int ly = i / (kWtX + 2), lx = i - ly * (kWtX + 2);
+    const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
+      const float h = float(M[int64_t(gy) * P.W + gx]);
+      v = literal ? dist3(float(gx), h, float(gy), 0.f, h00, 0.f) : h;
+    }
+    fld[ly][lx] = v;
+  }
+  __syncthreads();
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= P.W || y >= P.H) return;
+  const int64_t idx = int64_t(f) * npx + int64_t(y) * P.W + x;
+  auto F = [&](int dx, int dy) { return fld[ty + 1 + dy][tx + 1 + dx]; };
+  // weight of the link from pixel a = p + (adx, ady) (the "pos" of the shader invocation) to b = p + (bdx, bdy)
+  auto link = [&](int adx, int ady, int bdx, int bdy) {
+    if (literal) return F(adx, ady);
+    return dist3(float(x + adx), F(adx, ady), float(y + ady), float(x + bdx), F(bdx, bdy), float(y + bdy));
   };
   const bool nxmin = x > 0, nxmax = x < P.W - 1, nymin = y > 0, nymax = y < P.H - 1;
-  if (world) world[idx] = make_float4(float(x), h(x, y), float(y), 0.f);  // :59-69
+  if (world) __stcs(world + idx, make_float4(float(x), float(M[int64_t(y) * P.W + x]), float(y), 0.f));  // :59-69
   if (conn1) {  // :86-107  (below, below-left, left, above-left)
     float4 c;
-    c.x = nymax ? link(x, y, x, y + 1) : -1.f;
-    c.y = (nxmin && nymax) ? link(x, y, x - 1, y + 1) : -1.f;
-    c.z = nxmin ? link(x, y, x - 1, y) : -1.f;
-    c.w = (nxmin && nymin) ? link(x, y, x - 1, y - 1) : -1.f;
-    conn1[idx] = c;
+    c.x = nymax ? link(0, 0, 0, 1) : -1.f;
+    c.y = (nxmin && nymax) ? link(0, 0, -1, 1) : -1.f;
+    c.z = nxmin ? link(0, 0, -1, 0) : -1.f;
+    c.w = (nxmin && nymin) ? link(0, 0, -1, -1) : -1.f;
+    __stcs(conn1 + idx, c);
   }
   if (conn0) {  // :112-122  conn1[up].r, conn1[up-right].g, conn1[right].b, conn1[down-right].a
     float4 c;
-    c.x = nymin ? link(x, y - 1, x, y) : -1.f;
-    c.y = (nxmax && nymin) ? link(x + 1, y - 1, x, y) : -1.f;
-    c.z = nxmax ? link(x + 1, y, x, y) : -1.f;
-    c.w = (nxmax && nymax) ? link(x + 1, y + 1, x, y) : -1.f;
-    conn0[idx] = c;
+    c.x = nymin ? link(0, -1, 0, 0) : -1.f;
+    c.y = (nxmax && nymin) ? link(1, -1, 0, 0) : -1.f;
+    c.z = nxmax ? link(1, 0, 0, 0) : -1.f;
+    c.w = (nxmax && nymax) ? link(1, 1, 0, 0) : -1.f;
+    __stcs(conn0 + idx, c);
   }
 }
 
@@ -484,6 +696,77 @@ void spans_of(const uint16_t* lut, int d, uint8_t* span) {  // per ox: [lo, hi) 
   }
 }
 
+// ---- tables of the pruned stamp kernel; returns false when the bump tables do not have the structure it relies on
+struct PrunedTables {
+  std::vector<uint16_t> ttab;   // [H][40]: class k of source row y
+  std::vector<uint32_t> btab;   // [2][33][17]
+  std::vector<uint32_t> bspan;  // [33]
+};
+
+bool build_pruned_tables(const std::vector<uint16_t>& lut_t, int H, int st, const std::vector<uint16_t>& lut_b, int sb, PrunedTables* out) {
+  if (H > 1024) return false;  // list entries hold the source row in 10 bits
+  int cls_of[kPrD2Max + 1];
+  int ncls = 0;
+  for (int d2 = 0; d2 <= kPrD2Max; ++d2) {
+    bool is_sum = false;
+    for (int a = 0; a <= kPrRadius && !is_sum; ++a)
+      for (int b = 0; b <= kPrRadius && !is_sum; ++b) is_sum = a * a + b * b == d2;
+    cls_of[d2] = is_sum ? ncls++ : -1;
+  }
+  if (ncls != kPrClasses) return false;
+  const int dt = 2 * st;
+  out->ttab.assign(size_t(H) * 2 * kPrRowWords, 0);
+  for (int y = 0; y < H; ++y) {
+    std::vector<int> seen(kPrClasses, -1);
+    for (int ox = 0; ox < dt; ++ox)
+      for (int oy = 0; oy < dt; ++oy) {
+        const int v = lut_t[(size_t(y) * dt + ox) * dt + oy];
+        const int d2 = (st - ox) * (st - ox) + (st - oy) * (st - oy);
+        if (d2 > kPrD2Max || d2 >= st * st) {   // outside the pattern, or a cell whose mirror image the shader never writes
+          if (v) return false;
+          continue;
+        }
+        const int k = cls_of[d2];
+        if (seen[k] >= 0 && seen[k] != v) return false;  // not a function of d2 alone
+        seen[k] = v;
+      }
+    for (int k = 0; k < kPrClasses; ++k) {
+      const int v = seen[k] < 0 ? 0 : seen[k];
+      if (y > 0 && v < out->ttab[size_t(y - 1) * 2 * kPrRowWords + k]) return false;  // dominance needs monotone in val
+      out->ttab[size_t(y) * 2 * kPrRowWords + k] = uint16_t(v);
+    }
+  }
+  // robot: column c <-> dx = c - 16, word k of parity p covers dy = 2k - 16 - p, 2k - 15 - p
+  const int db = 2 * sb;
+  auto bval = [&](int dx, int dy) -> uint32_t {
+    const int ox = dx + sb, oy = dy + sb;
+    return (ox >= 0 && ox < db && oy >= 0 && oy < db) ? lut_b[size_t(ox) * db + oy] : 0u;
+  };
+  for (int ox = 0; ox < db; ++ox)
+    for (int oy = 0; oy < db; ++oy)
+      if (lut_b[size_t(ox) * db + oy] && (std::abs(ox - sb) > kPrHalo || std::abs(oy - sb) > kPrHalo)) return false;
+  out->btab.assign(size_t(2) * kPrBotCols * kPrBotWords, 0u);
+  out->bspan.assign(kPrBotCols, 0u);
+  for (int c = 0; c < kPrBotCols; ++c) {
+    int klo = kPrBotWords, khi = 0;
+    for (int p = 0; p < 2; ++p)
+      for (int k = 0; k < kPrBotWords; ++k) {
+        const int dy0 = 2 * k - kPrHalo - p;
+        const uint32_t lo = (dy0 >= -kPrHalo && dy0 <= kPrHalo) ? bval(c - kPrHalo, dy0) : 0u;
+        const uint32_t hi = (dy0 + 1 >= -kPrHalo && dy0 + 1 <= kPrHalo) ? bval(c - kPrHalo, dy0 + 1) : 0u;
+        const uint32_t w = lo | (hi << 16);
+        out->btab[(size_t(p) * kPrBotCols + c) * kPrBotWords + k] = w;
+        if (w) {
+          klo = k < klo ? k : klo;
+          khi = k + 1 > khi ? k + 1 : khi;
+        }
+      }
+    if (khi <= klo) klo = khi = 0;
+    out->bspan[c] = uint32_t(klo) | (uint32_t(khi) << 8);
+  }
+  return true;
+}
+
 }  // namespace
 }  // namespace tod
 
@@ -503,6 +786,14 @@ struct tod_scene {
   unsigned int* row_mask = nullptr;  // per source row: which stamp columns are non-empty
   size_t packed_smem = 0;
   size_t atomic_smem = 0;
+  // pruned stamp kernel (default): class table, robot table, per (strip, row) landing ranges, tile staging
+  uint4* ttab = nullptr;
+  uint32_t *btab = nullptr, *bspan = nullptr, *rowinfo_t = nullptr, *rowinfo_b = nullptr, *staging = nullptr;
+  PrunedDev pruned{};
+  bool pruned_ok = false;
+  int stamp_impl = 0;
+  bool own_results = false;   // the last append call left map / world / conn / balls in the handle's own buffers
+  cudaEvent_t caller_done = nullptr;  // recorded on a caller's stream so that materialize can order itself behind it
   // per-batch buffers
   uint16_t *depth = nullptr, *target = nullptr, *land = nullptr;
   unsigned int* row_robot = nullptr;
@@ -538,12 +829,13 @@ void tod_scene_default_params(tod_scene_params* p) {
 void tod_scene_destroy(tod_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  void* ptrs[] = {s->lut_pack, s->row_mask, s->cy, s->cx, s->lut_t, s->lut_b, s->span_t, s->span_b, s->depth, s->target, s->land, s->row_robot,
+  void* ptrs[] = {s->ttab, s->btab, s->bspan, s->rowinfo_t, s->rowinfo_b, s->staging, s->lut_pack, s->row_mask, s->cy, s->cx, s->lut_t, s->lut_b, s->span_t, s->span_b, s->depth, s->target, s->land, s->row_robot,
                   s->ball_sums, s->map, s->world, s->conn0, s->conn1, s->balls, s->m_height, s->m_pos, s->m_conn, s->m_balls};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->ev)
     if (e) cudaEventDestroy(e);
+  if (s->caller_done) cudaEventDestroy(s->caller_done);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -568,6 +860,7 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
   tod_scene* s = new tod_scene();
   s->device = device;
   s->prm = p;
+  s->stamp_impl = std::getenv("TOD_STAMP_IMPL") ? std::atoi(std::getenv("TOD_STAMP_IMPL")) : 0;
   const int W = p.width, H = p.height, st = p.terrain_norm_const, sb = p.bot_norm_const;
   const int smax = st > sb ? st : sb;
   s->dev = SceneDev{W, H, st, sb, 2 * smax + 2, 2 * smax, p.max_depth_in, p.sample_shift, p.weights_mode};
@@ -604,6 +897,7 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
   } while (0)
   SC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   for (cudaEvent_t& e : s->ev) SC_CUDA(cudaEventCreate(&e));
+  SC_CUDA(cudaEventCreateWithFlags(&s->caller_done, cudaEventDisableTiming));
   SC_CUDA(cudaMalloc(&s->cy, H * sizeof(float)));
   SC_CUDA(cudaMalloc(&s->cx, W * sizeof(float)));
   SC_CUDA(cudaMalloc(&s->lut_t, lut_t.size() * 2));
@@ -630,10 +924,37 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
   SC_CUDA(cudaMalloc(&s->m_pos, npx * 12));
   SC_CUDA(cudaMalloc(&s->m_conn, npx * 32));
   SC_CUDA(cudaMalloc(&s->m_balls, kMaxBalls * 8));
-  SC_CUDA(cudaFuncSetAttribute(stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->stamp_smem)));
+  // Opt-in shared memory is a per-function, per-device attribute: every handle asks for the same fixed ceiling, so a
+  // smaller handle created later cannot lower the limit under an existing one.
+  constexpr size_t kSmemCeil = 227 * 1024;
+  if (s->stamp_smem > kSmemCeil) return cleanup_fail(fail(TOD_ERR_UNSUPPORTED, "tod_scene_create: a %d-row strip does not fit shared memory", H));
+  SC_CUDA(cudaFuncSetAttribute(stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemCeil)));
+  // the eight-warp atomic kernel stages 64 source columns per warp: a strip needs 2 * s_t + 31 of them
   s->atomic_smem = size_t(H + 2 * s->dev.pad_rows) * kStripW * 4 + size_t(kAtomWarps) * size_t((dt * dt + 7) / 8 * 16);
-  if (s->atomic_smem <= 110 * 1024) SC_CUDA(cudaFuncSetAttribute(stamp_atomic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->atomic_smem)));
+  if (s->atomic_smem <= 110 * 1024 && 2 * st + 31 <= 64) SC_CUDA(cudaFuncSetAttribute(stamp_atomic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemCeil)));
   else s->atomic_smem = 0;
+  {
+    PrunedTables pt;
+    if (build_pruned_tables(lut_t, H, st, lut_b, sb, &pt)) {
+      const int nstrips = (W + kStripW - 1) / kStripW;
+      const int r_min = 1 - kPrHalo;
+      const int nbands = (H - 2 + 2 * kPrHalo + kPrBand - 1) / kPrBand;
+      s->pruned = PrunedDev{r_min, nbands, nstrips};
+      SC_CUDA(cudaMalloc(&s->ttab, pt.ttab.size() * 2));
+      SC_CUDA(cudaMalloc(&s->btab, pt.btab.size() * 4));
+      SC_CUDA(cudaMalloc(&s->bspan, pt.bspan.size() * 4));
+      SC_CUDA(cudaMemcpy(s->ttab, pt.ttab.data(), pt.ttab.size() * 2, cudaMemcpyHostToDevice));
+      SC_CUDA(cudaMemcpy(s->btab, pt.btab.data(), pt.btab.size() * 4, cudaMemcpyHostToDevice));
+      SC_CUDA(cudaMemcpy(s->bspan, pt.bspan.data(), pt.bspan.size() * 4, cudaMemcpyHostToDevice));
+      SC_CUDA(cudaMalloc(&s->staging, nb * size_t(nstrips) * nbands * kPrTileWords * 4));
+      s->pruned_ok = true;
+    }
+  }
+  {
+    const size_t nstrips = size_t(W + kStripW - 1) / kStripW;
+    SC_CUDA(cudaMalloc(&s->rowinfo_t, nb * nstrips * H * 4));
+    SC_CUDA(cudaMalloc(&s->rowinfo_b, nb * nstrips * H * 4));
+  }
   if (st == 10) {
     // word k of a stamp column covers tile rows (2k, 2k+1) counted from the even-aligned start row; per (y, ox)
     // the table holds the even-aligned and the odd-aligned packing, 12 words each
@@ -655,7 +976,7 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
     SC_CUDA(cudaMemcpy(s->lut_pack, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     SC_CUDA(cudaMemcpy(s->row_mask, rmask.data(), rmask.size() * 4, cudaMemcpyHostToDevice));
     s->packed_smem = (size_t(H + 2 * s->dev.pad_rows + 1) / 2 + kPackWords) * kStripW * sizeof(uint32_t) + size_t(dt) * 6 * 16;
-    SC_CUDA(cudaFuncSetAttribute(stamp_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s->packed_smem)));
+    SC_CUDA(cudaFuncSetAttribute(stamp_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemCeil)));
   }
 #undef SC_CUDA
   *out = s;
@@ -670,21 +991,29 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   TOD_CUDA(cudaMemsetAsync(s->row_robot, 0, size_t(n) * P.H * sizeof(unsigned int), st));
   TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(n) * kMaxBalls * 3 * sizeof(unsigned long long), st));
   const unsigned blocks = unsigned((npx * n + 255) / 256);
-  land_kernel<<<blocks, 256, 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums, n);
+  const int nstrips = (P.W + kStripW - 1) / kStripW;
+  land_kernel<<<dim3(nstrips, (P.H + 7) / 8, n), dim3(32, 8), 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums,
+                                                                        s->rowinfo_t, s->rowinfo_b);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[0], st));
-  dim3 grid((P.W + kStripW - 1) / kStripW, n);
-  // default: the eight-warp atomic kernel (9.8 ms vs 10.8 ms per 256 frames of 640x480); TOD_STAMP_ATOMIC=0 selects the single-warp ones
-  static const int atom_env = std::getenv("TOD_STAMP_ATOMIC") ? std::atoi(std::getenv("TOD_STAMP_ATOMIC")) : 1;
-  if (atom_env && s->atomic_smem)
+  dim3 grid(nstrips, n);
+  // TOD_STAMP_IMPL: 0 = pruned (default: 1 entry per (column, landing row), no atomics), 1 = eight-warp shared-atomic kernel,
+  // 2 = single-warp packed kernel (bump size 10), 3 = single-warp generic kernel.  A handle whose bump tables lack the
+  // structure a kernel relies on falls through to the next one; all four produce the same bytes.
+  const int impl_env = s->stamp_impl;   // read from the environment when the handle was created
+  if (impl_env <= 0 && s->pruned_ok) {
+    stamp_pruned_kernel<<<dim3(nstrips * s->pruned.nbands, n), 32, 0, st>>>(s->land, s->rowinfo_t, s->rowinfo_b, s->ttab, s->btab, s->bspan, P,
+                                                                              s->pruned, s->staging);
+    merge_kernel<<<blocks, 256, 0, st>>>(s->staging, P, s->pruned, d_map, n);
+  } else if (impl_env <= 1 && s->atomic_smem)
     stamp_atomic_kernel<<<grid, kAtomWarps * 32, s->atomic_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
-  else if (s->lut_pack)
+  else if (impl_env <= 2 && s->lut_pack)
     stamp_packed_kernel<<<grid, 32, s->packed_smem, st>>>(s->land, s->row_robot, s->lut_pack, s->row_mask, s->lut_b, s->span_b, P, d_map);
   else
     stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[1], st));
   if (d_world || d_conn0 || d_conn1)
-    weights_kernel<<<blocks, 256, 0, st>>>(d_map, P, reinterpret_cast<float4*>(d_world), reinterpret_cast<float4*>(d_conn0),
-                                           reinterpret_cast<float4*>(d_conn1), n);
+    weights_kernel<<<dim3((P.W + kWtX - 1) / kWtX, (P.H + kWtY - 1) / kWtY, n), dim3(kWtX, kWtY), 0, st>>>(
+        d_map, P, reinterpret_cast<float4*>(d_world), reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[2], st));
   if (d_balls) balls_kernel<<<(n * kMaxBalls + 127) / 128, 128, 0, st>>>(s->ball_sums, d_balls, n * kMaxBalls);
   TOD_CUDA(cudaGetLastError());
@@ -700,7 +1029,16 @@ int tod_scene_append_batch_device(tod_scene* s, const uint16_t* d_depth, const u
   TOD_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->stream;
   s->last_n = n;
-  return scene_run(s, d_depth, d_target, n, d_map ? d_map : s->map, d_world4, d_conn0, d_conn1, d_balls4, st, stream == nullptr);
+  // tod_scene_materialize reads the handle's own images: it is only valid after a call that filled all of them
+  s->own_results = !d_map && !d_world4 && !d_conn0 && !d_conn1 && !d_balls4;
+  const bool own = s->own_results;
+  TOD_TRY(scene_run(s, d_depth, d_target, n, d_map ? d_map : s->map, own ? s->world : d_world4, own ? s->conn0 : d_conn0,
+                    own ? s->conn1 : d_conn1, own ? s->balls : d_balls4, st, stream == nullptr));
+  if (stream) {  // later work on the handle's stream (materialize) must follow the caller's stream
+    TOD_CUDA(cudaEventRecord(s->caller_done, st));
+    TOD_CUDA(cudaStreamWaitEvent(s->stream, s->caller_done, 0));
+  }
+  return TOD_OK;
 }
 
 int tod_scene_append_batch(tod_scene* s, const uint16_t* depth, const uint16_t* target, int n, uint32_t* map,
@@ -721,12 +1059,15 @@ int tod_scene_append_batch(tod_scene* s, const uint16_t* depth, const uint16_t* 
   if (balls4) TOD_CUDA(cudaMemcpyAsync(balls4, s->balls, size_t(n) * kMaxBalls * 16, cudaMemcpyDeviceToHost, st));
   TOD_CUDA(cudaStreamSynchronize(st));  // scene.rs:282 future.wait
   s->last_n = n;
+  s->own_results = true;
   return TOD_OK;
 }
 
 int tod_scene_materialize(tod_scene* s, int frame, float* height, float* pos3, int32_t* balls2, float* connections8) {
   if (!s) return fail(TOD_ERR_INVALID_ARG, "tod_scene_materialize: null handle");
   if (frame < 0 || frame >= s->last_n) return fail(TOD_ERR_INVALID_ARG, "tod_scene_materialize: frame %d not in the last batch of %d", frame, s->last_n);
+  if (!s->own_results)
+    return fail(TOD_ERR_INVALID_ARG, "tod_scene_materialize: the last tod_scene_append_batch_device call wrote to caller buffers; pass NULL outputs to keep the results in the handle");
   TOD_CUDA(cudaSetDevice(s->device));
   const size_t npx = size_t(s->dev.W) * s->dev.H;
   cudaStream_t st = s->stream;
