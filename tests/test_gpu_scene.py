@@ -157,3 +157,27 @@ def test_bench_size_batch_sampled_against_oracle(tod):
         assert np.array_equal(full["world"][f].view(np.uint32), world.view(np.uint32))
         assert np.array_equal(full["conn0"][f].view(np.uint32), c0.view(np.uint32))
         assert np.array_equal(full["conn1"][f].view(np.uint32), c1.view(np.uint32))
+
+
+def test_map_only_device_call_and_materialize_guard(tod):
+    """append_batch_device with no weight outputs takes the stand-alone tile merge; tod_scene_materialize refuses to run
+    on results that went to caller buffers (it reads the handle's own images)."""
+    torch = pytest.importorskip("torch")
+    depth = synth.depth_frames(2, W=320, H=240, seed=41)
+    target = synth.target_frames(2, W=320, H=240, seed=42)
+    sb = tod.SceneBuilder(width=320, height=240, max_batch=2)
+    want = sb.append_batch(depth, target)
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    d_target = torch.from_numpy(target.view(np.int16)).cuda()
+    d_map = torch.zeros((2, 240, 320), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    sb.append_batch_device(d_depth.data_ptr(), d_target.data_ptr(), 2, d_map.data_ptr())
+    with pytest.raises(tod.TodError):
+        sb.materialize(0)
+    torch.cuda.synchronize()
+    sb.append_batch(depth[:1], target[:1], want=())   # drains the handle's stream
+    assert np.array_equal(d_map.cpu().numpy().view(np.uint32), want["map"])
+    # all outputs NULL: the results stay in the handle and materialize works
+    sb.append_batch_device(d_depth.data_ptr(), d_target.data_ptr(), 2)
+    s = sb.materialize(1)
+    assert np.array_equal(s.height, want["map"][1].astype(np.float32).reshape(-1))

@@ -41,6 +41,8 @@ struct SceneDev {
 // ball sums, a per-row "row holds a robot pixel" flag (the single-warp stamp kernels skip the 40x40 pass on robot-free
 // rows) and, per (strip, source row), the range of encoded landing rows of its terrain / robot pixels (lo | hi<<16,
 // lo > hi when there is none): the pruned stamp kernel only visits the source rows that can land in its band.
+constexpr int kLandRows = 8;   // source rows per warp: sixteen independent loads in flight per thread
+
 __global__ void __launch_bounds__(256) land_kernel(const uint16_t* __restrict__ depth,
                                                   const uint16_t* __restrict__ target, const float* __restrict__ cy_tab,
                                                   const float* __restrict__ cx_tab, SceneDev P,
@@ -49,56 +51,73 @@ __global__ void __launch_bounds__(256) land_kernel(const uint16_t* __restrict__ 
                                                   uint32_t* __restrict__ rowinfo_t, uint32_t* __restrict__ rowinfo_b) {
   const int lane = threadIdx.x;
   const int x = blockIdx.x * kStripW + lane;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kLandRows;
   const int f = blockIdx.z;
-  if (y >= P.H) return;  // whole warp
+  if (y0 >= P.H) return;  // whole warp
   const bool valid = x < P.W;
-  const int64_t npx = int64_t(P.W) * P.H;
-  int kind = kKindNone, enc = 0;
-  if (valid) {
-    // nearest texture() fetch; SURVEY §9.4: texel (x - shift, y - shift) with Repeat addressing
-    int sx = x - P.sample_shift, sy = y - P.sample_shift;
-    if (sx < 0) sx += P.W;
+  const size_t fbase = size_t(f) * P.W * P.H;
+  // nearest texture() fetch; SURVEY §9.4: texel (x - shift, y - shift) with Repeat addressing
+  int sx = x - P.sample_shift;
+  if (sx < 0) sx += P.W;
+  unsigned dv[kLandRows], tv[kLandRows];
+#pragma unroll
+  for (int r = 0; r < kLandRows; ++r) {
+    int sy = y0 + r - P.sample_shift;
     if (sy < 0) sy += P.H;
-    const int64_t src = int64_t(f) * npx + int64_t(sy) * P.W + sx;
-    const unsigned d = depth[src];
-    const unsigned tg = target[src];
-    const int cls = tg & 0xFF, id = tg >> 8;  // R8G8 little-endian upload (scene.rs:198)
-    // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
-    const float de = __fmul_rn(__fmul_rn(float(d), cy_tab[y]), cx_tab[x]);
-    // :98  int(float(height) * depth / max_depth_in)
-    const int dz = int(__fdiv_rn(__fmul_rn(float(P.H), de), P.max_depth));
-    const int py = P.H - dz;  // :114
-    int action = cls;
-    if (action > 1) action -= 1;  // :108-111
-    if (action == 0) kind = kKindTerrain;
-    else if (action == 2) kind = kKindBall;
-    else kind = kKindRobot;
-    if (kind == kKindBall) {
-      if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
-        unsigned long long* b = ball_sums + (int64_t(f) * kMaxBalls + id) * 3;
-        atomicAdd(b + 0, (unsigned long long)(long long)x);
-        atomicAdd(b + 1, (unsigned long long)(long long)py);
-        atomicAdd(b + 2, 1ull);
-      }
-    } else {
-      const int s = kind == kKindTerrain ? P.s_t : P.s_b;
-      // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
-      if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
-    }
-    enc = max(0, min(py + P.py_bias, 0x3FFF));
-    land[int64_t(f) * npx + int64_t(y) * P.W + x] = uint16_t((kind << 14) | enc);
+    const bool ok = valid && y0 + r < P.H;
+    const size_t src = fbase + size_t(sy) * P.W + sx;
+    dv[r] = ok ? unsigned(__ldg(depth + src)) : 0u;
+    tv[r] = ok ? unsigned(__ldg(target + src)) : 0u;
   }
+  const float cxv = valid ? cx_tab[x] : 0.f;
+  const float fh = float(P.H);
   const unsigned full = 0xffffffffu;
-  const unsigned t_lo = __reduce_min_sync(full, kind == kKindTerrain ? unsigned(enc) : 0xFFFFu);
-  const unsigned t_hi = __reduce_max_sync(full, kind == kKindTerrain ? unsigned(enc) : 0u);
-  const unsigned b_lo = __reduce_min_sync(full, kind == kKindRobot ? unsigned(enc) : 0xFFFFu);
-  const unsigned b_hi = __reduce_max_sync(full, kind == kKindRobot ? unsigned(enc) : 0u);
-  if (lane == 0) {
-    const int64_t ri = (int64_t(f) * gridDim.x + blockIdx.x) * P.H + y;
-    rowinfo_t[ri] = t_lo | (t_hi << 16);
-    rowinfo_b[ri] = b_lo | (b_hi << 16);
-    if (b_lo <= b_hi) atomicOr(row_robot + int64_t(f) * P.H + y, 1u);
+#pragma unroll
+  for (int r = 0; r < kLandRows; ++r) {
+    const int y = y0 + r;
+    if (y >= P.H) break;  // warp-uniform
+    int kind = kKindNone, enc = 0;
+    if (valid) {
+      const int cls = tv[r] & 0xFF, id = tv[r] >> 8;  // R8G8 little-endian upload (scene.rs:198)
+      // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
+      const float de = __fmul_rn(__fmul_rn(float(dv[r]), cy_tab[y]), cxv);
+      // :98  int(float(height) * depth / max_depth_in)
+      const int dz = int(__fdiv_rn(__fmul_rn(fh, de), P.max_depth));
+      const int py = P.H - dz;  // :114
+      int action = cls;
+      if (action > 1) action -= 1;  // :108-111
+      if (action == 0) kind = kKindTerrain;
+      else if (action == 2) kind = kKindBall;
+      else kind = kKindRobot;
+      if (kind == kKindBall) {
+        if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
+          unsigned long long* b = ball_sums + (size_t(f) * kMaxBalls + id) * 3;
+          atomicAdd(b + 0, (unsigned long long)(long long)x);
+          atomicAdd(b + 1, (unsigned long long)(long long)py);
+          atomicAdd(b + 2, 1ull);
+        }
+      } else {
+        const int s = kind == kKindTerrain ? P.s_t : P.s_b;
+        // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
+        if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
+      }
+      enc = max(0, min(py + P.py_bias, 0x3FFF));
+      land[fbase + size_t(y) * P.W + x] = uint16_t((kind << 14) | enc);
+    }
+    const unsigned t_lo = __reduce_min_sync(full, kind == kKindTerrain ? unsigned(enc) : 0xFFFFu);
+    const unsigned t_hi = __reduce_max_sync(full, kind == kKindTerrain ? unsigned(enc) : 0u);
+    const unsigned b_any = __ballot_sync(full, kind == kKindRobot);
+    unsigned b_lo = 0xFFFFu, b_hi = 0u;
+    if (b_any) {  // robot pixels are rare
+      b_lo = __reduce_min_sync(full, kind == kKindRobot ? unsigned(enc) : 0xFFFFu);
+      b_hi = __reduce_max_sync(full, kind == kKindRobot ? unsigned(enc) : 0u);
+    }
+    if (lane == 0) {
+      const size_t ri = (size_t(f) * gridDim.x + blockIdx.x) * P.H + y;
+      rowinfo_t[ri] = t_lo | (t_hi << 16);
+      rowinfo_b[ri] = b_lo | (b_hi << 16);
+      if (b_any) atomicOr(row_robot + size_t(f) * P.H + y, 1u);
+    }
   }
 }
 
@@ -425,36 +444,45 @@ __device__ __forceinline__ void pr_append(unsigned v, int y, int want_kind, int 
   }
 }
 
-// Phase A for one pixel kind: per lane, the (landing row, largest source row) entries of its column inside the band
+// Phase A for one pixel kind: per lane, the (landing row, largest source row) entries of its column inside the band.
+// Source rows are visited bottom-up in blocks of kPrChunk rows: first every lane tests kPrChunk / 32 rows' landing ranges
+// against the band (all loads of a block in flight together) and the hit rows are compacted, in descending order, into
+// `rows`; then the hit rows' land values are read eight rows at a time.
+constexpr int kPrChunk = 256;
+
 __device__ __forceinline__ int pr_collect(const uint16_t* __restrict__ L, const uint32_t* __restrict__ RI, const SceneDev& P, int x, int lane,
-                                          int want_kind, int y_min, int enc_lo, uint16_t* list) {
+                                          int want_kind, int y_min, int enc_lo, uint16_t* list, uint16_t* rows) {
   int cnt = 0;
   unsigned long long seen = 0ull;
-  const unsigned enc_hi = unsigned(enc_lo + kPrBand - 1);
-  for (int y_top = P.H - 1; y_top >= y_min; y_top -= 32) {
-    const int yl = y_top - lane;
-    bool hit = false;
-    if (yl >= y_min) {
-      const uint32_t info = __ldg(RI + yl);
-      hit = int(info & 0xFFFFu) <= int(enc_hi) && int(info >> 16) >= enc_lo;
+  const int enc_hi = enc_lo + kPrBand - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int y_blk = P.H - 1; y_blk >= y_min; y_blk -= kPrChunk) {
+    uint32_t info[kPrChunk / 32];
+#pragma unroll
+    for (int c = 0; c < kPrChunk / 32; ++c) {
+      const int yl = y_blk - 32 * c - lane;
+      info[c] = yl >= y_min ? __ldg(RI + yl) : 0x0000FFFFu;   // lo > hi: no pixel of this kind
     }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    while (m) {  // descending y, four rows in flight
-      int ys[4];
-      unsigned vs[4];
+    int total = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ys[j] = -1;
-        if (m) {
-          ys[j] = y_top - (__ffs(m) - 1);
-          m &= m - 1;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) vs[j] = (ys[j] >= 0 && x < P.W) ? unsigned(L[int64_t(ys[j]) * P.W + x]) : unsigned(kKindNone << 14);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pr_append(vs[j], ys[j], want_kind, enc_lo, seen, cnt, list, lane);
+    for (int c = 0; c < kPrChunk / 32; ++c) {
+      const bool hit = int(info[c] & 0xFFFFu) <= enc_hi && int(info[c] >> 16) >= enc_lo;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) rows[total + __popc(m & lt)] = uint16_t(y_blk - 32 * c - lane);
+      total += __popc(m);
     }
+    __syncwarp();
+    for (int k = 0; k < total; k += 8) {
+      int ys[8];
+      unsigned vs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ys[j] = k + j < total ? int(rows[k + j]) : -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vs[j] = (ys[j] >= 0 && x < P.W) ? unsigned(L[int64_t(ys[j]) * P.W + x]) : unsigned(kKindNone << 14);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pr_append(vs[j], ys[j], want_kind, enc_lo, seen, cnt, list, lane);
+    }
+    __syncwarp();
   }
   return cnt;
 }
@@ -466,6 +494,7 @@ __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __rest
                                                          SceneDev P, PrunedDev Q, uint32_t* __restrict__ staging) {
   __shared__ __align__(16) uint32_t tile[kPrTileWords];
   __shared__ uint16_t list[kPrBand * 32];
+  __shared__ uint16_t rows[kPrChunk];
   const int lane = threadIdx.x;
   const int strip = blockIdx.x / Q.nbands, band = blockIdx.x - strip * Q.nbands;
   const int f = blockIdx.y;
@@ -477,23 +506,31 @@ __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __rest
   const int64_t ri = (int64_t(f) * Q.nstrips + strip) * P.H;
   // ---- terrain (val = source row; row 0 stamps nothing: val = 0 makes every y_add NaN -> 0)
   {
-    const int cnt = pr_collect(L, rowinfo_t + ri, P, x, lane, kKindTerrain, 1, enc_lo, list);
+    const int cnt = pr_collect(L, rowinfo_t + ri, P, x, lane, kKindTerrain, 1, enc_lo, list, rows);
     const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
+    // the table row of the next entry is fetched while the current one is stamped
+    uint32_t t[kPrRowWords];
+    {
+      const uint4* tr = ttab + int64_t(cnt > 0 ? (list[lane] & 1023u) : 0u) * (kPrRowWords / 4);
+#pragma unroll
+      for (int q = 0; q < kPrRowWords / 4; ++q) {
+        const uint4 v = __ldg(tr + q);
+        t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+      }
+    }
 #pragma unroll 1
     for (int i = 0; i < maxcnt; ++i) {
       const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
       if (i < cnt) {
         const unsigned e = list[i * 32 + lane];
+        const unsigned en = list[(i + 1 < cnt ? i + 1 : i) * 32 + lane];
         const int row0 = int(e >> 10) + (kPrHalo - kPrRadius);   // tile row of dy = -8
         uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane + kPrHalo;
         const unsigned sel = (row0 & 1) ? 0x5432u : 0x7654u;
-        const uint4* tr = ttab + int64_t(e & 1023u) * (kPrRowWords / 4);
-        uint32_t t[kPrRowWords];
+        const uint4* tr = ttab + int64_t(en & 1023u) * (kPrRowWords / 4);
+        uint4 tn[kPrRowWords / 4];
 #pragma unroll
-        for (int q = 0; q < kPrRowWords / 4; ++q) {
-          const uint4 v = __ldg(tr + q);
-          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-        }
+        for (int q = 0; q < kPrRowWords / 4; ++q) tn[q] = __ldg(tr + q);
 #define PR_PRMT(a, b, s) __byte_perm(a, b, s)
 #define PR_RMW(off, w) base[off] = __vmaxu2(base[off], w)
 #define PR_SYNC() __syncwarp(active)
@@ -501,13 +538,17 @@ __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __rest
 #undef PR_PRMT
 #undef PR_RMW
 #undef PR_SYNC
+#pragma unroll
+        for (int q = 0; q < kPrRowWords / 4; ++q) {
+          t[4 * q] = tn[q].x; t[4 * q + 1] = tn[q].y; t[4 * q + 2] = tn[q].z; t[4 * q + 3] = tn[q].w;
+        }
       }
     }
   }
   // ---- robot (constant val: one stamp per (column, landing row) is enough)
   {
     __syncwarp();
-    const int cnt = pr_collect(L, rowinfo_b + ri, P, x, lane, kKindRobot, 0, enc_lo, list);
+    const int cnt = pr_collect(L, rowinfo_b + ri, P, x, lane, kKindRobot, 0, enc_lo, list, rows);
     const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
 #pragma unroll 1
     for (int i = 0; i < maxcnt; ++i) {
@@ -533,20 +574,13 @@ __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __rest
   for (int i = lane; i < kPrTileWords / 4; i += 32) out[i] = reinterpret_cast<const uint4*>(tile)[i];
 }
 
-// map cell = max over the tiles that cover it (two strips x one or two bands); pt_cloud.comp:67 border rule
-__global__ void __launch_bounds__(256) merge_kernel(const uint32_t* __restrict__ staging, SceneDev P, PrunedDev Q,
-                                                   uint32_t* __restrict__ map, int frames) {
-  const int64_t npx = int64_t(P.W) * P.H;
-  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= npx * frames) return;
-  const int f = int(idx / npx);
-  const int p = int(idx - int64_t(f) * npx);
-  const int y = p / P.W, x = p - y * P.W;
+// map cell = max over the tiles that cover it (two strips x one or two bands); pt_cloud.comp:67 border rule.
+// S = this frame's tiles viewed as u16 (two map rows per word: even tile row in the low half).
+__device__ __forceinline__ uint32_t merged_cell(const uint16_t* __restrict__ S, const SceneDev& P, const PrunedDev& Q, int x, int y) {
   uint32_t v = 0u;
   if (x > 0 && x < P.W - 1 && y > 0 && y < P.H - 1) {
-    const int s1 = (x + kPrHalo) / kStripW;          // tile columns: x - 32 s + 16 in [0, 64)
+    const int s1 = (x + kPrHalo) / kStripW;             // tile columns: x - 32 s + 16 in [0, 64)
     const int b1 = (y - Q.r_min + kPrHalo) / kPrBand;   // tile rows:    y - r_min - 64 b + 16 in [0, 96)
-    const uint16_t* S = reinterpret_cast<const uint16_t*>(staging) + int64_t(f) * Q.nstrips * Q.nbands * (2 * kPrTileWords);
 #pragma unroll
     for (int ds = 0; ds < 2; ++ds) {
       const int s = s1 - ds;
@@ -557,12 +591,25 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint32_t* __restrict__
         const int b = b1 - db;
         const int r = y - Q.r_min - b * kPrBand + kPrHalo;
         if (b < 0 || b >= Q.nbands || r >= kPrBand + 2 * kPrHalo) continue;
-        const uint32_t t = S[(int64_t(s) * Q.nbands + b) * (2 * kPrTileWords) + ((r >> 1) * kPrTileW + c) * 2 + (r & 1)];
+        const uint32_t t = __ldg(S + size_t(s * Q.nbands + b) * (2 * kPrTileWords) + ((r >> 1) * kPrTileW + c) * 2 + (r & 1));
         v = t > v ? t : v;
       }
     }
   }
-  map[idx] = v;
+  return v;
+}
+
+// stand-alone merge: only when the caller wants the map without the weights (otherwise weights_kernel merges)
+__global__ void __launch_bounds__(256) merge_kernel(const uint32_t* __restrict__ staging, SceneDev P, PrunedDev Q,
+                                                   uint32_t* __restrict__ map, int frames) {
+  const int64_t npx = int64_t(P.W) * P.H;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= npx * frames) return;
+  const int f = int(idx / npx);
+  const int p = int(idx - int64_t(f) * npx);
+  const int y = p / P.W, x = p - y * P.W;
+  const uint16_t* S = reinterpret_cast<const uint16_t*>(staging) + size_t(f) * Q.nstrips * Q.nbands * (2 * kPrTileWords);
+  map[idx] = merged_cell(S, P, Q, x, y);
 }
 
 // ------------------------------------------------------------------ weights
@@ -579,32 +626,85 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
 // neighbours: the tile (+ 1-pixel halo) of D is computed once into shared memory - 1.3 square roots per pixel instead of
 // 5 - and the 48 output bytes per pixel leave as streaming 16-byte stores (nothing reads them back on the device).
 constexpr int kWtX = 32, kWtY = 8;
+static_assert(kWtY % 2 == 0 && ((1 - kPrHalo) & 1), "the fused merge pairs map rows (odd, odd + 1) with tile words");
 
-__global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __restrict__ map, SceneDev P,
-                                                             float4* __restrict__ world, float4* __restrict__ conn0,
-                                                             float4* __restrict__ conn1) {
-  __shared__ float fld[kWtY + 2][kWtX + 2];   // literal: D[a]; intent: h[a]
+// kFromTiles: the height map does not exist yet - the block merges its cells from the pruned stamp kernel's tiles
+// (merged_cell) and also writes them to `map`, which saves the map's round trip through HBM and a launch.
+template <bool kFromTiles>
+__global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __restrict__ src, SceneDev P, PrunedDev Q,
+                                                             uint32_t* __restrict__ map_out, float4* __restrict__ world,
+                                                             float4* __restrict__ conn0, float4* __restrict__ conn1) {
+  __shared__ float fld[kWtY + 2][kWtX + 2];      // literal: D[a]; intent: h[a]
+  __shared__ uint32_t cell[kWtY + 2][kWtX + 2];  // map values of the tile + halo
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int x0 = blockIdx.x * kWtX, y0 = blockIdx.y * kWtY;
   const int f = blockIdx.z;
-  const int64_t npx = int64_t(P.W) * P.H;
-  const uint32_t* M = map + int64_t(f) * npx;
+  const size_t npx = size_t(P.W) * P.H;
+  const uint32_t* M = src + size_t(f) * npx;
+  const uint16_t* S = reinterpret_cast<const uint16_t*>(src) + size_t(f) * Q.nstrips * Q.nbands * (2 * kPrTileWords);
   const bool literal = P.weights_mode == 0;
-  const float h00 = literal ? float(M[0]) : 0.f;
-  for (int i = ty * kWtX + tx; i < (kWtY + 2) * (kWtX + 2); i += kWtX * kWtY) {
-    const int ly = i / (kWtX + 2), lx = i - ly * (kWtX + 2);
-    const int gx = x0 + lx - 1, gy = y0 + ly - 1;
-    float v = 0.f;
-    if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
-      const float h = float(M[int64_t(gy) * P.W + gx]);
-      v = literal ? dist3(float(gx), h, float(gy), 0.f, h00, 0.f) : h;
+  // world[0,0].y: cell (0,0) is on the border no stamp ever writes (pt_cloud.comp:67), so the merged value is 0
+  const float h00 = literal ? (kFromTiles ? 0.f : float(M[0])) : 0.f;
+  if (kFromTiles) {
+    // A tile word holds map rows (y, y + 1) with y odd (r_min is odd), and a block's ten rows y0 - 1 .. y0 + 8 (y0 even)
+    // are exactly five such pairs: one thread per (pair, column) merges two cells from at most four 32-bit loads.
+    const int i = ty * kWtX + tx;
+    if (i < (kWtY / 2 + 1) * (kWtX + 2)) {
+      const int pr = i / (kWtX + 2), lx = i - pr * (kWtX + 2);
+      const int gx = x0 + lx - 1, gy = y0 - 1 + 2 * pr;
+      uint32_t w = 0u;
+      if (gx > 0 && gx < P.W - 1 && gy < P.H - 1) {   // gy + 1 >= 1 always; border cells are zeroed below
+        const uint32_t* S32 = reinterpret_cast<const uint32_t*>(S);
+        const int s1 = (gx + kPrHalo) / kStripW;
+        const int b1 = (gy - Q.r_min + kPrHalo) / kPrBand;
+#pragma unroll
+        for (int ds = 0; ds < 2; ++ds) {
+          const int sidx = s1 - ds;
+          if (sidx < 0 || sidx >= Q.nstrips) continue;
+          const int c = gx - sidx * kStripW + kPrHalo;
+#pragma unroll
+          for (int db = 0; db < 2; ++db) {
+            const int b = b1 - db;
+            const int r = gy - Q.r_min - b * kPrBand + kPrHalo;
+            if (b < 0 || b >= Q.nbands || r >= kPrBand + 2 * kPrHalo) continue;
+            w = __vmaxu2(w, __ldg(S32 + size_t(sidx * Q.nbands + b) * kPrTileWords + (r >> 1) * kPrTileW + c));
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int y = gy + h;
+        const uint32_t m = (y > 0 && y < P.H - 1) ? ((w >> (16 * h)) & 0xFFFFu) : 0u;
+        float v = 0.f;
+        if (gx >= 0 && gx < P.W && y >= 0 && y < P.H) {
+          const float hh = float(m);
+          v = literal ? dist3(float(gx), hh, float(y), 0.f, h00, 0.f) : hh;
+        }
+        fld[2 * pr + h][lx] = v;
+        cell[2 * pr + h][lx] = m;
+      }
     }
-    fld[ly][lx] = v;
+  } else {
+    for (int i = ty * kWtX + tx; i < (kWtY + 2) * (kWtX + 2); i += kWtX * kWtY) {
+      const int ly = i / (kWtX + 2), lx = i - ly * (kWtX + 2);
+      const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+      float v = 0.f;
+      uint32_t m = 0u;
+      if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
+        m = __ldg(M + size_t(gy) * P.W + gx);
+        const float h = float(m);
+        v = literal ? dist3(float(gx), h, float(gy), 0.f, h00, 0.f) : h;
+      }
+      fld[ly][lx] = v;
+      cell[ly][lx] = m;
+    }
   }
   __syncthreads();
   const int x = x0 + tx, y = y0 + ty;
   if (x >= P.W || y >= P.H) return;
-  const int64_t idx = int64_t(f) * npx + int64_t(y) * P.W + x;
+  const size_t idx = size_t(f) * npx + size_t(y) * P.W + x;
+  const uint32_t mine = cell[ty + 1][tx + 1];
+  if (kFromTiles) map_out[idx] = mine;
   auto F = [&](int dx, int dy) { return fld[ty + 1 + dy][tx + 1 + dx]; };
   // weight of the link from pixel a = p + (adx, ady) (the "pos" of the shader invocation) to b = p + (bdx, bdy)
   auto link = [&](int adx, int ady, int bdx, int bdy) {
@@ -612,7 +712,7 @@ __global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __
     return dist3(float(x + adx), F(adx, ady), float(y + ady), float(x + bdx), F(bdx, bdy), float(y + bdy));
   };
   const bool nxmin = x > 0, nxmax = x < P.W - 1, nymin = y > 0, nymax = y < P.H - 1;
-  if (world) __stcs(world + idx, make_float4(float(x), float(M[int64_t(y) * P.W + x]), float(y), 0.f));  // :59-69
+  if (world) __stcs(world + idx, make_float4(float(x), float(mine), float(y), 0.f));  // :59-69
   if (conn1) {  // :86-107  (below, below-left, left, above-left)
     float4 c;
     c.x = nymax ? link(0, 0, 0, 1) : -1.f;
@@ -992,7 +1092,7 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(n) * kMaxBalls * 3 * sizeof(unsigned long long), st));
   const unsigned blocks = unsigned((npx * n + 255) / 256);
   const int nstrips = (P.W + kStripW - 1) / kStripW;
-  land_kernel<<<dim3(nstrips, (P.H + 7) / 8, n), dim3(32, 8), 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums,
+  land_kernel<<<dim3(nstrips, (P.H + 8 * kLandRows - 1) / (8 * kLandRows), n), dim3(32, 8), 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums,
                                                                         s->rowinfo_t, s->rowinfo_b);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[0], st));
   dim3 grid(nstrips, n);
@@ -1000,10 +1100,14 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   // 2 = single-warp packed kernel (bump size 10), 3 = single-warp generic kernel.  A handle whose bump tables lack the
   // structure a kernel relies on falls through to the next one; all four produce the same bytes.
   const int impl_env = s->stamp_impl;   // read from the environment when the handle was created
+  const bool want_weights = d_world || d_conn0 || d_conn1;
+  const dim3 wgrid((P.W + kWtX - 1) / kWtX, (P.H + kWtY - 1) / kWtY, n), wblock(kWtX, kWtY);
+  bool merged_in_weights = false;
   if (impl_env <= 0 && s->pruned_ok) {
     stamp_pruned_kernel<<<dim3(nstrips * s->pruned.nbands, n), 32, 0, st>>>(s->land, s->rowinfo_t, s->rowinfo_b, s->ttab, s->btab, s->bspan, P,
                                                                               s->pruned, s->staging);
-    merge_kernel<<<blocks, 256, 0, st>>>(s->staging, P, s->pruned, d_map, n);
+    if (want_weights) merged_in_weights = true;
+    else merge_kernel<<<blocks, 256, 0, st>>>(s->staging, P, s->pruned, d_map, n);
   } else if (impl_env <= 1 && s->atomic_smem)
     stamp_atomic_kernel<<<grid, kAtomWarps * 32, s->atomic_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
   else if (impl_env <= 2 && s->lut_pack)
@@ -1011,9 +1115,12 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   else
     stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[1], st));
-  if (d_world || d_conn0 || d_conn1)
-    weights_kernel<<<dim3((P.W + kWtX - 1) / kWtX, (P.H + kWtY - 1) / kWtY, n), dim3(kWtX, kWtY), 0, st>>>(
-        d_map, P, reinterpret_cast<float4*>(d_world), reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
+  if (merged_in_weights)
+    weights_kernel<true><<<wgrid, wblock, 0, st>>>(s->staging, P, s->pruned, d_map, reinterpret_cast<float4*>(d_world),
+                                                   reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
+  else if (want_weights)
+    weights_kernel<false><<<wgrid, wblock, 0, st>>>(d_map, P, s->pruned, nullptr, reinterpret_cast<float4*>(d_world),
+                                                    reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[2], st));
   if (d_balls) balls_kernel<<<(n * kMaxBalls + 127) / 128, 128, 0, st>>>(s->ball_sums, d_balls, n * kMaxBalls);
   TOD_CUDA(cudaGetLastError());

@@ -62,7 +62,10 @@ class SceneBuilder:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().tod_scene_destroy(self._h)
+            try:
+                lib().tod_scene_destroy(self._h)
+            except Exception:  # interpreter shutdown: the module globals may already be gone
+                pass
             self._h = None
 
     __del__ = close
