@@ -92,13 +92,16 @@ void tod_scene_destroy(tod_scene* s);
 int tod_scene_append_batch(tod_scene* s, const uint16_t* depth, const uint16_t* target, int n, uint32_t* map,
                            float* world4, float* conn0, float* conn1, float* balls4);
 
-/* Same, device pointers, asynchronous on `stream` (a cudaStream_t; NULL = the handle's stream). */
+/* Same, device pointers, asynchronous on `stream` (a cudaStream_t; NULL = the handle's stream).  Output pointers that
+ * are NULL are skipped, except that with ALL five NULL the results are kept in the handle's own images (that is what
+ * tod_scene_materialize reads).  One handle serves one stream at a time (shared scratch buffers). */
 int tod_scene_append_batch_device(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n,
                                   uint32_t* d_map, float* d_world4, float* d_conn0, float* d_conn1,
                                   float* d_balls4, void* stream);
 
-/* `Scene` materialisation (scene.rs:312-327), fused on the device: from the device-resident results of
- * the last append call for frame `frame`, fills host buffers
+/* `Scene` materialisation (scene.rs:312-327), fused on the device: from the results the last append call left in the
+ * handle's own images (tod_scene_append_batch, or tod_scene_append_batch_device with all outputs NULL; after a device
+ * call that wrote to caller buffers this returns TOD_ERR_INVALID_ARG) for frame `frame`, fills host buffers
  *   height f32[H*W], pos f32[H*W][3], balls i32[100][2], connections f32[H*W][8]. */
 int tod_scene_materialize(tod_scene* s, int frame, float* height, float* pos3, int32_t* balls2,
                           float* connections8);
@@ -163,6 +166,8 @@ int tod_yolact_last_diverged(tod_yolact* y, int* diverged);
 
 /* Model introspection (what interpreter.tensor_info gives the reference, yolact.rs:150,169-176) */
 int tod_yolact_num_outputs(const tod_yolact* y);
+/* shape of the model input [1, tile_h, tile_w, 3] (the dims classify_tile checks, yolact.rs:149-158) */
+int tod_yolact_input_info(const tod_yolact* y, int32_t shape4[4]);
 int tod_yolact_output_info(const tod_yolact* y, int index, int32_t shape4[4], float* scale, int32_t* zero_point,
                            int32_t* elems);
 int tod_yolact_num_tensors(const tod_yolact* y);
@@ -193,13 +198,22 @@ typedef struct tod_detections {
  * Returns TOD_OK, or TOD_WARN_REFERENCE_DIVERGES if id_mode == 0 and some tile would hang the reference. */
 int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8,
                            uint32_t* tile_classes, tod_detections* dets);
+/* Same call with one more output: cell_classes (may be NULL) u32[n][28][28] is the packed (class, id) grid *before* the
+ * 8x8 nearest replication of yolact.rs:127-128 - tile_classes[t][y][x] == cell_classes[t][y / 8][x / 8] - i.e. the same
+ * information in 1/64 of the read-back (12.8 MB -> 0.2 MB per 64 tiles).  A frame loop that only needs the classes
+ * passes tile_classes = NULL. */
+int tod_yolact_infer_tiles_cells(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8,
+                                 uint32_t* tile_classes, uint32_t* cell_classes, tod_detections* dets);
 
 /* Output k of the last call dequantised on the GPU exactly as the reference does for its `results: Vec<Vec<f32>>`
  * (yolact.rs:169-188): out[t][e] = scale * ((u8 as i32 - zero_point) as f32), f32[n][elems_k]. */
 int tod_yolact_fetch_output_f32(tod_yolact* y, int index, int n, float* out);
 
 /* Device-resident form used by the fused RGB-D pipeline and the benchmark: input tiles already on the GPU;
- * results stay on the GPU (fetch with tod_yolact_fetch_*).  Asynchronous on `stream`. */
+ * results stay on the GPU (fetch with tod_yolact_fetch_*).  Asynchronous on `stream` (NULL = the handle's own).
+ * A handle serves ONE stream at a time (its activation arena and scratch buffers are shared): do not drive one handle
+ * from two streams concurrently.  tod_yolact_fetch_* copy on the handle's own stream, which the library orders behind
+ * the caller's stream (an event recorded at the end of this call); they block until the data is on the host. */
 int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int n, void* stream);
 int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out);
 int tod_yolact_fetch_tensor(tod_yolact* y, int tensor, int n, void* out, size_t out_bytes);
@@ -212,6 +226,32 @@ int tod_yolact_stats(const tod_yolact* y, int64_t* macs_per_tile, int32_t* launc
 /* times every op of the graph once with CUDA events for n resident tiles: fills up to `cap` entries of
  * ms[] (per op, graph order) and returns the op count */
 int tod_yolact_profile_ops(tod_yolact* y, int n, float* ms, int32_t* kinds, int cap);
+
+/* ======================================================================================
+ * Pool: the frame sharder.  Independent frames / tiles are cut into contiguous ranges, ceil(n / G) per
+ * GPU; every GPU runs `depth` Yolact handles, one host thread each, that take the range's chunks (<= max_tiles tiles)
+ * in turn, so a chunk's copies and tail overlap the next chunk's backbone.  Results land in the caller's buffers at
+ * the frame's index; a frame's bytes do not depend on the number of GPUs or handles.  No collective, no NCCL.
+ * Replaces the reference's one-frame-at-a-time loops (scene.rs:77-119 `process_scene`, main.rs:78-96 `manage`)
+ * for a box with several GPUs; with one GPU it is the pipelined (double-buffered) form of the single-handle calls.
+ * ====================================================================================== */
+typedef struct tod_pool tod_pool;
+/* devices == NULL or n_devices <= 0: every visible sm_100 device.  opts as for tod_yolact_create (max_tiles = chunk size). */
+int tod_pool_create(const char* tflite_path, const int32_t* devices, int n_devices, int depth,
+                    const tod_yolact_options* opts, tod_pool** out);
+void tod_pool_destroy(tod_pool* p);
+int tod_pool_num_devices(const tod_pool* p);
+int tod_pool_num_handles(const tod_pool* p);
+/* tod_yolact_infer_tiles_cells over any n (same buffers, n tiles long) */
+int tod_pool_infer_tiles(tod_pool* p, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8, uint32_t* tile_classes,
+                         uint32_t* cell_classes, tod_detections* dets);
+/* tod_yolact_classify_batch over any n: <- Yolact::classify (yolact.rs:39) for every frame, in place */
+int tod_pool_classify_batch(tod_pool* p, uint32_t* frames, int n, int width, int height);
+/* The fused RGB-D frame loop for n frames (scene.rs:84-97 feeding scene.rs:147-331): classify in place, target = low
+ * 16 bits (scene.rs:93) kept on the GPU, then pt_cloud + pt_cloud_weights.  frames u32[n][H][W] in/out, depth
+ * u16[n][H][W]; outputs as tod_scene_append_batch (any may be NULL). */
+int tod_pool_rgbd_batch(tod_pool* p, const tod_scene_params* scene_params, uint32_t* frames, const uint16_t* depth, int n,
+                        uint32_t* map, float* world4, float* conn0, float* conn1, float* balls4);
 
 /* ======================================================================================
  * Micro-benchmark used as the int8 roofline denominator (MEASURED_PEAKS.json has no int8 peak,

@@ -23,16 +23,18 @@ def _worker(rank, world, port, n, q):
     import torch.distributed as dist
     import tod_b200
     from tod_b200 import shard
+    from tests import dist_helpers
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     frames = np.arange(n * 5, dtype=np.int64).reshape(n, 5)          # stand-in for per-frame results
     lo, hi = shard.shard_range(n, world, rank)
     mine = frames[lo:hi] * 2 + 1                                       # "process" this rank's shard
-    gathered = shard.gather_frames(mine, n, world, rank)               # host-side gather, rank 0 only
-    ms = shard.max_over_ranks(10.0 + rank)                             # bench.py's max-over-ranks timing
+    gathered = dist_helpers.gather_frames(mine, n, world, rank)               # host-side gather, rank 0 only
+    ms = dist_helpers.max_over_ranks(10.0 + rank)
+    same = dist_helpers.all_equal_over_ranks(1234567) and not dist_helpers.all_equal_over_ranks(1000 + rank)                             # bench.py's max-over-ranks timing
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, None if gathered is None else gathered.tolist(), ms))
+    q.put((rank, None if gathered is None else gathered.tolist(), ms, same))
 
 
 def test_two_rank_gloo_gather_is_order_independent():
@@ -53,3 +55,4 @@ def test_two_rank_gloo_gather_is_order_independent():
     want = (np.arange(n * 5, dtype=np.int64).reshape(n, 5) * 2 + 1).tolist()
     assert res[0][1] == want and res[1][1] is None
     assert res[0][2] == res[1][2] == 11.0
+    assert res[0][3] and res[1][3]

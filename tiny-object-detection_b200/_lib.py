@@ -22,10 +22,12 @@ SYMBOLS = [
     "tod_yolact_default_options", "tod_yolact_create", "tod_yolact_destroy", "tod_yolact_classify",
     "tod_yolact_classify_batch", "tod_yolact_classify_batch_device", "tod_model_inspect", "tod_yolact_set_priors",
     "tod_yolact_last_diverged", "tod_yolact_num_outputs", "tod_yolact_output_info", "tod_yolact_num_tensors",
-    "tod_yolact_num_ops", "tod_yolact_tensor_info", "tod_yolact_infer_tiles", "tod_yolact_infer_tiles_device",
+    "tod_yolact_num_ops", "tod_yolact_tensor_info", "tod_yolact_infer_tiles", "tod_yolact_infer_tiles_cells", "tod_yolact_infer_tiles_device",
     "tod_yolact_fetch_output", "tod_yolact_fetch_tensor", "tod_yolact_fetch_tile_classes", "tod_yolact_fetch_detections",
     "tod_yolact_stats", "tod_yolact_profile_ops", "tod_i8_gemm_selftest", "tod_conv_selftest",
     "tod_conv_selftest_ex", "tod_i8_mma_peak", "tod_yolact_step_macs", "tod_yolact_trace_steps", "tod_yolact_fetch_output_f32",
+    "tod_yolact_input_info", "tod_pool_create", "tod_pool_destroy", "tod_pool_num_devices", "tod_pool_num_handles",
+    "tod_pool_infer_tiles", "tod_pool_classify_batch", "tod_pool_rgbd_batch",
 ]
 
 
@@ -93,6 +95,7 @@ def lib():
         L.tod_yolact_output_info.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.tod_yolact_tensor_info.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.tod_yolact_infer_tiles.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+        L.tod_yolact_infer_tiles_cells.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
         L.tod_yolact_infer_tiles_device.argtypes = [vp, vp, C.c_int, vp]
         L.tod_yolact_fetch_output.argtypes = [vp, C.c_int, C.c_int, vp]
         L.tod_yolact_fetch_tensor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
@@ -107,6 +110,15 @@ def lib():
         L.tod_yolact_step_macs.argtypes = [vp, vp, C.c_int]
         L.tod_yolact_trace_steps.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
         L.tod_yolact_fetch_output_f32.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.tod_yolact_input_info.argtypes = [vp, vp]
+        L.tod_pool_create.argtypes = [C.c_char_p, vp, C.c_int, C.c_int, vp, vp]
+        L.tod_pool_destroy.argtypes = [vp]
+        L.tod_pool_destroy.restype = None
+        L.tod_pool_num_devices.argtypes = [vp]
+        L.tod_pool_num_handles.argtypes = [vp]
+        L.tod_pool_infer_tiles.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+        L.tod_pool_classify_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.tod_pool_rgbd_batch.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -19,7 +19,8 @@ namespace {
 //                                     reference never returns; intent: 4-connected components)
 //   yolact.rs:127-128  pack + 8x nearest replicate
 __global__ void __launch_bounds__(1024) seg_post_kernel(const uint8_t* __restrict__ seg, int64_t ts, SegPost P,
-                                                       uint32_t* __restrict__ out, int* __restrict__ diverges) {
+                                                       uint32_t* __restrict__ out, uint32_t* __restrict__ cells_out,
+                                                       int* __restrict__ diverges) {
   __shared__ uint8_t s_cls[1024];
   __shared__ int s_label[1024];
   __shared__ uint32_t s_val[1024];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(1024) seg_post_kernel(const uint8_t* __restric
     else v = (uint32_t(cls) << 24) | ((idu & 0xFFu) << 16);
   }
   s_val[tid] = v;
+  if (tid < cells && cells_out) cells_out[int64_t(t) * cells + tid] = v;   // the grid before the 8x replication
   __syncthreads();
   const int OW = P.gw * P.up, OH = P.gh * P.up;
   uint32_t* o = out + int64_t(t) * OW * OH;
@@ -649,10 +651,10 @@ inline int next_pow2(int v) {
 
 }  // namespace
 
-void launch_seg_postprocess(const uint8_t* seg, int64_t ts, int tiles, const SegPost& p, uint32_t* out, int* diverges,
-                            cudaStream_t s) {
+void launch_seg_postprocess(const uint8_t* seg, int64_t ts, int tiles, const SegPost& p, uint32_t* out, uint32_t* cells_out,
+                            int* diverges, cudaStream_t s) {
   cudaMemsetAsync(diverges, 0, sizeof(int) * tiles, s);
-  seg_post_kernel<<<tiles, 1024, 0, s>>>(seg, ts, p, out, diverges);
+  seg_post_kernel<<<tiles, 1024, 0, s>>>(seg, ts, p, out, cells_out, diverges);
 }
 
 void launch_classify_pre(const uint32_t* frames, int n, int W, int H, const ResampleAxis& vert, const ResampleAxis& horz,

@@ -19,7 +19,7 @@ struct SegPost {
 // seg: u8 [tiles][gh][gw][ch] (tile stride in bytes); out: u32 [tiles][gh*up][gw*up];
 // diverges: int[tiles], set to 1 where the reference's flood fill would not terminate.
 void launch_seg_postprocess(const uint8_t* seg, int64_t tile_stride, int tiles, const SegPost& p, uint32_t* out,
-                            int* diverges, cudaStream_t s);
+                            uint32_t* cells_out, int* diverges, cudaStream_t s);
 
 // ---------------------------------------------------------------- Triangle resampling
 constexpr int kMaxTaps = 8;

@@ -147,6 +147,8 @@ int read_tflite(const char* path, Graph* g) {
 
   const size_t tv = sg.vec(0);
   const uint32_t nt = vec_len(b, tv);
+  // every vector element occupies at least four bytes of the file: a count beyond that is a corrupt length, not a model
+  if (size_t(nt) > g->blob.size() / 4) return fail(TOD_ERR_MODEL, "tensor count %u exceeds what a %zu-byte file can hold", nt, g->blob.size());
   g->tensors.resize(nt);
   for (uint32_t i = 0; i < nt && !b.bad; ++i) {
     const Table t = vec_table(b, tv, i);
@@ -183,6 +185,7 @@ int read_tflite(const char* path, Graph* g) {
 
   const size_t ov = sg.vec(3);
   const uint32_t no = vec_len(b, ov);
+  if (size_t(no) > g->blob.size() / 4) return fail(TOD_ERR_MODEL, "operator count %u exceeds what a %zu-byte file can hold", no, g->blob.size());
   g->ops.resize(no);
   for (uint32_t i = 0; i < no && !b.bad; ++i) {
     const Table o = vec_table(b, ov, i);

@@ -166,6 +166,10 @@ struct tod_yolact {
   // literal post-processing
   int seg_out = -1;
   uint32_t* d_tile_classes = nullptr;  // [max_tiles][th][tw]
+  uint32_t* d_cell_classes = nullptr;  // [max_tiles][gh][gw]: the same values before the 8x replication of yolact.rs:127-128
+  cudaEvent_t caller_done = nullptr;   // recorded on a caller's stream: later fetches on the handle's stream wait for it
+  cudaEvent_t done_ev = nullptr, done_ev2 = nullptr;  // blocking-sync events: a waiting host thread sleeps instead of spinning
+  bool spin_sync = false;              // TOD_SPIN_SYNC=1: cudaStreamSynchronize (lower wake-up latency, burns a core per waiting thread)
   int* d_diverges = nullptr;
   int* h_diverges = nullptr;           // pinned
   // detection
@@ -212,6 +216,29 @@ int plan(tod_yolact* y, ConstArena* arena) {
 
   for (int t : G.outputs)
     if (t < 0 || t >= nt) return fail(TOD_ERR_MODEL, "graph output %d out of range", t);
+  if (G.inputs.empty() || G.inputs[0] < 0 || G.inputs[0] >= nt) return fail(TOD_ERR_MODEL, "graph input index out of range");
+  for (size_t i = 0; i < G.ops.size(); ++i) {
+    const GOp& op = G.ops[i];
+    if (op.outputs.empty() || op.inputs.empty()) return fail(TOD_ERR_MODEL, "operator %zu has no inputs or no outputs", i);
+    for (int t : op.outputs)
+      if (t < 0 || t >= nt) return fail(TOD_ERR_MODEL, "operator %zu: output tensor index %d out of range", i, t);
+    for (int t : op.inputs)
+      if (t >= nt || t < -1) return fail(TOD_ERR_MODEL, "operator %zu: input tensor index %d out of range", i, t);
+    if (op.inputs[0] < 0) return fail(TOD_ERR_MODEL, "operator %zu: first input is absent", i);
+    if (op.code == kConcat)
+      for (int t : op.inputs)
+        if (t < 0) return fail(TOD_ERR_MODEL, "CONCATENATION operator %zu: absent input", i);
+    if ((op.code == kConv2D || op.code == kDepthwise || op.code == kPad || op.code == kAdd) && (op.inputs.size() < 2 || op.inputs[1] < 0))
+      return fail(TOD_ERR_MODEL, "operator %zu: second input is absent", i);
+  }
+  for (int t = 0; t < nt; ++t) {   // dimension products must stay far from int64 overflow
+    double prod = 1.0;
+    for (int d = 0; d < 4; ++d) {
+      if (G.tensors[t].dims[d] < 0) return fail(TOD_ERR_MODEL, "tensor %d has a negative dimension", t);
+      prod *= double(G.tensors[t].dims[d] > 0 ? G.tensors[t].dims[d] : 1);
+    }
+    if (prod > 1e12) return fail(TOD_ERR_MODEL, "tensor %d is implausibly large", t);
+  }
   const GTensor& in0 = G.tensors[G.inputs[0]];
   if (in0.type != kU8 || in0.dims[0] != 1 || in0.dims[3] != 3)
     return fail(TOD_ERR_MODEL, "expected a uint8 [1,H,W,3] input (yolact.rs:143-153), got type %d [%d,%d,%d,%d]", in0.type, in0.dims[0],
@@ -1036,7 +1063,7 @@ int enqueue_post(tod_yolact* y, int n, bool dets, int masks, cudaStream_t s) {
     const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
     const Place& ps = y->place[y->graph.outputs[y->seg_out]];
     SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
-    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, s);
+    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_cell_classes, y->d_diverges, s);
   }
   if (dets) {
     const Place& pc = y->place[y->graph.outputs[y->o_cls]];
@@ -1143,7 +1170,7 @@ int enqueue_all_parallel(tod_yolact* y, int n, bool dets, int masks, cudaStream_
     const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
     const Place& ps = y->place[y->graph.outputs[y->seg_out]];
     SegPost p{S.dims[1], S.dims[2], S.dims[3], S.scale(), S.zp(), y->opt.id_mode, y->tile_w() / S.dims[2]};
-    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_diverges, y->lanes[lane]);
+    launch_seg_postprocess(ps.base, ps.tile_stride, n, p, y->d_tile_classes, y->d_cell_classes, y->d_diverges, y->lanes[lane]);
     // an external event node: the host-facing call starts copying the class maps back as soon as they exist
     if (y->trace_events.empty()) TOD_CUDA(cudaEventRecordWithFlags(y->seg_ready, y->lanes[lane], cudaEventRecordExternal));
     else TOD_CUDA(cudaEventRecord(y->seg_ready, y->lanes[lane]));  // tod_yolact_trace_steps runs outside a capture
@@ -1233,6 +1260,7 @@ ResampleAxis axis_of(const AxisTables& t) { return ResampleAxis{t.d_left, t.d_co
 int ensure_classify_buffers(tod_yolact* y, int W, int H) {
   if (y->cw == W && y->chh == H) return TOD_OK;
   if (W < 2 || H < 2 || W > 8192 || H > 8192) return fail(TOD_ERR_INVALID_ARG, "classify: unsupported frame size %dx%d", W, H);
+  y->cw = y->chh = 0;   // nothing below is valid for the old size any more; set again only when everything succeeded
   const int tw = y->tile_w(), th = y->tile_h();
   TOD_TRY(build_axis(H, th, &y->pre_v));       // 640x480 -> 448x224 (yolact.rs:208): vertical pass first
   TOD_TRY(build_axis(W, 2 * tw, &y->pre_h));
@@ -1267,13 +1295,46 @@ int classify_device(tod_yolact* y, uint32_t* d_frames, int n, int W, int H, uint
   return TOD_OK;
 }
 
-int check_diverged(tod_yolact* y, int tiles, cudaStream_t s) {
+// Host-facing calls block like the reference's (`invoke()`, `future.wait`).  The wait sleeps on a blocking-sync event
+// instead of spinning in cudaStreamSynchronize: a frame loop keeps several handles / GPUs busy from a few host threads,
+// and a spinning waiter per handle starves them once threads outnumber cores (8 ranks x 3 handles on 16 cores).
+int wait_stream(tod_yolact* y, cudaStream_t s, cudaEvent_t ev) {
+  if (y->spin_sync) {
+    TOD_CUDA(cudaStreamSynchronize(s));
+    return TOD_OK;
+  }
+  TOD_CUDA(cudaEventRecord(ev, s));
+  TOD_CUDA(cudaEventSynchronize(ev));
+  return TOD_OK;
+}
+
+// A device-resident call may run on a caller's stream; tod_yolact_fetch_* copy on the handle's own stream, which is made
+// to follow the caller's work here (one handle still serves one stream at a time: its scratch buffers are shared).
+int order_after_caller(tod_yolact* y, cudaStream_t s) {
+  if (s == y->stream) return TOD_OK;
+  TOD_CUDA(cudaEventRecord(y->caller_done, s));
+  TOD_CUDA(cudaStreamWaitEvent(y->stream, y->caller_done, 0));
+  return TOD_OK;
+}
+
+int enqueue_diverged(tod_yolact* y, int tiles, cudaStream_t s) {
   if (y->opt.id_mode != 0 || y->seg_out < 0) return TOD_OK;
   TOD_CUDA(cudaMemcpyAsync(y->h_diverges, y->d_diverges, sizeof(int) * tiles, cudaMemcpyDeviceToHost, s));
-  TOD_CUDA(cudaStreamSynchronize(s));
+  return TOD_OK;
+}
+
+int read_diverged(const tod_yolact* y, int tiles) {
+  if (y->opt.id_mode != 0 || y->seg_out < 0) return TOD_OK;
   for (int i = 0; i < tiles; ++i)
     if (y->h_diverges[i]) return TOD_WARN_REFERENCE_DIVERGES;
   return TOD_OK;
+}
+
+int check_diverged(tod_yolact* y, int tiles, cudaStream_t s) {
+  if (y->opt.id_mode != 0 || y->seg_out < 0) return TOD_OK;
+  TOD_TRY(enqueue_diverged(y, tiles, s));
+  TOD_TRY(wait_stream(y, s, y->done_ev));
+  return read_diverged(y, tiles);
 }
 
 }  // namespace
@@ -1333,7 +1394,10 @@ void tod_yolact_destroy(tod_yolact* y) {
     cudaFree(t->d_left); cudaFree(t->d_count); cudaFree(t->d_weight);
   }
   cudaFree(y->d_tmp); cudaFree(y->d_frames); cudaFree(y->d_tiles_rgb);
-  cudaFree(y->d_tile_classes); cudaFree(y->d_diverges); cudaFree(y->d_tile_bits);
+  cudaFree(y->d_tile_classes); cudaFree(y->d_cell_classes); cudaFree(y->d_diverges); cudaFree(y->d_tile_bits);
+  if (y->caller_done) cudaEventDestroy(y->caller_done);
+  if (y->done_ev) cudaEventDestroy(y->done_ev);
+  if (y->done_ev2) cudaEventDestroy(y->done_ev2);
   if (y->h_diverges) cudaFreeHost(y->h_diverges);
   cudaFree(y->d_const); cudaFree(y->d_act);
   if (y->copy_stream) cudaStreamDestroy(y->copy_stream);
@@ -1384,7 +1448,13 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
       raw->seg_out = 4;
   }
   const size_t mt = size_t(o.max_tiles);
-  if ((ce = cudaMalloc(&raw->d_tile_classes, mt * raw->tile_w() * raw->tile_h() * 4)) != cudaSuccess ||
+  raw->spin_sync = std::getenv("TOD_SPIN_SYNC") && std::atoi(std::getenv("TOD_SPIN_SYNC")) != 0;
+  if ((ce = cudaEventCreateWithFlags(&raw->caller_done, cudaEventDisableTiming)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&raw->done_ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&raw->done_ev2, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess)
+    return bail(fail(TOD_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce)));
+  if ((ce = cudaMalloc(&raw->d_cell_classes, mt * 1024 * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&raw->d_tile_classes, mt * raw->tile_w() * raw->tile_h() * 4)) != cudaSuccess ||
       (ce = cudaMalloc(&raw->d_diverges, mt * sizeof(int))) != cudaSuccess ||
       (ce = cudaMallocHost(&raw->h_diverges, mt * sizeof(int))) != cudaSuccess)
     return bail(fail(TOD_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(ce)));
@@ -1430,6 +1500,11 @@ int tod_yolact_tensor_info(const tod_yolact* y, int tensor, int32_t shape4[4], i
   return TOD_OK;
 }
 
+int tod_yolact_input_info(const tod_yolact* y, int32_t shape4[4]) {
+  if (!y || !shape4) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_input_info: null argument");
+  return tod_yolact_tensor_info(y, y->graph.inputs[0], shape4, nullptr, nullptr, nullptr, nullptr);
+}
+
 int tod_yolact_output_info(const tod_yolact* y, int index, int32_t shape4[4], float* scale, int32_t* zero_point, int32_t* elems) {
   if (!y || index < 0 || index >= int(y->graph.outputs.size())) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_output_info: bad output index");
   return tod_yolact_tensor_info(y, y->graph.outputs[index], shape4, nullptr, scale, zero_point, elems);
@@ -1445,7 +1520,8 @@ int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int
                              cudaMemcpyDeviceToDevice, s));
   const bool dets = y->det_ready && y->have_priors;
   y->last_mask_mode = dets ? 2 : 0;
-  return run_pipeline(y, n, dets, dets ? 2 : 0, s);
+  TOD_TRY(run_pipeline(y, n, dets, dets ? 2 : 0, s));
+  return order_after_caller(y, s);
 }
 
 int tod_yolact_fetch_output(tod_yolact* y, int index, int n, uint8_t* out) {
@@ -1518,14 +1594,14 @@ int tod_yolact_last_diverged(tod_yolact* y, int* diverged) {
   return TOD_OK;
 }
 
-int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
-  if (!y || !d) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: null argument");
+static int enqueue_fetch_detections(tod_yolact* y, int n, tod_detections* d, cudaStream_t s) {
   if (!y->det_ready) return fail(TOD_ERR_UNSUPPORTED, "this model's outputs do not form a YOLACT detection head");
   if (n < 1 || n > y->last_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: n=%d but the last call ran %d tiles", n, y->last_tiles);
   const DetectCfg& c = y->dcfg;
   if (d->max_dets != c.max_dets) return fail(TOD_ERR_INVALID_ARG, "tod_detections.max_dets=%d, handle was created with %d", d->max_dets, c.max_dets);
-  TOD_CUDA(cudaSetDevice(y->device));
-  cudaStream_t s = y->stream;
+  if (d->masks && y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute float masks");
+  if ((d->masks_bin || d->masks_bits) && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
+  if (d->masks_tile_bits && y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: tile-resolution masks need the float masks of the last call");
   const size_t nd = size_t(n) * c.max_dets;
   const DetectBuffers& b = y->dbuf;
   if (d->count) TOD_CUDA(cudaMemcpyAsync(d->count, b.det_count, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
@@ -1533,28 +1609,30 @@ int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
   if (d->scores) TOD_CUDA(cudaMemcpyAsync(d->scores, b.det_score, nd * 4, cudaMemcpyDeviceToHost, s));
   if (d->classes) TOD_CUDA(cudaMemcpyAsync(d->classes, b.det_class, nd * 4, cudaMemcpyDeviceToHost, s));
   if (d->priors) TOD_CUDA(cudaMemcpyAsync(d->priors, b.det_prior, nd * 4, cudaMemcpyDeviceToHost, s));
-  if (d->masks && y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute float masks");
-  if (d->masks_bin && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
   if (d->masks) TOD_CUDA(cudaMemcpyAsync(d->masks, b.masks, nd * c.ph * c.pw * 4, cudaMemcpyDeviceToHost, s));
-  if (d->masks_bits && y->last_mask_mode < 1) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: the last call did not compute masks");
   if (d->masks_bits) TOD_CUDA(cudaMemcpyAsync(d->masks_bits, b.masks_bits, nd * size_t((c.ph * c.pw + 31) / 32) * 4, cudaMemcpyDeviceToHost, s));
   if (d->masks_bin) TOD_CUDA(cudaMemcpyAsync(d->masks_bin, b.masks_bin, nd * c.ph * c.pw, cudaMemcpyDeviceToHost, s));
   if (d->masks_tile_bits) {
-    if (y->last_mask_mode < 2) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: tile-resolution masks need the float masks of the last call");
     const size_t words = size_t(y->tile_h() * y->tile_w() + 31) / 32;
     if (!y->d_tile_bits) TOD_CUDA(cudaMalloc(&y->d_tile_bits, size_t(y->opt.max_tiles) * c.max_dets * words * 4));
     TOD_TRY(launch_mask_upsample(c, b, n, y->tile_h(), y->tile_w(), y->d_tile_bits, s));
     TOD_CUDA(cudaMemcpyAsync(d->masks_tile_bits, y->d_tile_bits, nd * words * 4, cudaMemcpyDeviceToHost, s));
   }
-  TOD_CUDA(cudaStreamSynchronize(s));
   return TOD_OK;
 }
 
-int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8, uint32_t* tile_classes,
-                           tod_detections* dets) {
+int tod_yolact_fetch_detections(tod_yolact* y, int n, tod_detections* d) {
+  if (!y || !d) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_fetch_detections: null argument");
+  TOD_CUDA(cudaSetDevice(y->device));
+  TOD_TRY(enqueue_fetch_detections(y, n, d, y->stream));
+  return wait_stream(y, y->stream, y->done_ev);
+}
+
+int tod_yolact_infer_tiles_cells(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8, uint32_t* tile_classes,
+                                 uint32_t* cell_classes, tod_detections* dets) {
   if (!y || !rgb_tiles) return fail(TOD_ERR_INVALID_ARG, "tod_yolact_infer_tiles: null argument");
   if (n < 1 || n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "tod_yolact_infer_tiles: n=%d outside [1,%d]", n, y->opt.max_tiles);
-  if (tile_classes && y->seg_out < 0) return fail(TOD_ERR_UNSUPPORTED, "the model has no segmentation output #4");
+  if ((tile_classes || cell_classes) && y->seg_out < 0) return fail(TOD_ERR_UNSUPPORTED, "the model has no segmentation output #4");
   TOD_CUDA(cudaSetDevice(y->device));
   cudaStream_t s = y->stream;
   const Place& pin = y->place[y->graph.inputs[0]];
@@ -1567,17 +1645,27 @@ int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8
   if (outputs_u8)
     for (size_t k = 0; k < y->graph.outputs.size(); ++k)
       if (outputs_u8[k]) TOD_TRY(fetch_strided(outputs_u8[k], y->place[y->graph.outputs[k]], n, s));
-  if (tile_classes) {
-    // the class maps are final as soon as seg_post_kernel has run (the graph records y->seg_ready right behind it):
-    // read them back on a second stream while boxes / NMS / masks are still being computed
-    cudaStream_t cs = (y->opt.use_cuda_graph && y->seg_out >= 0) ? y->copy_stream : s;
-    if (cs != s) TOD_CUDA(cudaStreamWaitEvent(cs, y->seg_ready, 0));
-    TOD_CUDA(cudaMemcpyAsync(tile_classes, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, cs));
-    if (cs != s) TOD_CUDA(cudaStreamSynchronize(cs));
+  // the class maps are final as soon as seg_post_kernel has run (the graph records y->seg_ready right behind it):
+  // they are read back on a second stream while boxes / NMS / masks are still being computed
+  cudaStream_t cs = (y->opt.use_cuda_graph && y->seg_out >= 0) ? y->copy_stream : s;
+  const bool side = (tile_classes || cell_classes) && cs != s;
+  if (side) TOD_CUDA(cudaStreamWaitEvent(cs, y->seg_ready, 0));
+  if (tile_classes) TOD_CUDA(cudaMemcpyAsync(tile_classes, y->d_tile_classes, size_t(n) * y->tile_w() * y->tile_h() * 4, cudaMemcpyDeviceToHost, cs));
+  if (cell_classes && y->seg_out >= 0) {
+    const GTensor& S = y->T(y->graph.outputs[y->seg_out]);
+    TOD_CUDA(cudaMemcpyAsync(cell_classes, y->d_cell_classes, size_t(n) * S.dims[1] * S.dims[2] * 4, cudaMemcpyDeviceToHost, cs));
   }
-  TOD_CUDA(cudaStreamSynchronize(s));
-  if (want_dets) TOD_TRY(tod_yolact_fetch_detections(y, n, dets));
-  return check_diverged(y, n, s);
+  if (want_dets) TOD_TRY(enqueue_fetch_detections(y, n, dets, s));
+  TOD_TRY(enqueue_diverged(y, n, s));
+  // one wait per stream for the whole call
+  if (side) TOD_TRY(wait_stream(y, cs, y->done_ev2));
+  TOD_TRY(wait_stream(y, s, y->done_ev));
+  return read_diverged(y, n);
+}
+
+int tod_yolact_infer_tiles(tod_yolact* y, const uint8_t* rgb_tiles, int n, uint8_t* const* outputs_u8, uint32_t* tile_classes,
+                           tod_detections* dets) {
+  return tod_yolact_infer_tiles_cells(y, rgb_tiles, n, outputs_u8, tile_classes, nullptr, dets);
 }
 
 int tod_yolact_classify_batch_device(tod_yolact* y, uint32_t* d_frames, int n, int width, int height, uint16_t* d_target, void* stream) {
@@ -1585,7 +1673,9 @@ int tod_yolact_classify_batch_device(tod_yolact* y, uint32_t* d_frames, int n, i
   if (n < 1 || 2 * n > y->opt.max_tiles) return fail(TOD_ERR_CAPACITY, "classify: %d frames need %d tiles, handle holds %d", n, 2 * n, y->opt.max_tiles);
   TOD_CUDA(cudaSetDevice(y->device));
   TOD_TRY(ensure_classify_buffers(y, width, height));
-  return classify_device(y, d_frames, n, width, height, d_target, stream ? static_cast<cudaStream_t>(stream) : y->stream);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : y->stream;
+  TOD_TRY(classify_device(y, d_frames, n, width, height, d_target, s));
+  return order_after_caller(y, s);
 }
 
 int tod_yolact_classify_batch(tod_yolact* y, uint32_t* frames, int n, int width, int height) {
@@ -1598,8 +1688,9 @@ int tod_yolact_classify_batch(tod_yolact* y, uint32_t* frames, int n, int width,
   TOD_CUDA(cudaMemcpyAsync(y->d_frames, frames, bytes, cudaMemcpyHostToDevice, s));
   TOD_TRY(classify_device(y, y->d_frames, n, width, height, nullptr, s));
   TOD_CUDA(cudaMemcpyAsync(frames, y->d_frames, bytes, cudaMemcpyDeviceToHost, s));  // yolact.rs:233 copy_from_slice
-  TOD_CUDA(cudaStreamSynchronize(s));
-  return check_diverged(y, 2 * n, s);
+  TOD_TRY(enqueue_diverged(y, 2 * n, s));
+  TOD_TRY(wait_stream(y, s, y->done_ev));
+  return read_diverged(y, 2 * n);
 }
 
 int tod_yolact_classify(tod_yolact* y, uint32_t* frame, int width, int height) { return tod_yolact_classify_batch(y, frame, 1, width, height); }

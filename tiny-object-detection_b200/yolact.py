@@ -46,7 +46,10 @@ class Yolact:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().tod_yolact_destroy(self._h)
+            try:
+                lib().tod_yolact_destroy(self._h)
+            except Exception:  # interpreter shutdown: the module globals may already be gone
+                pass
             self._h = None
 
     __del__ = close
@@ -91,8 +94,10 @@ class Yolact:
         check(lib().tod_yolact_classify_batch_device(self._h, d_frames_ptr, n, width, height, d_target_ptr, stream))
 
     # ------------------------------------------------------------------ batched tile inference
-    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True, float_masks=True, tile_masks=False):
-        """tiles: u8[n, th, tw, 3].  Returns dict(outputs=[u8 arrays], tile_classes=u32[n,th,tw], dets=..., diverged=bool)."""
+    def infer_tiles(self, tiles, outputs=True, tile_classes=True, detections=False, masks=True, float_masks=True, tile_masks=False,
+                    cell_classes=False):
+        """tiles: u8[n, th, tw, 3].  Returns dict(outputs=[u8 arrays], tile_classes=u32[n,th,tw], dets=..., diverged=bool);
+        cell_classes=True adds the 28x28 grid the tile map is an 8x replication of (1/64 of the read-back)."""
         tiles = np.ascontiguousarray(tiles, np.uint8)
         n, th, tw = tiles.shape[0], tiles.shape[1], tiles.shape[2]
         res = {}
@@ -107,10 +112,15 @@ class Yolact:
             if not float_masks:  # binary masks only: the library then skips the sigmoid (sign of the integer logit)
                 det.masks = None
                 keep["masks"] = None
-        rc = check(lib().tod_yolact_infer_tiles(self._h, _ptr(tiles), n, arr if outputs else None, _ptr(tc),
-                                                C.byref(det) if det is not None else None))
+        cells = None
+        if cell_classes:
+            gh, gw = self.outputs[4]["shape"][1], self.outputs[4]["shape"][2]
+            cells = np.zeros((n, gh, gw), np.uint32)
+        rc = check(lib().tod_yolact_infer_tiles_cells(self._h, _ptr(tiles), n, arr if outputs else None, _ptr(tc), _ptr(cells),
+                                                      C.byref(det) if det is not None else None))
         res["outputs"] = outs
         res["tile_classes"] = tc
+        res["cell_classes"] = cells
         res["diverged"] = rc == _lib.TOD_WARN_REFERENCE_DIVERGES
         if detections:
             res["dets"] = self._unpack_dets(keep, n)
@@ -235,6 +245,85 @@ class YolactPool:
             w.shutdown(wait=True)
         for h in self.handles:
             h.close()
+
+
+class Pool:
+    """The C-ABI frame sharder (`tod_pool_*`, include/tod.h): `depth` handles on each device, one host thread per handle
+    inside the library; n tiles / frames are cut into contiguous per-GPU ranges and chunks of `max_tiles`, and results land
+    in the caller's arrays at the frame's index.  devices=None -> every visible GPU."""
+
+    def __init__(self, model_path=DEFAULT_MODEL, devices=None, depth=3, **options):
+        o = YolactOptions()
+        lib().tod_yolact_default_options(C.byref(o))
+        for k, v in options.items():
+            if not hasattr(o, k):
+                raise TypeError("unknown option %r" % k)
+            setattr(o, k, v)
+        self.options = o
+        dev = (C.c_int32 * len(devices))(*devices) if devices else None
+        h = C.c_void_p()
+        check(lib().tod_pool_create(str(model_path).encode(), dev, len(devices) if devices else 0, int(depth), C.byref(o), C.byref(h)))
+        self._h = h
+        self.num_devices = lib().tod_pool_num_devices(h)
+        self.num_handles = lib().tod_pool_num_handles(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().tod_pool_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    __del__ = close
+
+    def infer_tiles(self, tiles, shapes, tile_classes=False, cell_classes=True, detections=True, masks_bits=True):
+        """tiles u8[n,th,tw,3]; shapes = Yolact.outputs of a handle on the same model (output shapes).  Returns
+        dict(outputs, tile_classes, cell_classes, dets=dict of [n, max_dets, ...] arrays)."""
+        tiles = np.ascontiguousarray(tiles, np.uint8)
+        n, th, tw = tiles.shape[:3]
+        outs = [np.zeros((n,) + o["shape"][1:], np.uint8) for o in shapes]
+        arr = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
+        tc = np.zeros((n, th, tw), np.uint32) if tile_classes else None
+        gh, gw = shapes[4]["shape"][1], shapes[4]["shape"][2]
+        cells = np.zeros((n, gh, gw), np.uint32) if cell_classes else None
+        det, keep = None, None
+        if detections:
+            md = self.options.max_dets
+            sp = [o["shape"] for i, o in enumerate(shapes) if o["shape"][1] > 1 and i != 4]
+            ph, pw = sp[0][1], sp[0][2]
+            keep = dict(count=np.zeros(n, np.int32), boxes=np.zeros((n, md, 4), np.float32), scores=np.zeros((n, md), np.float32),
+                        classes=np.zeros((n, md), np.int32), priors=np.zeros((n, md), np.int32),
+                        masks_bits=np.zeros((n, md, (ph * pw + 31) // 32), np.uint32) if masks_bits else None)
+            det = Detections(md, keep["count"].ctypes.data, keep["boxes"].ctypes.data, keep["scores"].ctypes.data, keep["classes"].ctypes.data,
+                             keep["priors"].ctypes.data, None, None, keep["masks_bits"].ctypes.data if masks_bits else None, None)
+        rc = check(lib().tod_pool_infer_tiles(self._h, _ptr(tiles), n, arr, _ptr(tc), _ptr(cells), C.byref(det) if det is not None else None))
+        return dict(outputs=outs, tile_classes=tc, cell_classes=cells, dets=keep, diverged=rc == _lib.TOD_WARN_REFERENCE_DIVERGES)
+
+    def classify(self, frames, width=640, height=480):
+        """`Yolact::classify` for every frame of u32[n, height*width], in place, sharded over the pool."""
+        fb = frames
+        if not (isinstance(fb, np.ndarray) and fb.dtype == np.uint32 and fb.flags.c_contiguous and fb.flags.writeable):
+            raise TypeError("classify needs a writable, contiguous uint32 array (it is mutated in place)")
+        if fb.size % (width * height) != 0 or fb.size == 0:
+            raise TodError(-1, "frame buffer holds %d pixels, not a multiple of %dx%d" % (fb.size, width, height))
+        rc = check(lib().tod_pool_classify_batch(self._h, _ptr(fb), fb.size // (width * height), width, height))
+        return rc == _lib.TOD_WARN_REFERENCE_DIVERGES
+
+    def rgbd(self, frames, depth, scene_params, want=("map", "world", "conn0", "conn1", "balls")):
+        """The fused RGB-D loop (scene.rs:84-97 -> scene.rs:147-331) for n frames: frames u32[n, H*W] classified in place,
+        depth u16[n, H, W]; returns the scene outputs as SceneBuilder.append_batch does."""
+        W, H = scene_params.width, scene_params.height
+        n = frames.size // (W * H)
+        depth = np.ascontiguousarray(depth, np.uint16).reshape(n, H, W)
+        out = dict(map=np.zeros((n, H, W), np.uint32) if "map" in want else None,
+                   world=np.zeros((n, H, W, 4), np.float32) if "world" in want else None,
+                   conn0=np.zeros((n, H, W, 4), np.float32) if "conn0" in want else None,
+                   conn1=np.zeros((n, H, W, 4), np.float32) if "conn1" in want else None,
+                   balls=np.zeros((n, 100, 4), np.float32) if "balls" in want else None)
+        check(lib().tod_pool_rgbd_batch(self._h, C.byref(scene_params), _ptr(frames), _ptr(depth), n, _ptr(out["map"]), _ptr(out["world"]),
+                                        _ptr(out["conn0"]), _ptr(out["conn1"]), _ptr(out["balls"])))
+        return out
 
 
 def model_inspect(path):

@@ -6,6 +6,12 @@
                     of pixels whose depth could be recovered exactly, and the low byte of the reference's map.
   oracle_golden.npz outputs of the CPU oracle on seeded inputs (CRC32 per array + a few small arrays), so that both a
                     change of the oracle and a drift of the CUDA path are caught against a committed value.
+  ref_tiles.npz     the reference's only model-input fixtures, /root/reference/data/frc_balls.png and red_robot.png
+                    (224x224 RGB = exactly one tile, data/README.md:5-14), decoded to u8[2,224,224,3].
+  config2_oracle.json  BASELINE config 2 at its size: CRC32 of every output tensor, of the literal class grid and of the
+                    detection keep indices, per tile, for the 64 bench tiles (synth.rgb_tiles(64, seed=2)) and the two
+                    reference PNG tiles, computed by the CPU oracle.  bench.py and tests/test_gpu_baseline_size.py compare
+                    the CUDA path's bytes with these.
 """
 import os
 import sys
@@ -85,7 +91,46 @@ def oracle_golden():
     print("oracle_golden: %d entries" % len(g))
 
 
+def ref_tiles():
+    import cv2
+    out = []
+    for name in ("frc_balls.png", "red_robot.png"):
+        bgr = cv2.imread("/root/reference/data/" + name, cv2.IMREAD_COLOR)
+        assert bgr.shape == (224, 224, 3), bgr.shape
+        out.append(bgr[..., ::-1].copy())
+    np.savez_compressed(os.path.join(OUT, "ref_tiles.npz"), tiles=np.stack(out).astype(np.uint8), names=np.array(["frc_balls.png", "red_robot.png"]))
+    print("ref_tiles: 2 tiles")
+
+
+def tile_record(m, tile, threads=8):
+    """per-tile CRCs the CUDA path is compared with: the five outputs, the literal 28x28 class grid, detections"""
+    m.invoke(tile, threads=threads)
+    outs = [m.tensor(o) for o in m.outputs]
+    info = [m.tensor_info(o) for o in m.outputs]
+    qp = lambda i: (info[i]["scale"], info[i]["zero_point"])
+    d = oracle.detect(outs[1], qp(1), outs[0], qp(0), outs[2], qp(2), outs[3], qp(3))
+    px, div = oracle.postprocess_tile(outs[4], info[4]["scale"], info[4]["zero_point"], 0)
+    cells = np.ascontiguousarray(px.reshape(224, 224)[::8, ::8])
+    return {"out": [int(crc(o)) for o in outs], "cells": int(crc(cells)), "diverges": bool(div), "n_det": int(d["n"]),
+            "prior": int(crc(d["prior"].astype(np.int32))), "cls": int(crc(d["cls"].astype(np.int32))), "score": int(crc(d["score"].astype(np.float32))),
+            "box": int(crc(d["box"].astype(np.float32)))}
+
+
+def config2_oracle():
+    import hashlib
+    import json
+    full, _ = synth_model.ensure_models()
+    m = oracle.Model(full)
+    tiles = synth.rgb_tiles(64, seed=2)
+    ref = np.load(os.path.join(OUT, "ref_tiles.npz"))["tiles"]
+    rec = {"model_sha256": hashlib.sha256(open(full, "rb").read()).hexdigest(), "input": "tests.synth.rgb_tiles(64, seed=2)",
+           "tiles": [tile_record(m, tiles[t]) for t in range(64)], "ref_tiles": [tile_record(m, ref[t]) for t in range(2)]}
+    json.dump(rec, open(os.path.join(OUT, "config2_oracle.json"), "w"), indent=0)
+    print("config2_oracle: %d + %d tiles, detections per tile %s" % (len(rec["tiles"]), len(rec["ref_tiles"]), sorted({r["n_det"] for r in rec["tiles"]})))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    bmp_trio()
-    oracle_golden()
+    which = sys.argv[1:] or ["bmp_trio", "oracle_golden", "ref_tiles", "config2_oracle"]
+    for w in which:
+        globals()[w]()
