@@ -66,7 +66,80 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
+
+
+def bench_config(n, world, depth):
+    """config of the line: the same dict for both arms (the reference arm times a bounded sample of this workload)"""
+    return {"workload": "FRC_model int8 YOLACT full graph + decode/Fast-NMS/mask assembly, synthetic RGB batch %d tiles per GPU (configs[1])" % n,
+            "tiles_per_step": n, "frames_per_step": n // TILES_PER_FRAME, "tile": "224x224x3 u8",
+            "graph": "synthetic FRC_model.tflite stand-in with the reference's operator histogram (real blob missing), 5.62 GMAC/tile",
+            "parallelism": "frame-sharded x%d, no collective" % world,
+            "pipeline": ("%d batches in flight: %d handles take alternate %d-tile steps on their own streams (frame-loop double buffering); "
+                         "single_stream = one handle, steps back to back" % (depth, depth, n)) if depth > 1 else "1 (one handle, steps back to back)",
+            "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)}
+
+
+def _crc(a):
+    import zlib
+    import numpy as np
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
+def self_check(tod_b200, y, full, n, rank, world, timed_is_golden_input):
+    """The bytes behind the number.  (1) rank 0's timed input is tests.synth.rgb_tiles(64, seed=2), the input the CPU oracle's
+    committed CRCs (tests/golden/config2_oracle.json, tools/make_golden.py) were computed on: the outputs, class grids and
+    detections the LAST TIMED STEP left on the device are fetched and compared tile by tile.  (2) every rank then runs that
+    same input once and the digests are compared across ranks: a frame's bytes do not depend on the GPU it ran on
+    (SURVEY 8e).  Never raises: a mismatch is reported in the line."""
+    import ctypes as C
+    import hashlib
+    import numpy as np
+    from tests import synth
+    out = {"golden": "tests/golden/config2_oracle.json (CPU oracle, all %d tiles: 5 outputs + class grid + NMS keep indices / classes / scores / boxes)" % min(n, 64)}
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "config2_oracle.json")))
+        model_ok = hashlib.sha256(open(full, "rb").read()).hexdigest() == g["model_sha256"]
+        out["model_matches_golden"] = model_ok
+
+        def digest_of_last_call(m):
+            outs = [y.fetch_output(k, m) for k in range(5)]
+            det, keep = y._alloc_dets(m, True)
+            det.masks = None
+            det.masks_bin = None
+            tod_b200._lib.check(tod_b200.lib().tod_yolact_fetch_detections(y._h, m, C.byref(det)))
+            cells = y.fetch_tile_classes(m)[:, ::8, ::8]
+            bad, crcs = 0, []
+            for t in range(m):
+                c = keep["count"][t]
+                rec = {"out": [_crc(o[t]) for o in outs], "cells": _crc(cells[t]), "n_det": int(c), "prior": _crc(keep["priors"][t, :c]),
+                       "cls": _crc(keep["classes"][t, :c]), "score": _crc(keep["scores"][t, :c]), "box": _crc(keep["boxes"][t, :c])}
+                crcs.append(rec)
+                if model_ok and t < len(g["tiles"]):
+                    w = g["tiles"][t]
+                    bad += int(any(rec[k] != w[k] for k in ("out", "cells", "n_det", "prior", "cls", "score", "box")))
+            return bad, _crc(np.array([[r["cells"], r["prior"], r["score"], r["box"]] + r["out"] for r in crcs], np.uint32))
+
+        m = min(n, 64)
+        if rank == 0 and timed_is_golden_input:
+            bad, dig = digest_of_last_call(m)
+            out["timed_step_tiles_checked"] = m
+            out["timed_step_tiles_differing_from_oracle"] = bad if model_ok else None
+        tiles = synth.rgb_tiles(64, seed=2)[:m]
+        y.infer_tiles(tiles, outputs=False, tile_classes=False, detections=True, float_masks=False)
+        bad2, dig2 = digest_of_last_call(m)
+        out["rerun_tiles_differing_from_oracle"] = bad2 if model_ok else None
+        out["digest"] = int(dig2)
+        if world > 1:
+            from tests import dist_helpers
+            out["ranks_agree"] = bool(dist_helpers.all_equal_over_ranks(dig2))
+        out["ok"] = bool((not model_ok or (bad2 == 0 and out.get("timed_step_tiles_differing_from_oracle", 0) in (0, None))) and out.get("ranks_agree", True))
+    except Exception as e:  # the check must never cost the measurement
+        out["error"] = str(e)[:300]
+        out["ok"] = False
+    return out
 
 
 def run_reference(args, rank):
@@ -104,10 +177,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "yolact_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
-        "config": {"workload": "FRC int8 YOLACT graph + literal postprocess + decode/Fast-NMS/mask, CPU oracle port of the reference path",
-                   "tiles_per_step": sample_tiles, "frames_per_step": sample_tiles // TILES_PER_FRAME},
+        "config": bench_config(args.tiles, args.gpus, max(1, args.pipeline)),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d tiles (1 camera frame) per step through oracle/ (TFLite reference-kernel loop nests, OpenMP over %d threads)" % (sample_tiles, cores)},
+                         "sample": "%d tiles (1 camera frame) of the %d-tile step per timed step, through oracle/ (int8 graph with TFLite reference-kernel loop nests, literal postprocess, decode / Fast-NMS / masks; OpenMP over %d threads)" % (sample_tiles, args.tiles, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -127,6 +199,7 @@ def main():
     ap.add_argument("--pipeline", type=int, default=3,
                     help="batches in flight: handles that take alternate steps on their own streams (1 = one handle, steps back to back)")
     ap.add_argument("--fused", type=int, default=512, help="frames of the fused 320x240 RGB-D side measurement (0 = skip)")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained side figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,10 +265,15 @@ def main():
     barrier()
     frames_per_step = n // TILES_PER_FRAME
     value = world * frames_per_step * args.steps / (ms * 1e-3)
+    check = self_check(tod_b200, y, full, n, rank, world, timed_is_golden_input=(n == 64))
+    barrier()
 
     # ---- end to end through the reference-facing C-ABI call with host buffers
     out_bufs = y._alloc_dets(n, True)
-    tc_h = torch.empty((n, 224, 224), dtype=torch.int32).pin_memory()
+    GH, GW = y.outputs[4]["shape"][1], y.outputs[4]["shape"][2]
+    # the literal postprocess result as the 28x28 (class, id) grid: tile_classes is its 8x8 replication (yolact.rs:127-128),
+    # 64x the bytes for the same information
+    tc_h = torch.empty((n, GH, GW), dtype=torch.int32).pin_memory()
     det, keep = out_bufs
     keep_pinned = {}
     import ctypes as C
@@ -210,7 +288,7 @@ def main():
     lib = tod_b200.lib()
 
     def e2e_step():
-        tod_b200._lib.check(lib.tod_yolact_infer_tiles(y._h, tiles_h.data_ptr(), n, None, tc_h.data_ptr(), C.byref(det)))
+        tod_b200._lib.check(lib.tod_yolact_infer_tiles_cells(y._h, tiles_h.data_ptr(), n, None, None, tc_h.data_ptr(), C.byref(det)))
 
     for _ in range(3):
         e2e_step()
@@ -264,6 +342,32 @@ def main():
         ms = pms
         value = world * frames_per_step * args.steps / (pms * 1e-3)
 
+        # sustained side figure: the same pipelined steps for >= 2 s under its own clock / power record (the headline region is
+        # only steps x ~1 ms long)
+        sustained = None
+        if args.sustain > 0:
+            sus_steps = max(args.steps, int(args.sustain * 1e3 / max(pms / args.steps, 1e-3)))
+            sclk = ClockSampler(local_rank)
+            if rank == 0:
+                sclk.start()
+            p0.record()
+            for ps in pstreams:
+                ps.wait_event(p0)
+            for k in range(sus_steps):
+                pstep(k)
+            for ps in pstreams:
+                tstream.wait_stream(ps)
+            p1.record()
+            torch.cuda.synchronize()
+            sus_ms = p0.elapsed_time(p1)
+            if dist is not None:
+                t = torch.tensor([sus_ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sus_ms = float(t.item())
+            sustained = {"value": world * frames_per_step * sus_steps / (sus_ms * 1e-3), "unit": "frames/s", "steps": sus_steps, "seconds": sus_ms * 1e-3,
+                         "clocks": sclk.stop() if rank == 0 else None}
+            barrier()
+
         # end to end: one host thread per handle, each with its own pinned buffers
         ctx = []
         for h in range(depth):
@@ -275,14 +379,14 @@ def main():
                 setattr(d_h, kk, tt.data_ptr())
             d_h.masks = None
             d_h.masks_bin = None
-            ctx.append((ys[h], d_h, pin, torch.empty((n, 224, 224), dtype=torch.int32).pin_memory(), (tiles_h if h == 0 else ptiles[h].cpu().pin_memory())))
+            ctx.append((ys[h], d_h, pin, torch.empty((n, GH, GW), dtype=torch.int32).pin_memory(), (tiles_h if h == 0 else ptiles[h].cpu().pin_memory())))
         counts = [args.steps // depth + (1 if h < args.steps % depth else 0) for h in range(depth)]
 
         def worker(h, reps):
             torch.cuda.set_device(local_rank)
             yy, d_h, _, tc_p, th = ctx[h]
             for _ in range(reps):
-                tod_b200._lib.check(lib.tod_yolact_infer_tiles(yy._h, th.data_ptr(), n, None, tc_p.data_ptr(), C.byref(d_h)))
+                tod_b200._lib.check(lib.tod_yolact_infer_tiles_cells(yy._h, th.data_ptr(), n, None, None, tc_p.data_ptr(), C.byref(d_h)))
 
         def run_threads(cs):
             ths = [threading.Thread(target=worker, args=(h, cs[h])) for h in range(depth)]
@@ -340,15 +444,13 @@ def main():
     line = {
         "metric": "yolact_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": "FRC_model int8 YOLACT full graph + decode/Fast-NMS/mask assembly, synthetic RGB batch %d tiles per GPU (configs[1])" % n,
-                   "tiles_per_step": n, "frames_per_step": frames_per_step, "tile": "224x224x3 u8", "graph": "synthetic FRC_model.tflite stand-in with the reference's operator histogram (real blob missing), 5.62 GMAC/tile",
-                   "parallelism": "frame-sharded x%d, no collective" % world,
-                   "pipeline": ("%d batches in flight: %d handles take alternate %d-tile steps on their own streams (frame-loop double buffering); "
-                                "single_stream = one handle, steps back to back" % (depth, depth, n)) if depth > 1 else "1 (one handle, steps back to back)", "l2": "activation working set ~%.0f MB per step (19.5 MB/tile) > 126 MB L2; no flush needed" % (19.5 * n)},
+        "config": bench_config(n, world, depth),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "call": "tod_yolact_infer_tiles (host tiles in; tile class maps + detections + bit-packed binary masks out)"},
+                "call": "tod_yolact_infer_tiles_cells (host tiles in; 28x28 class grids + detections + bit-packed binary masks out)"},
         "single_stream": {"value": single["value"], "ms_per_step": single["ms_per_step"], "e2e_value": single["e2e"], "unit": "frames/s"},
         "gpu_launches": int(st["launches_per_call"] * args.steps),
+        "check": check,
+        "sustained": sustained if depth > 1 else None,
         "roofline": roofline,
         "clocks": clk,
         "tiles_per_sec": value * TILES_PER_FRAME,
@@ -367,50 +469,97 @@ def main():
     except Exception as e:
         line["detection_tail"] = {"error": str(e)[:200]}
 
-    # ---- scene path (configs[2]): depth -> point cloud + weights, HBM-bound streaming + shared-memory stamp
-    if not args.no_scene and rank == 0:
-        nb = SCENE_BATCH
-        sb = tod_b200.SceneBuilder(device=local_rank, max_batch=nb)
-        base = synth.depth_frames(8, seed=3)
-        depth = torch.from_numpy(np.tile(base, (nb // 8, 1, 1)).astype(np.int16)).cuda()
-        target = torch.zeros_like(depth)
-        npx = 640 * 480
-        o_map = torch.empty((nb, npx), dtype=torch.int32, device="cuda")
-        o_w = torch.empty((nb, npx, 4), dtype=torch.float32, device="cuda")
-        o_c0, o_c1 = torch.empty_like(o_w), torch.empty_like(o_w)
-        o_b = torch.empty((nb, 100, 4), dtype=torch.float32, device="cuda")
+    def rank_max(v):
+        if dist is None:
+            return float(v)
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-        def sstep():
-            sb.append_batch_device(depth.data_ptr(), target.data_ptr(), nb, o_map.data_ptr(), o_w.data_ptr(), o_c0.data_ptr(), o_c1.data_ptr(), o_b.data_ptr(), stream)
-
-        for _ in range(3):
-            sstep()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        s0.record()
+    def host_timed(fn, reps, warm=2):
+        """wall-clock seconds of `reps` blocking C-ABI calls (host buffers in and out), max over ranks"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(reps):
-            sstep()
-        s1.record()
-        torch.cuda.synchronize()
-        sms = s0.elapsed_time(s1) / reps
-        bytes_per_frame = 56 * npx + 1600
-        sb.append_batch_device(depth.data_ptr(), target.data_ptr(), nb, o_map.data_ptr(), o_w.data_ptr(), o_c0.data_ptr(), o_c1.data_ptr(), o_b.data_ptr(), None)
-        stamp_ms, weights_ms = sb.last_kernel_ms()
-        line["scene"] = {"workload": "640x480 depth -> point cloud + weights, batch %d (configs[2])" % nb, "frames_per_sec": nb / (sms * 1e-3),
-                         "ms_per_batch": sms, "algorithmic_GBps": nb * bytes_per_frame / (sms * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm"],
-                         "frac_of_hbm": nb * bytes_per_frame / (sms * 1e-3) / 1e9 / peaks["hbm"], "stamp_ms": stamp_ms, "weights_ms": weights_ms,
-                         "weights_GBps": nb * 52 * npx / (weights_ms * 1e-3) / 1e9, "stamps_per_sec": nb * npx * 400 / (stamp_ms * 1e-3)}
+            fn()
+        return rank_max(time.perf_counter() - t0)
 
-    # ---- fused RGB-D pipeline (configs[3]): 320x240 frames, classify -> u16 target -> point cloud, all on the device
-    if args.fused and rank == 0:
+    # ---- scene path (configs[2]): depth -> point cloud + weights; every rank runs its own 256 frames (weak scaling)
+    if not args.no_scene:
+        try:
+            nb = SCENE_BATCH
+            sb = tod_b200.SceneBuilder(device=local_rank, max_batch=nb)
+            base = synth.depth_frames(8, seed=3 + rank)
+            depth = torch.from_numpy(np.tile(base, (nb // 8, 1, 1)).astype(np.int16)).cuda()
+            target = torch.zeros_like(depth)
+            npx = 640 * 480
+            o_map = torch.empty((nb, npx), dtype=torch.int32, device="cuda")
+            o_w = torch.empty((nb, npx, 4), dtype=torch.float32, device="cuda")
+            o_c0, o_c1 = torch.empty_like(o_w), torch.empty_like(o_w)
+            o_b = torch.empty((nb, 100, 4), dtype=torch.float32, device="cuda")
+
+            def sstep():
+                sb.append_batch_device(depth.data_ptr(), target.data_ptr(), nb, o_map.data_ptr(), o_w.data_ptr(), o_c0.data_ptr(), o_c1.data_ptr(), o_b.data_ptr(), stream)
+
+            for _ in range(3):
+                sstep()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            s0.record()
+            for _ in range(reps):
+                sstep()
+            s1.record()
+            torch.cuda.synchronize()
+            sms = rank_max(s0.elapsed_time(s1) / reps)
+            bytes_per_frame = 56 * npx + 1600
+            sb.append_batch_device(depth.data_ptr(), target.data_ptr(), nb, o_map.data_ptr(), o_w.data_ptr(), o_c0.data_ptr(), o_c1.data_ptr(), o_b.data_ptr(), None)
+            stamp_ms, weights_ms = sb.last_kernel_ms()
+            scene = {"workload": "640x480 depth -> point cloud + weights, batch %d per GPU (configs[2]), device-resident" % nb,
+                     "frames_per_sec": world * nb / (sms * 1e-3), "ms_per_batch": sms,
+                     "algorithmic_GBps_per_gpu": nb * bytes_per_frame / (sms * 1e-3) / 1e9, "hbm_peak_GBps": peaks["hbm"],
+                     "frac_of_hbm": nb * bytes_per_frame / (sms * 1e-3) / 1e9 / peaks["hbm"], "stamp_ms": stamp_ms, "weights_ms": weights_ms,
+                     "weights_GBps": nb * 52 * npx / (weights_ms * 1e-3) / 1e9, "weights_frac_of_hbm": nb * 52 * npx / (weights_ms * 1e-3) / 1e9 / peaks["hbm"],
+                     "stamp_kernel": "stamp_pruned_kernel (one entry per column and landing row) + tile merge fused into weights_kernel",
+                     "shader_stamps_per_sec": nb * npx * 400 / (stamp_ms * 1e-3)}
+            del o_w, o_c0, o_c1, o_map
+            # end to end through the drop-in call: host depth + target in, the reference's four read-backs out (scene.rs:246,257-259),
+            # then the Scene conversion of one frame (scene.rs:312-327)
+            eb = 32
+            sbe = tod_b200.SceneBuilder(device=local_rank, max_batch=eb)
+            h_depth = torch.from_numpy(np.tile(base, (eb // 8, 1, 1)).astype(np.int16)).pin_memory()
+            h_target = torch.zeros_like(h_depth).pin_memory()
+            h_map = torch.empty((eb, npx), dtype=torch.int32).pin_memory()
+            h_w = torch.empty((eb, npx, 4), dtype=torch.float32).pin_memory()
+            h_c0, h_c1 = torch.empty_like(h_w).pin_memory(), torch.empty_like(h_w).pin_memory()
+            h_b = torch.empty((eb, 100, 4), dtype=torch.float32).pin_memory()
+            sc_h = np.zeros(npx, np.float32), np.zeros((npx, 3), np.float32), np.zeros((100, 2), np.int32), np.zeros((npx, 8), np.float32)
+
+            def scene_e2e():
+                tod_b200._lib.check(lib.tod_scene_append_batch(sbe._h, h_depth.data_ptr(), h_target.data_ptr(), eb, h_map.data_ptr(), h_w.data_ptr(),
+                                                               h_c0.data_ptr(), h_c1.data_ptr(), h_b.data_ptr()))
+                tod_b200._lib.check(lib.tod_scene_materialize(sbe._h, eb - 1, sc_h[0].ctypes.data, sc_h[1].ctypes.data, sc_h[2].ctypes.data, sc_h[3].ctypes.data))
+
+            es = host_timed(scene_e2e, 5)
+            scene["e2e"] = {"value": world * eb * 5 / es, "unit": "frames/s", "h2d_bytes_per_step": int(eb * npx * 4),
+                            "d2h_bytes_per_step": int(eb * (npx * 52 + 1600) + npx * 48 + 800),
+                            "call": "tod_scene_append_batch (32 frames, host depth + target in, map + world + conn0 + conn1 + balls out) + tod_scene_materialize of one frame; PCIe-bound: 16 MB of read-back per frame as in the reference"}
+            line["scene"] = scene
+            del sb, sbe
+        except Exception as e:
+            line["scene"] = {"error": str(e)[:200]}
+
+    # ---- fused RGB-D pipeline (configs[3] / [4]): 320x240 frames, classify -> u16 target -> point cloud, all on the device; every rank
+    if args.fused:
         try:
             fb = args.fused
             W4, H4 = 320, 240
             y4 = tod_b200.Yolact.init(full, device=local_rank, max_tiles=2 * fb)
             sb4 = tod_b200.SceneBuilder(device=local_rank, width=W4, height=H4, max_batch=fb)
-            fr = torch.from_numpy(np.tile(synth.rgb_frames(8, W=W4, H=H4, seed=5), (fb // 8, 1)).view(np.int32)).cuda()
-            dp = torch.from_numpy(np.tile(synth.depth_frames(8, W=W4, H=H4, seed=3), (fb // 8, 1, 1)).view(np.int16)).cuda()
+            fr = torch.from_numpy(np.tile(synth.rgb_frames(8, W=W4, H=H4, seed=5 + rank), (fb // 8, 1)).view(np.int32)).cuda()
+            dp = torch.from_numpy(np.tile(synth.depth_frames(8, W=W4, H=H4, seed=3 + rank), (fb // 8, 1, 1)).view(np.int16)).cuda()
             tg = torch.zeros((fb, H4, W4), dtype=torch.int16, device="cuda")
             o_map = torch.empty((fb, H4 * W4), dtype=torch.int32, device="cuda")
             o_w = torch.empty((fb, H4 * W4, 4), dtype=torch.float32, device="cuda")
@@ -424,19 +573,72 @@ def main():
 
             for _ in range(2):
                 fstep()
-            torch.cuda.synchronize()
+            barrier()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record()
             for _ in range(3):
                 fstep()
             f1.record()
             torch.cuda.synchronize()
-            fms = f0.elapsed_time(f1) / 3
-            line["fused_rgbd"] = {"workload": "320x240 RGB-D frames: classify (2 tiles/frame) -> target -> point cloud + weights, batch %d, device-resident (configs[3])" % fb,
-                                  "frames_per_sec": fb / (fms * 1e-3), "ms_per_batch": fms}
-            del y4, sb4
+            fms = rank_max(f0.elapsed_time(f1) / 3)
+            line["fused_rgbd"] = {"workload": "320x240 RGB-D frames: classify (2 tiles/frame) -> target -> point cloud + weights, batch %d per GPU, device-resident (configs[3]); configs[4] = this at N GPUs" % fb,
+                                  "frames_per_sec": world * fb / (fms * 1e-3), "ms_per_batch": fms, "n_gpus": world}
+            del y4, sb4, o_w, o_c0, o_c1, o_map, work
+            # end to end behind the C ABI: tod_pool_rgbd_batch on this rank's GPU (3 handles, chunks of 32 frames), host frames + depth in,
+            # classified frames + map + world + conn0 + conn1 out
+            pool = tod_b200.Pool(full, devices=[local_rank], depth=3, max_tiles=64)
+            pn = 192
+            sp = tod_b200.default_params(width=W4, height=H4)
+            pf = torch.from_numpy(np.tile(synth.rgb_frames(8, W=W4, H=H4, seed=5 + rank), (pn // 8, 1)).view(np.int32)).pin_memory()
+            pf0 = pf.clone()
+            pd = torch.from_numpy(np.tile(synth.depth_frames(8, W=W4, H=H4, seed=3 + rank), (pn // 8, 1, 1)).view(np.int16)).pin_memory()
+            pm = torch.empty((pn, H4 * W4), dtype=torch.int32).pin_memory()
+            pw = torch.empty((pn, H4 * W4, 4), dtype=torch.float32).pin_memory()
+            pc0, pc1 = torch.empty_like(pw).pin_memory(), torch.empty_like(pw).pin_memory()
+
+            def rgbd_e2e():
+                pf.copy_(pf0)
+                tod_b200._lib.check(lib.tod_pool_rgbd_batch(pool._h, C.byref(sp), pf.data_ptr(), pd.data_ptr(), pn, pm.data_ptr(), pw.data_ptr(), pc0.data_ptr(), pc1.data_ptr(), None))
+
+            es = host_timed(rgbd_e2e, 3, warm=1)
+            line["fused_rgbd"]["e2e"] = {"value": world * pn * 3 / es, "unit": "frames/s", "h2d_bytes_per_step": int(pn * W4 * H4 * 6),
+                                         "d2h_bytes_per_step": int(pn * W4 * H4 * (4 + 52)),
+                                         "call": "tod_pool_rgbd_batch: 192 host frames + depth per call, 3 handles behind the C ABI; 4.3 MB of read-back per frame (PCIe-bound)"}
+            # the reference's own call: Yolact::classify on 640x480 frames, in place, host buffer (yolact.rs:39)
+            cn = 96
+            cf0 = torch.from_numpy(np.tile(synth.rgb_frames(8, seed=5 + rank), (cn // 8, 1)).view(np.int32)).pin_memory()
+            cf = cf0.clone().pin_memory()
+
+            def classify_e2e():
+                cf.copy_(cf0)
+                tod_b200._lib.check(lib.tod_pool_classify_batch(pool._h, cf.data_ptr(), cn, 640, 480))
+
+            es = host_timed(classify_e2e, 3, warm=1)
+            line["classify_e2e"] = {"value": world * cn * 3 / es, "unit": "frames/s", "h2d_bytes_per_step": int(cn * 640 * 480 * 4), "d2h_bytes_per_step": int(cn * 640 * 480 * 4),
+                                    "call": "tod_pool_classify_batch: 96 frames of 640x480 u32 per call, classified in place (Yolact::classify for every frame), 3 handles behind the C ABI"}
+            # one synchronous caller, tiles: the pooled form of tod_yolact_infer_tiles_cells
+            tn = 3 * n
+            pt = torch.from_numpy(np.tile(synth.rgb_tiles(n, seed=2 + rank), (3, 1, 1, 1))).pin_memory()
+            pdet, pkeep = y._alloc_dets(tn, True)
+            ppin = {}
+            for kk in ("count", "boxes", "scores", "classes", "priors", "masks_bits"):
+                tt = torch.from_numpy(pkeep[kk].view(np.int32) if pkeep[kk].dtype == np.uint32 else pkeep[kk]).pin_memory()
+                ppin[kk] = tt
+                setattr(pdet, kk, tt.data_ptr())
+            pdet.masks = None
+            pdet.masks_bin = None
+            pcells = torch.empty((tn, GH, GW), dtype=torch.int32).pin_memory()
+
+            def pool_tiles():
+                tod_b200._lib.check(lib.tod_pool_infer_tiles(pool._h, pt.data_ptr(), tn, None, None, pcells.data_ptr(), C.byref(pdet)))
+
+            reps = max(3, args.steps // 3)
+            es = host_timed(pool_tiles, reps, warm=2)
+            line["e2e"]["one_caller"] = {"value": world * (tn // TILES_PER_FRAME) * reps / es, "unit": "frames/s",
+                                         "call": "tod_pool_infer_tiles: %d tiles per blocking call, the library's own 3 handles / host threads (no Python threads)" % tn}
+            del pool
         except Exception as e:  # never let the side measurement break the headline line
-            line["fused_rgbd"] = {"error": str(e)[:200]}
+            line.setdefault("fused_rgbd", {})["error"] = str(e)[:200]
 
     # ---- CPU baseline (oracle port of the reference's CPU path), rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

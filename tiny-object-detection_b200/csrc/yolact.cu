@@ -9,12 +9,14 @@
 // convolution, per-channel requantisation constants / byte LUTs are tabulated on the host with the exact
 // TFLite integer rules, and the whole per-batch launch sequence is replayed from a CUDA graph.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -1304,6 +1306,16 @@ int wait_stream(tod_yolact* y, cudaStream_t s, cudaEvent_t ev) {
     return TOD_OK;
   }
   TOD_CUDA(cudaEventRecord(ev, s));
+  // poll with sched_yield for the first few milliseconds (a step is ~1 ms: no interrupt wake-up latency, and a core that
+  // other runnable threads want is handed over at once), then sleep on the blocking-sync event
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t q = cudaEventQuery(ev);
+    if (q == cudaSuccess) return TOD_OK;
+    if (q != cudaErrorNotReady) return fail(TOD_ERR_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(q));
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(4)) break;
+    std::this_thread::yield();
+  }
   TOD_CUDA(cudaEventSynchronize(ev));
   return TOD_OK;
 }
