@@ -55,9 +55,22 @@ int main() {
     uint32_t* base = tile.data() + (row0 >> 1) * W + col;
     const uint32_t sel = (row0 & 1) ? 0x5432u : 0x7654u;
 #define PR_PRMT(a, b, s) prmt(a, b, s)
-#define PR_RMW(off, w) base[off] = vmaxu2(base[off], w)
+    // the kernel includes the pattern twice: upper words for every entry, lower words for the non-dominated ones
+    {
+#define PR_RMW_U(off, w) base[off] = vmaxu2(base[off], w)
+#define PR_RMW_L(off, w)
 #define PR_SYNC()
 #include "../../tiny-object-detection_b200/csrc/stamp_pattern.inc"
+#undef PR_RMW_U
+#undef PR_RMW_L
+    }
+    {
+#define PR_RMW_U(off, w)
+#define PR_RMW_L(off, w) base[off] = vmaxu2(base[off], w)
+#include "../../tiny-object-detection_b200/csrc/stamp_pattern.inc"
+#undef PR_RMW_U
+#undef PR_RMW_L
+    }
     for (int r = 0; r < 2 * pairs; ++r)
       for (int c = 0; c < W; ++c) {
         const uint32_t got = (tile[(r >> 1) * W + c] >> (16 * (r & 1))) & 0xFFFF;
@@ -66,6 +79,26 @@ int main() {
           ++bad;
         }
       }
+  }
+  // the split the dominance argument needs: the lower words only touch rows dy >= 1
+  for (int parity = 0; parity < 2; ++parity) {
+    std::vector<uint32_t> tile(pairs * W, 0u);
+    uint32_t t[18];
+    for (int k = 0; k < 18; ++k) t[k] = 0x00010001u;
+    const int row0 = 20 + parity, col = 30;
+    uint32_t* base = tile.data() + (row0 >> 1) * W + col;
+    const uint32_t sel = (row0 & 1) ? 0x5432u : 0x7654u;
+#define PR_RMW_U(off, w)
+#define PR_RMW_L(off, w) base[off] = vmaxu2(base[off], w)
+#include "../../tiny-object-detection_b200/csrc/stamp_pattern.inc"
+#undef PR_RMW_U
+#undef PR_RMW_L
+    for (int r = 0; r < 2 * pairs; ++r)
+      for (int c = 0; c < W; ++c)
+        if (((tile[(r >> 1) * W + c] >> (16 * (r & 1))) & 0xFFFF) && r - (row0 + 8) < 1) {
+          printf("lower words touch row dy = %d (parity %d)\n", r - (row0 + 8), parity);
+          ++bad;
+        }
   }
   printf("stamp pattern: %s (%d mismatching cells)\n", bad ? "FAIL" : "ok", bad);
   return bad ? 1 : 0;

@@ -431,15 +431,21 @@ struct PrunedDev {
   int r_min, nbands, nstrips;   // band b holds the landing rows [r_min + 64 b, r_min + 64 b + 64)
 };
 
-__device__ __forceinline__ void pr_append(unsigned v, int y, int want_kind, int enc_lo, unsigned long long& seen, int& cnt,
+// Entries whose column already holds an entry one landing row further down (found earlier = larger source row) are
+// "dominated below": that neighbour's stamp is at least as large on every row dy >= 1, so only the upper words of the
+// stamp are needed.  The lane's list is two-ended: the other entries grow from slot 0, the dominated ones from slot 63.
+__device__ __forceinline__ void pr_append(unsigned v, int y, int want_kind, int enc_lo, unsigned long long& seen, int& cnt_n, int& cnt_d,
                                           uint16_t* list, int lane) {
   const int rel = int(v & 0x3FFF) - enc_lo;
   if (int(v >> 14) == want_kind && unsigned(rel) < unsigned(kPrBand)) {
     const unsigned long long bit = 1ull << rel;
     if (!(seen & bit)) {
+      const bool dominated = rel + 1 < kPrBand && ((seen >> (rel + 1)) & 1ull);
       seen |= bit;
-      list[cnt * 32 + lane] = uint16_t((rel << 10) | y);
-      ++cnt;
+      const int slot = dominated ? kPrBand - 1 - cnt_d : cnt_n;
+      list[slot * 32 + lane] = uint16_t((rel << 10) | y);
+      if (dominated) ++cnt_d;
+      else ++cnt_n;
     }
   }
 }
@@ -450,9 +456,10 @@ __device__ __forceinline__ void pr_append(unsigned v, int y, int want_kind, int 
 // `rows`; then the hit rows' land values are read eight rows at a time.
 constexpr int kPrChunk = 256;
 
-__device__ __forceinline__ int pr_collect(const uint16_t* __restrict__ L, const uint32_t* __restrict__ RI, const SceneDev& P, int x, int lane,
-                                          int want_kind, int y_min, int enc_lo, uint16_t* list, uint16_t* rows) {
-  int cnt = 0;
+__device__ __forceinline__ void pr_collect(const uint16_t* __restrict__ L, const uint32_t* __restrict__ RI, const SceneDev& P, int x, int lane,
+                                           int want_kind, int y_min, int enc_lo, uint16_t* list, uint16_t* rows, int& cnt_n, int& cnt_d) {
+  cnt_n = 0;
+  cnt_d = 0;
   unsigned long long seen = 0ull;
   const int enc_hi = enc_lo + kPrBand - 1;
   const unsigned lt = (1u << lane) - 1u;
@@ -480,11 +487,10 @@ __device__ __forceinline__ int pr_collect(const uint16_t* __restrict__ L, const 
 #pragma unroll
       for (int j = 0; j < 8; ++j) vs[j] = (ys[j] >= 0 && x < P.W) ? unsigned(L[int64_t(ys[j]) * P.W + x]) : unsigned(kKindNone << 14);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pr_append(vs[j], ys[j], want_kind, enc_lo, seen, cnt, list, lane);
+      for (int j = 0; j < 8; ++j) pr_append(vs[j], ys[j], want_kind, enc_lo, seen, cnt_n, cnt_d, list, lane);
     }
     __syncwarp();
   }
-  return cnt;
 }
 
 __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __restrict__ land, const uint32_t* __restrict__ rowinfo_t,
@@ -506,54 +512,75 @@ __global__ void __launch_bounds__(32) stamp_pruned_kernel(const uint16_t* __rest
   const int64_t ri = (int64_t(f) * Q.nstrips + strip) * P.H;
   // ---- terrain (val = source row; row 0 stamps nothing: val = 0 makes every y_add NaN -> 0)
   {
-    const int cnt = pr_collect(L, rowinfo_t + ri, P, x, lane, kKindTerrain, 1, enc_lo, list, rows);
-    const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
-    // the table row of the next entry is fetched while the current one is stamped
-    uint32_t t[kPrRowWords];
-    {
-      const uint4* tr = ttab + int64_t(cnt > 0 ? (list[lane] & 1023u) : 0u) * (kPrRowWords / 4);
-#pragma unroll
-      for (int q = 0; q < kPrRowWords / 4; ++q) {
-        const uint4 v = __ldg(tr + q);
-        t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-      }
-    }
+    int cnt_n, cnt_d;
+    pr_collect(L, rowinfo_t + ri, P, x, lane, kKindTerrain, 1, enc_lo, list, rows, cnt_n, cnt_d);
+    // pass 0: the upper words (rows dy <= 0) of every entry; pass 1: the lower words of the entries not dominated below
 #pragma unroll 1
-    for (int i = 0; i < maxcnt; ++i) {
-      const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
-      if (i < cnt) {
-        const unsigned e = list[i * 32 + lane];
-        const unsigned en = list[(i + 1 < cnt ? i + 1 : i) * 32 + lane];
-        const int row0 = int(e >> 10) + (kPrHalo - kPrRadius);   // tile row of dy = -8
-        uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane + kPrHalo;
-        const unsigned sel = (row0 & 1) ? 0x5432u : 0x7654u;
-        const uint4* tr = ttab + int64_t(en & 1023u) * (kPrRowWords / 4);
-        uint4 tn[kPrRowWords / 4];
-#pragma unroll
-        for (int q = 0; q < kPrRowWords / 4; ++q) tn[q] = __ldg(tr + q);
-#define PR_PRMT(a, b, s) __byte_perm(a, b, s)
-#define PR_RMW(off, w) base[off] = __vmaxu2(base[off], w)
-#define PR_SYNC() __syncwarp(active)
-#include "stamp_pattern.inc"
-#undef PR_PRMT
-#undef PR_RMW
-#undef PR_SYNC
+    for (int pass = 0; pass < 2; ++pass) {
+      const int cnt = pass == 0 ? cnt_n + cnt_d : cnt_n;
+      const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
+      auto slot_of = [&](int i) { return i < cnt_n ? i : kPrBand - 1 - (i - cnt_n); };
+      // the table row of the next entry is fetched while the current one is stamped
+      uint32_t t[kPrRowWords];
+      {
+        const uint4* tr = ttab + int64_t(cnt > 0 ? (list[slot_of(0) * 32 + lane] & 1023u) : 0u) * (kPrRowWords / 4);
 #pragma unroll
         for (int q = 0; q < kPrRowWords / 4; ++q) {
-          t[4 * q] = tn[q].x; t[4 * q + 1] = tn[q].y; t[4 * q + 2] = tn[q].z; t[4 * q + 3] = tn[q].w;
+          const uint4 v = __ldg(tr + q);
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
         }
       }
+#pragma unroll 1
+      for (int i = 0; i < maxcnt; ++i) {
+        const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
+        if (i < cnt) {
+          const unsigned e = list[slot_of(i) * 32 + lane];
+          const unsigned en = list[slot_of(i + 1 < cnt ? i + 1 : i) * 32 + lane];
+          const int row0 = int(e >> 10) + (kPrHalo - kPrRadius);   // tile row of dy = -8
+          uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane + kPrHalo;
+          const unsigned sel = (row0 & 1) ? 0x5432u : 0x7654u;
+          const uint4* tr = ttab + int64_t(en & 1023u) * (kPrRowWords / 4);
+          uint4 tn[kPrRowWords / 4];
+#pragma unroll
+          for (int q = 0; q < kPrRowWords / 4; ++q) tn[q] = __ldg(tr + q);
+#define PR_PRMT(a, b, s) __byte_perm(a, b, s)
+#define PR_SYNC() __syncwarp(active)
+          if (pass == 0) {
+#define PR_RMW_U(off, w) base[off] = __vmaxu2(base[off], w)
+#define PR_RMW_L(off, w)
+#include "stamp_pattern.inc"
+#undef PR_RMW_U
+#undef PR_RMW_L
+          } else {
+#define PR_RMW_U(off, w)
+#define PR_RMW_L(off, w) base[off] = __vmaxu2(base[off], w)
+#include "stamp_pattern.inc"
+#undef PR_RMW_U
+#undef PR_RMW_L
+          }
+#undef PR_PRMT
+#undef PR_SYNC
+#pragma unroll
+          for (int q = 0; q < kPrRowWords / 4; ++q) {
+            t[4 * q] = tn[q].x; t[4 * q + 1] = tn[q].y; t[4 * q + 2] = tn[q].z; t[4 * q + 3] = tn[q].w;
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   // ---- robot (constant val: one stamp per (column, landing row) is enough)
   {
     __syncwarp();
-    const int cnt = pr_collect(L, rowinfo_b + ri, P, x, lane, kKindRobot, 0, enc_lo, list, rows);
+    int cnt_n, cnt_d;
+    pr_collect(L, rowinfo_b + ri, P, x, lane, kKindRobot, 0, enc_lo, list, rows, cnt_n, cnt_d);
+    const int cnt = cnt_n + cnt_d;   // the constant robot table is applied whole to every entry
     const int maxcnt = __reduce_max_sync(0xffffffffu, unsigned(cnt));
 #pragma unroll 1
-    for (int i = 0; i < maxcnt; ++i) {
-      const unsigned active = __ballot_sync(0xffffffffu, i < cnt);
-      if (i < cnt) {
+    for (int ii = 0; ii < maxcnt; ++ii) {
+      const unsigned active = __ballot_sync(0xffffffffu, ii < cnt);
+      if (ii < cnt) {
+        const int i = ii < cnt_n ? ii : kPrBand - 1 - (ii - cnt_n);
         const int row0 = int(list[i * 32 + lane] >> 10);   // tile row of dy = -16
         uint32_t* base = tile + (row0 >> 1) * kPrTileW + lane;   // column of dx = -16
         const uint32_t* tp = btab + (row0 & 1) * (kPrBotCols * kPrBotWords);
@@ -625,78 +652,80 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
 // all eight link weights of a pixel are values of one field D[a] = |world[a] - world[0,0]| at the pixel and four of its
 // neighbours: the tile (+ 1-pixel halo) of D is computed once into shared memory - 1.3 square roots per pixel instead of
 // 5 - and the 48 output bytes per pixel leave as streaming 16-byte stores (nothing reads them back on the device).
-constexpr int kWtX = 32, kWtY = 8;
-static_assert(kWtY % 2 == 0 && ((1 - kPrHalo) & 1), "the fused merge pairs map rows (odd, odd + 1) with tile words");
+constexpr int kWtX = 32;
+static_assert(((1 - kPrHalo) & 1), "the fused merge pairs map rows (odd, odd + 1) with tile words");
 
 // kFromTiles: the height map does not exist yet - the block merges its cells from the pruned stamp kernel's tiles
 // (merged_cell) and also writes them to `map`, which saves the map's round trip through HBM and a launch.
-template <bool kFromTiles>
-__global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __restrict__ src, SceneDev P, PrunedDev Q,
+template <bool kStream>
+__device__ __forceinline__ void st16(float4* p, float4 v) {
+  if (kStream) __stcs(p, v);
+  else *p = v;
+}
+
+// kFromTiles: the height map does not exist yet - the block merges its cells from the pruned stamp kernel's tiles
+// and also writes them to `map`, which saves the map's round trip through HBM and a launch.  A tile word holds map rows
+// (y, y + 1) with y odd (r_min is odd), and a block's rows y0 - 1 .. y0 + kWtY (y0 even) are exactly kWtY / 2 + 1 such
+// pairs: warp w merges pair w for the block's 34 columns, so the band arithmetic is warp-uniform and a lane's share is
+// the strip choice and at most four 32-bit loads per two cells.
+template <bool kFromTiles, int kWtY, bool kStream, bool kLiteral>
+__global__ void __launch_bounds__(kWtX * kWtY, 1792 / (kWtX * kWtY)) weights_kernel(const uint32_t* __restrict__ src, SceneDev P, PrunedDev Q,
                                                              uint32_t* __restrict__ map_out, float4* __restrict__ world,
                                                              float4* __restrict__ conn0, float4* __restrict__ conn1) {
   __shared__ float fld[kWtY + 2][kWtX + 2];      // literal: D[a]; intent: h[a]
   __shared__ uint32_t cell[kWtY + 2][kWtX + 2];  // map values of the tile + halo
+  static_assert(kWtY % 2 == 0 && kWtY / 2 + 1 <= kWtY, "one warp per row pair");
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int x0 = blockIdx.x * kWtX, y0 = blockIdx.y * kWtY;
   const int f = blockIdx.z;
   const size_t npx = size_t(P.W) * P.H;
-  const uint32_t* M = src + size_t(f) * npx;
-  const uint16_t* S = reinterpret_cast<const uint16_t*>(src) + size_t(f) * Q.nstrips * Q.nbands * (2 * kPrTileWords);
-  const bool literal = P.weights_mode == 0;
   // world[0,0].y: cell (0,0) is on the border no stamp ever writes (pt_cloud.comp:67), so the merged value is 0
-  const float h00 = literal ? (kFromTiles ? 0.f : float(M[0])) : 0.f;
+  const float h00 = kLiteral ? (kFromTiles ? 0.f : float(src[size_t(f) * npx])) : 0.f;
+  auto put = [&](int ly, int lx, int gx, int gy, uint32_t m) {
+    float v = 0.f;
+    if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
+      const float h = float(m);
+      v = kLiteral ? dist3(float(gx), h, float(gy), 0.f, h00, 0.f) : h;
+    }
+    fld[ly][lx] = v;
+    cell[ly][lx] = m;
+  };
   if (kFromTiles) {
-    // A tile word holds map rows (y, y + 1) with y odd (r_min is odd), and a block's ten rows y0 - 1 .. y0 + 8 (y0 even)
-    // are exactly five such pairs: one thread per (pair, column) merges two cells from at most four 32-bit loads.
-    const int i = ty * kWtX + tx;
-    if (i < (kWtY / 2 + 1) * (kWtX + 2)) {
-      const int pr = i / (kWtX + 2), lx = i - pr * (kWtX + 2);
-      const int gx = x0 + lx - 1, gy = y0 - 1 + 2 * pr;
-      uint32_t w = 0u;
-      if (gx > 0 && gx < P.W - 1 && gy < P.H - 1) {   // gy + 1 >= 1 always; border cells are zeroed below
-        const uint32_t* S32 = reinterpret_cast<const uint32_t*>(S);
-        const int s1 = (gx + kPrHalo) / kStripW;
-        const int b1 = (gy - Q.r_min + kPrHalo) / kPrBand;
+    if (ty < kWtY / 2 + 1) {
+      const uint32_t* S32 = src + size_t(f) * Q.nstrips * Q.nbands * kPrTileWords;
+      const int gy = y0 - 1 + 2 * ty;                      // odd; rows gy, gy + 1 share the words of (at most) two bands
+      const int rr = gy - Q.r_min + kPrHalo;               // >= 0
+      const int b1 = rr / kPrBand, r1 = rr - b1 * kPrBand;  // band b1: tile row r1 in [0, 64); band b1 - 1: r1 + 64 (< 96 or absent)
+      const bool rows_ok = gy < P.H - 1;                   // else both rows are border / outside
+      const bool use_b1 = rows_ok && b1 < Q.nbands, use_b0 = rows_ok && b1 >= 1 && r1 + kPrBand < kPrBand + 2 * kPrHalo;
+      const int s_blk = x0 / kStripW;                      // kWtX == kStripW: the block's columns are strip s_blk's
+      for (int lx = tx; lx < kWtX + 2; lx += kWtX) {
+        const int gx = x0 + lx - 1;
+        uint32_t w = 0u;
+        if (gx > 0 && gx < P.W - 1) {
+          const int s1 = (gx + kPrHalo) / kStripW;         // s_blk - 1 .. s_blk + 1
+          (void)s_blk;
 #pragma unroll
-        for (int ds = 0; ds < 2; ++ds) {
-          const int sidx = s1 - ds;
-          if (sidx < 0 || sidx >= Q.nstrips) continue;
-          const int c = gx - sidx * kStripW + kPrHalo;
-#pragma unroll
-          for (int db = 0; db < 2; ++db) {
-            const int b = b1 - db;
-            const int r = gy - Q.r_min - b * kPrBand + kPrHalo;
-            if (b < 0 || b >= Q.nbands || r >= kPrBand + 2 * kPrHalo) continue;
-            w = __vmaxu2(w, __ldg(S32 + size_t(sidx * Q.nbands + b) * kPrTileWords + (r >> 1) * kPrTileW + c));
+          for (int ds = 0; ds < 2; ++ds) {
+            const int sidx = s1 - ds;
+            if (sidx < 0 || sidx >= Q.nstrips) continue;
+            const int c = gx - sidx * kStripW + kPrHalo;
+            const uint32_t* T0 = S32 + size_t(sidx * Q.nbands) * kPrTileWords + c;
+            if (use_b1) w = __vmaxu2(w, __ldg(T0 + size_t(b1) * kPrTileWords + (r1 >> 1) * kPrTileW));
+            if (use_b0) w = __vmaxu2(w, __ldg(T0 + size_t(b1 - 1) * kPrTileWords + ((r1 + kPrBand) >> 1) * kPrTileW));
           }
         }
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int y = gy + h;
-        const uint32_t m = (y > 0 && y < P.H - 1) ? ((w >> (16 * h)) & 0xFFFFu) : 0u;
-        float v = 0.f;
-        if (gx >= 0 && gx < P.W && y >= 0 && y < P.H) {
-          const float hh = float(m);
-          v = literal ? dist3(float(gx), hh, float(y), 0.f, h00, 0.f) : hh;
-        }
-        fld[2 * pr + h][lx] = v;
-        cell[2 * pr + h][lx] = m;
+        put(2 * ty, lx, gx, gy, gy > 0 ? (w & 0xFFFFu) : 0u);
+        put(2 * ty + 1, lx, gx, gy + 1, (gy + 1 > 0 && gy + 1 < P.H - 1) ? (w >> 16) : 0u);
       }
     }
   } else {
+    const uint32_t* M = src + size_t(f) * npx;
     for (int i = ty * kWtX + tx; i < (kWtY + 2) * (kWtX + 2); i += kWtX * kWtY) {
       const int ly = i / (kWtX + 2), lx = i - ly * (kWtX + 2);
       const int gx = x0 + lx - 1, gy = y0 + ly - 1;
-      float v = 0.f;
-      uint32_t m = 0u;
-      if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
-        m = __ldg(M + size_t(gy) * P.W + gx);
-        const float h = float(m);
-        v = literal ? dist3(float(gx), h, float(gy), 0.f, h00, 0.f) : h;
-      }
-      fld[ly][lx] = v;
-      cell[ly][lx] = m;
+      const bool in = gx >= 0 && gx < P.W && gy >= 0 && gy < P.H;
+      put(ly, lx, gx, gy, in ? __ldg(M + size_t(gy) * P.W + gx) : 0u);
     }
   }
   __syncthreads();
@@ -708,18 +737,18 @@ __global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __
   auto F = [&](int dx, int dy) { return fld[ty + 1 + dy][tx + 1 + dx]; };
   // weight of the link from pixel a = p + (adx, ady) (the "pos" of the shader invocation) to b = p + (bdx, bdy)
   auto link = [&](int adx, int ady, int bdx, int bdy) {
-    if (literal) return F(adx, ady);
+    if (kLiteral) return F(adx, ady);   // pack() == 0 -> unpack loads world[0,0]
     return dist3(float(x + adx), F(adx, ady), float(y + ady), float(x + bdx), F(bdx, bdy), float(y + bdy));
   };
   const bool nxmin = x > 0, nxmax = x < P.W - 1, nymin = y > 0, nymax = y < P.H - 1;
-  if (world) __stcs(world + idx, make_float4(float(x), float(mine), float(y), 0.f));  // :59-69
+  if (world) st16<kStream>(world + idx, make_float4(float(x), float(mine), float(y), 0.f));  // :59-69
   if (conn1) {  // :86-107  (below, below-left, left, above-left)
     float4 c;
     c.x = nymax ? link(0, 0, 0, 1) : -1.f;
     c.y = (nxmin && nymax) ? link(0, 0, -1, 1) : -1.f;
     c.z = nxmin ? link(0, 0, -1, 0) : -1.f;
     c.w = (nxmin && nymin) ? link(0, 0, -1, -1) : -1.f;
-    __stcs(conn1 + idx, c);
+    st16<kStream>(conn1 + idx, c);
   }
   if (conn0) {  // :112-122  conn1[up].r, conn1[up-right].g, conn1[right].b, conn1[down-right].a
     float4 c;
@@ -727,7 +756,93 @@ __global__ void __launch_bounds__(kWtX * kWtY) weights_kernel(const uint32_t* __
     c.y = (nxmax && nymin) ? link(1, -1, 0, 0) : -1.f;
     c.z = nxmax ? link(1, 0, 0, 0) : -1.f;
     c.w = (nxmax && nymax) ? link(1, 1, 0, 0) : -1.f;
-    __stcs(conn0 + idx, c);
+    st16<kStream>(conn0 + idx, c);
+  }
+}
+
+// ------------------------------------------------------------------ weights, literal mode, lean form (default)
+// The general kernel above spends ~230 instructions per pixel and runs at half the rate a pure 52-byte-per-pixel writer
+// could (measured: 3.5 TB/s against 7.5 TB/s for a memset) - it is instruction-bound.  In literal mode every link weight
+// is a value of the one field D (see above), so this kernel keeps D for a 32 x 32 pixel block (+ halo) in shared memory
+// and lets each warp walk four rows of one 32-column strip: per pixel three shared loads (D below, D below-right, the
+// map cell), the boundary selects, and four 16-byte streaming stores with pointer increments.
+constexpr int kWfRows = 32, kWfThreads = 256, kWfWarpRows = kWfRows / (kWfThreads / 32);
+
+template <bool kFromTiles>
+__global__ void __launch_bounds__(kWfThreads) weights_literal_kernel(const uint32_t* __restrict__ src, SceneDev P, PrunedDev Q,
+                                                                     uint32_t* __restrict__ map_out, float4* __restrict__ world,
+                                                                     float4* __restrict__ conn0, float4* __restrict__ conn1) {
+  __shared__ float fld[kWfRows + 2][kWtX + 2];
+  __shared__ uint32_t cell[kWfRows + 2][kWtX + 2];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kWtX, y0 = blockIdx.y * kWfRows;
+  const int f = blockIdx.z;
+  const size_t npx = size_t(P.W) * P.H;
+  const float h00 = kFromTiles ? 0.f : float(src[size_t(f) * npx]);   // cell (0,0) is never stamped (pt_cloud.comp:67)
+  auto put = [&](int ly, int lx, int gx, int gy, uint32_t m) {
+    float v = 0.f;
+    if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) v = dist3(float(gx), float(m), float(gy), 0.f, h00, 0.f);
+    fld[ly][lx] = v;
+    cell[ly][lx] = m;
+  };
+  if (kFromTiles) {
+    // row pairs (y, y + 1), y odd, are the words of the stamp tiles: (kWfRows / 2 + 1) pairs x 34 columns
+    const uint32_t* S32 = src + size_t(f) * Q.nstrips * Q.nbands * kPrTileWords;
+    for (int i = tid; i < (kWfRows / 2 + 1) * (kWtX + 2); i += kWfThreads) {
+      const int pr = i / (kWtX + 2), lx = i - pr * (kWtX + 2);
+      const int gx = x0 + lx - 1, gy = y0 - 1 + 2 * pr;
+      uint32_t w = 0u;
+      if (gx > 0 && gx < P.W - 1 && gy < P.H - 1) {
+        const int rr = gy - Q.r_min + kPrHalo;
+        const int b1 = rr / kPrBand, r1 = rr - b1 * kPrBand;
+        const int s1 = (gx + kPrHalo) / kStripW;
+#pragma unroll
+        for (int ds = 0; ds < 2; ++ds) {
+          const int sidx = s1 - ds;
+          if (sidx < 0 || sidx >= Q.nstrips) continue;
+          const uint32_t* T0 = S32 + size_t(sidx * Q.nbands) * kPrTileWords + (gx - sidx * kStripW + kPrHalo);
+          if (b1 < Q.nbands) w = __vmaxu2(w, __ldg(T0 + size_t(b1) * kPrTileWords + (r1 >> 1) * kPrTileW));
+          if (b1 >= 1 && r1 < 2 * kPrHalo) w = __vmaxu2(w, __ldg(T0 + size_t(b1 - 1) * kPrTileWords + ((r1 + kPrBand) >> 1) * kPrTileW));
+        }
+      }
+      put(2 * pr, lx, gx, gy, gy > 0 ? (w & 0xFFFFu) : 0u);
+      put(2 * pr + 1, lx, gx, gy + 1, (gy + 1 > 0 && gy + 1 < P.H - 1) ? (w >> 16) : 0u);
+    }
+  } else {
+    const uint32_t* M = src + size_t(f) * npx;
+    for (int i = tid; i < (kWfRows + 2) * (kWtX + 2); i += kWfThreads) {
+      const int ly = i / (kWtX + 2), lx = i - ly * (kWtX + 2);
+      const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+      const bool in = gx >= 0 && gx < P.W && gy >= 0 && gy < P.H;
+      put(ly, lx, gx, gy, in ? __ldg(M + size_t(gy) * P.W + gx) : 0u);
+    }
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int x = x0 + lane;
+  if (x >= P.W) return;
+  const bool nxmin = x > 0, nxmax = x < P.W - 1;
+  const float fx = float(x);
+  const int ly0 = warp * kWfWarpRows;   // first row of this warp inside the block
+  float d_up = fld[ly0][lane + 1], dr_up = fld[ly0][lane + 2];             // row y - 1: D[x], D[x + 1]
+  float d_me = fld[ly0 + 1][lane + 1], dr_me = fld[ly0 + 1][lane + 2];     // row y
+  size_t idx = size_t(f) * npx + size_t(y0 + ly0) * P.W + x;
+#pragma unroll
+  for (int k = 0; k < kWfWarpRows; ++k) {
+    const int y = y0 + ly0 + k;
+    if (y >= P.H) break;   // warp-uniform
+    const float d_dn = fld[ly0 + k + 2][lane + 1], dr_dn = fld[ly0 + k + 2][lane + 2];
+    const uint32_t mine = cell[ly0 + k + 1][lane + 1];
+    const bool nymin = y > 0, nymax = y < P.H - 1;
+    if (kFromTiles) map_out[idx] = mine;
+    if (world) __stcs(world + idx, make_float4(fx, float(mine), float(y), 0.f));  // :59-69
+    if (conn1)   // :86-107 (below, below-left, left, above-left): every present link is D[p]
+      __stcs(conn1 + idx, make_float4(nymax ? d_me : -1.f, (nxmin && nymax) ? d_me : -1.f, nxmin ? d_me : -1.f, (nxmin && nymin) ? d_me : -1.f));
+    if (conn0)   // :112-122 conn1[up].r, conn1[up-right].g, conn1[right].b, conn1[down-right].a
+      __stcs(conn0 + idx, make_float4(nymin ? d_up : -1.f, (nxmax && nymin) ? dr_up : -1.f, nxmax ? dr_me : -1.f, (nxmax && nymax) ? dr_dn : -1.f));
+    d_up = d_me; dr_up = dr_me;
+    d_me = d_dn; dr_me = dr_dn;
+    idx += size_t(P.W);
   }
 }
 
@@ -832,7 +947,8 @@ bool build_pruned_tables(const std::vector<uint16_t>& lut_t, int H, int st, cons
       }
     for (int k = 0; k < kPrClasses; ++k) {
       const int v = seen[k] < 0 ? 0 : seen[k];
-      if (y > 0 && v < out->ttab[size_t(y - 1) * 2 * kPrRowWords + k]) return false;  // dominance needs monotone in val
+      if (y > 0 && v < out->ttab[size_t(y - 1) * 2 * kPrRowWords + k]) return false;  // dominance needs monotone in val ...
+      if (k > 0 && v > out->ttab[size_t(y) * 2 * kPrRowWords + k - 1]) return false;    // ... and non-increasing in d2 (classes ascend in d2)
       out->ttab[size_t(y) * 2 * kPrRowWords + k] = uint16_t(v);
     }
   }
@@ -892,6 +1008,9 @@ struct tod_scene {
   PrunedDev pruned{};
   bool pruned_ok = false;
   int stamp_impl = 0;
+  int weights_variant = 3;
+  int chunk_frames = 0;      // frames per land -> stamp -> weights round (0 = the whole batch at once)
+  int timed_frames = 0, timed_total = 0;
   bool own_results = false;   // the last append call left map / world / conn / balls in the handle's own buffers
   cudaEvent_t caller_done = nullptr;  // recorded on a caller's stream so that materialize can order itself behind it
   // per-batch buffers
@@ -961,6 +1080,9 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
   s->device = device;
   s->prm = p;
   s->stamp_impl = std::getenv("TOD_STAMP_IMPL") ? std::atoi(std::getenv("TOD_STAMP_IMPL")) : 0;
+  s->weights_variant = std::getenv("TOD_WEIGHTS_VARIANT") ? std::atoi(std::getenv("TOD_WEIGHTS_VARIANT")) : 3;
+  // default chunk: what keeps ~2.7 MB of inter-kernel data per 640x480 frame inside ~3/4 of the L2
+  s->chunk_frames = std::getenv("TOD_SCENE_CHUNK") ? std::atoi(std::getenv("TOD_SCENE_CHUNK")) : 0;
   const int W = p.width, H = p.height, st = p.terrain_norm_const, sb = p.bot_norm_const;
   const int smax = st > sb ? st : sb;
   s->dev = SceneDev{W, H, st, sb, 2 * smax + 2, 2 * smax, p.max_depth_in, p.sample_shift, p.weights_mode};
@@ -1084,12 +1206,13 @@ int tod_scene_create(int device, const tod_scene_params* params, tod_scene** out
 }
 
 // kernels only; all pointers on the device
-static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n, uint32_t* d_map,
-                     float* d_world, float* d_conn0, float* d_conn1, float* d_balls, cudaStream_t st, bool timed) {
+// One chunk of frames through land -> stamp -> (merge +) weights -> balls.  The caller cuts a batch into chunks small enough
+// that what one kernel leaves for the next (land + row ranges 0.7 MB, stamp tiles 2 MB per 640x480 frame) is still in the
+// 126 MB L2 when it is read back; the 52 output bytes per pixel leave with streaming stores.
+static int scene_chunk(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n, uint32_t* d_map, float* d_world,
+                       float* d_conn0, float* d_conn1, float* d_balls, cudaStream_t st, bool timed) {
   const SceneDev& P = s->dev;
   const int64_t npx = int64_t(P.W) * P.H;
-  TOD_CUDA(cudaMemsetAsync(s->row_robot, 0, size_t(n) * P.H * sizeof(unsigned int), st));
-  TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(n) * kMaxBalls * 3 * sizeof(unsigned long long), st));
   const unsigned blocks = unsigned((npx * n + 255) / 256);
   const int nstrips = (P.W + kStripW - 1) / kStripW;
   land_kernel<<<dim3(nstrips, (P.H + 8 * kLandRows - 1) / (8 * kLandRows), n), dim3(32, 8), 0, st>>>(d_depth, d_target, s->cy, s->cx, P, s->land, s->row_robot, s->ball_sums,
@@ -1101,7 +1224,6 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   // structure a kernel relies on falls through to the next one; all four produce the same bytes.
   const int impl_env = s->stamp_impl;   // read from the environment when the handle was created
   const bool want_weights = d_world || d_conn0 || d_conn1;
-  const dim3 wgrid((P.W + kWtX - 1) / kWtX, (P.H + kWtY - 1) / kWtY, n), wblock(kWtX, kWtY);
   bool merged_in_weights = false;
   if (impl_env <= 0 && s->pruned_ok) {
     stamp_pruned_kernel<<<dim3(nstrips * s->pruned.nbands, n), 32, 0, st>>>(s->land, s->rowinfo_t, s->rowinfo_b, s->ttab, s->btab, s->bspan, P,
@@ -1115,16 +1237,63 @@ static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_ta
   else
     stamp_kernel<<<grid, 32, s->stamp_smem, st>>>(s->land, s->row_robot, s->lut_t, s->span_t, s->lut_b, s->span_b, P, d_map);
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[1], st));
-  if (merged_in_weights)
-    weights_kernel<true><<<wgrid, wblock, 0, st>>>(s->staging, P, s->pruned, d_map, reinterpret_cast<float4*>(d_world),
-                                                   reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
-  else if (want_weights)
-    weights_kernel<false><<<wgrid, wblock, 0, st>>>(d_map, P, s->pruned, nullptr, reinterpret_cast<float4*>(d_world),
-                                                    reinterpret_cast<float4*>(d_conn0), reinterpret_cast<float4*>(d_conn1));
+  if (want_weights) {
+    float4 *w4 = reinterpret_cast<float4*>(d_world), *c04 = reinterpret_cast<float4*>(d_conn0), *c14 = reinterpret_cast<float4*>(d_conn1);
+    const uint32_t* src = merged_in_weights ? s->staging : d_map;
+    uint32_t* mo = merged_in_weights ? d_map : nullptr;
+#define TOD_WT(FT, WY, CS)                                                                                                          \
+  do {                                                                                                                              \
+    const dim3 g_((P.W + kWtX - 1) / kWtX, (P.H + WY - 1) / WY, n), b_(kWtX, WY);                                                   \
+    if (P.weights_mode == 0) weights_kernel<FT, WY, CS, true><<<g_, b_, 0, st>>>(src, P, s->pruned, mo, w4, c04, c14);             \
+    else weights_kernel<FT, WY, CS, false><<<g_, b_, 0, st>>>(src, P, s->pruned, mo, w4, c04, c14);                                \
+  } while (0)
+    const int v = s->weights_variant;   // TOD_WEIGHTS_VARIANT: 3 (default) = lean literal-mode kernel; 0 / 1 / 2 = general kernel with 4 / 8 / 16 rows per block
+    if (P.weights_mode == 0 && v == 3) {
+      const dim3 g_((P.W + kWtX - 1) / kWtX, (P.H + kWfRows - 1) / kWfRows, n);
+      if (merged_in_weights) weights_literal_kernel<true><<<g_, kWfThreads, 0, st>>>(src, P, s->pruned, mo, w4, c04, c14);
+      else weights_literal_kernel<false><<<g_, kWfThreads, 0, st>>>(src, P, s->pruned, mo, w4, c04, c14);
+    } else if (merged_in_weights) {
+      switch (v) {
+        case 0: TOD_WT(true, 4, true); break;
+        case 2: TOD_WT(true, 16, true); break;
+        case 9: TOD_WT(true, 8, false); break;
+        default: TOD_WT(true, 8, true); break;
+      }
+    } else {
+      TOD_WT(false, 8, true);
+    }
+#undef TOD_WT
+  }
   if (timed) TOD_CUDA(cudaEventRecord(s->ev[2], st));
   if (d_balls) balls_kernel<<<(n * kMaxBalls + 127) / 128, 128, 0, st>>>(s->ball_sums, d_balls, n * kMaxBalls);
   TOD_CUDA(cudaGetLastError());
+  return TOD_OK;
+}
+
+// kernels only; all pointers on the device
+static int scene_run(tod_scene* s, const uint16_t* d_depth, const uint16_t* d_target, int n, uint32_t* d_map,
+                     float* d_world, float* d_conn0, float* d_conn1, float* d_balls, cudaStream_t st, bool timed) {
+  const SceneDev& P = s->dev;
+  const size_t npx = size_t(P.W) * P.H;
+  TOD_CUDA(cudaMemsetAsync(s->row_robot, 0, size_t(n) * P.H * sizeof(unsigned int), st));
+  TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(n) * kMaxBalls * 3 * sizeof(unsigned long long), st));
+  const int chunk = s->chunk_frames > 0 ? s->chunk_frames : n;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int cn = std::min(chunk, n - c0);
+    const bool last = c0 + cn >= n;
+    // per-chunk scratch (land, row ranges, tiles, ball sums, robot flags) is reused: the kernels of consecutive chunks
+    // are ordered by the stream.  The timing events bracket the last chunk only; tod_scene_last_kernel_ms scales them.
+    TOD_TRY(scene_chunk(s, d_depth + c0 * npx, d_target + c0 * npx, cn, d_map + c0 * npx, d_world ? d_world + c0 * npx * 4 : nullptr,
+                        d_conn0 ? d_conn0 + c0 * npx * 4 : nullptr, d_conn1 ? d_conn1 + c0 * npx * 4 : nullptr,
+                        d_balls ? d_balls + size_t(c0) * kMaxBalls * 4 : nullptr, st, timed && last));
+    if (!last) {
+      TOD_CUDA(cudaMemsetAsync(s->row_robot, 0, size_t(cn) * P.H * sizeof(unsigned int), st));
+      TOD_CUDA(cudaMemsetAsync(s->ball_sums, 0, size_t(cn) * kMaxBalls * 3 * sizeof(unsigned long long), st));
+    }
+    s->timed_frames = cn;
+  }
   s->timed = timed;
+  s->timed_total = n;
   return TOD_OK;
 }
 
@@ -1197,8 +1366,16 @@ int tod_scene_last_kernel_ms(tod_scene* s, float* stamp_ms, float* weights_ms) {
   if (!s->timed) return fail(TOD_ERR_INVALID_ARG, "tod_scene_last_kernel_ms: the last call ran on a caller stream and was not timed");
   TOD_CUDA(cudaSetDevice(s->device));
   TOD_CUDA(cudaEventSynchronize(s->ev[2]));
-  if (stamp_ms) TOD_CUDA(cudaEventElapsedTime(stamp_ms, s->ev[0], s->ev[1]));
-  if (weights_ms) TOD_CUDA(cudaEventElapsedTime(weights_ms, s->ev[1], s->ev[2]));
+  // the events bracket the last chunk of the call: scale to the whole batch
+  const float scale = s->timed_frames > 0 ? float(s->timed_total) / float(s->timed_frames) : 1.f;
+  if (stamp_ms) {
+    TOD_CUDA(cudaEventElapsedTime(stamp_ms, s->ev[0], s->ev[1]));
+    *stamp_ms *= scale;
+  }
+  if (weights_ms) {
+    TOD_CUDA(cudaEventElapsedTime(weights_ms, s->ev[1], s->ev[2]));
+    *weights_ms *= scale;
+  }
   return TOD_OK;
 }
 
