@@ -254,6 +254,27 @@ int tod_pool_rgbd_batch(tod_pool* p, const tod_scene_params* scene_params, uint3
                         uint32_t* map, float* world4, float* conn0, float* conn1, float* balls4);
 
 /* ======================================================================================
+ * Path: the Scene's consumer.  <- `path::modify_path` (src/path.rs:25-120) and `Path::serialize`
+ * (path.rs:17-21).  The reference function cannot complete on any input (224*224-element arrays indexed with 640x480
+ * node numbers, path.rs:29-30,38,99; cost[usize::MAX - 2] on the last extraction step, path.rs:105) and is never
+ * reached (main.rs:92): tod_path_reference_panics() == 1 states that, and tod_path_modify computes the evident intent
+ * (rules in DESIGN.md §5.5 / oracle/path.cpp): multi-target shortest paths over Scene::neighbors' 4-neighbourhood with
+ * edge weight connections[node][cn] + |height[node] - height[neighbor]| (path.rs:64), then the (magnitude, rotation)
+ * list walked from START_NODE = W*H - H/2 as path.rs:99-117.
+ *   height f32[W*H], pos3 f32[W*H][3], balls2 i32[>=3][2], connections8 f32[W*H][8]: the Scene (tod_scene_materialize)
+ *   cost_out f32[W*H] / pred_out i32[W*H] (may be NULL): converged costs (f32::MAX = unreached) and predecessors
+ *                 (-2 = target, -1 = none)
+ *   directions f32[cap][2], *n_directions = entries of the path (may exceed cap; -1 = start cannot reach a target)
+ * ====================================================================================== */
+int tod_path_reference_panics(void);
+int tod_path_modify(int device, int width, int height_px, const float* height, const float* pos3, const int32_t* balls2,
+                    const float* connections8, float* cost_out, int32_t* pred_out, float* directions, int cap,
+                    int32_t* n_directions);
+/* Path::serialize: u64 seconds since the epoch, big-endian, then big-endian f32 (magnitude, rotation) pairs - what
+ * handle_path_request writes to the RoboRIO socket (path.rs:158-162).  *bytes = 8 + 8 n. */
+int tod_path_serialize(uint64_t created_secs, const float* directions, int n, uint8_t* out, size_t cap, size_t* bytes);
+
+/* ======================================================================================
  * Micro-benchmark used as the int8 roofline denominator (MEASURED_PEAKS.json has no int8 peak,
  * SURVEY §8d): a plain tcgen05 kind::i8 GEMM  C[M,N] s32 = A[M,K] s8 * B[N,K]^T s8.
  * ====================================================================================== */

@@ -117,6 +117,31 @@ def pt_cloud_weights(m, params=None):
     return world, c0, c1
 
 
+def path_modify(height, pos, balls, connections, width=640, height_px=480, cap=4096):
+    """path.rs:25-120 in intent mode (see oracle/path.cpp): returns dict(cost, pred, directions [n,2] or None if unreachable)"""
+    n = width * height_px
+    h = _c(height, np.float32).reshape(n)
+    p3 = _c(pos, np.float32).reshape(n, 3)
+    b2 = _c(balls, np.int32).reshape(-1, 2)
+    c8 = _c(connections, np.float32).reshape(n, 8)
+    cost = np.zeros(n, np.float32)
+    pred = np.zeros(n, np.int32)
+    dirs = np.zeros((cap, 2), np.float32)
+    L = lib()
+    L.tod_oracle_path_modify.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
+    k = L.tod_oracle_path_modify(width, height_px, _p(h), _p(p3), _p(b2), _p(c8), _p(cost), _p(pred), _p(dirs), cap)
+    return dict(cost=cost, pred=pred, directions=None if k < 0 else dirs[:min(k, cap)].copy(), n=k)
+
+
+def path_serialize(created_secs, directions):
+    d = _c(directions, np.float32).reshape(-1, 2)
+    out = np.zeros(8 + 8 * len(d), np.uint8)
+    L = lib()
+    L.tod_oracle_path_serialize.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
+    L.tod_oracle_path_serialize(int(created_secs), _p(d), len(d), _p(out))
+    return out.tobytes()
+
+
 def scene_materialize(m, world, c0, c1, balls):
     n = m.size
     height = np.zeros(n, np.float32)

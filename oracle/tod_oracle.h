@@ -36,6 +36,12 @@ void tod_oracle_scene_materialize(int npx, const uint32_t* map, const float* wor
                                   const float* conn1, const float* balls4, float* height, float* pos3,
                                   int32_t* balls2, float* connections8);
 
+/* ---------------- path.rs (path.cpp): the Scene's consumer ---------------- */
+int tod_oracle_path_literal_panics(void);
+int tod_oracle_path_modify(int W, int H, const float* height, const float* pos3, const int32_t* balls2, const float* conn8,
+                           float* cost, int32_t* pred, float* dirs, int cap);
+int tod_oracle_path_serialize(uint64_t created_secs, const float* dirs, int n, uint8_t* out);
+
 /* ---------------- yolact.rs literal pre/post-processing (yolact_post.cpp) ---------------- */
 /* yolact.rs:169-188 */
 void tod_oracle_dequant_u8(const uint8_t* q, int n, float scale, int zero_point, float* out);

@@ -8,4 +8,5 @@ Nothing here computes on the CPU and nothing here imports the test oracle.
 from ._lib import LIB_PATH, SYMBOLS, TodError, build, device_count, lib  # noqa: F401
 from .scene import Scene, SceneBuilder, default_params  # noqa: F401
 from . import shard  # noqa: F401
+from .path import Path, modify_path  # noqa: F401
 from .yolact import Pool, Yolact, YolactPool, model_inspect  # noqa: F401

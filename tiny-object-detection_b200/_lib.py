@@ -28,6 +28,7 @@ SYMBOLS = [
     "tod_conv_selftest_ex", "tod_i8_mma_peak", "tod_yolact_step_macs", "tod_yolact_trace_steps", "tod_yolact_fetch_output_f32",
     "tod_yolact_input_info", "tod_pool_create", "tod_pool_destroy", "tod_pool_num_devices", "tod_pool_num_handles",
     "tod_pool_infer_tiles", "tod_pool_classify_batch", "tod_pool_rgbd_batch",
+    "tod_path_reference_panics", "tod_path_modify", "tod_path_serialize",
 ]
 
 
@@ -119,6 +120,8 @@ def lib():
         L.tod_pool_infer_tiles.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
         L.tod_pool_classify_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.tod_pool_rgbd_batch.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+        L.tod_path_modify.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+        L.tod_path_serialize.argtypes = [C.c_uint64, vp, C.c_int, vp, C.c_size_t, vp]
         _lib = L
     return _lib
 
