@@ -636,6 +636,23 @@ def main():
         except Exception as e:  # never let the side measurement break the headline line
             line.setdefault("fused_rgbd", {})["error"] = str(e)[:200]
 
+    # ---- the Scene's consumer: path::modify_path on one materialised 640x480 scene, rank 0 only
+    if not args.no_scene and rank == 0:
+        try:
+            sp1 = tod_b200.SceneBuilder(device=local_rank, max_batch=1, weights_mode=1)
+            d1 = synth.depth_frames(1, seed=18)
+            sp1.append_batch(d1, synth.target_frames(1, seed=19), want=())
+            sc1 = sp1.materialize(0)
+            sc1.balls[:3] = [(100, 60), (500, 200), (320, 400)]
+            tod_b200.modify_path(sc1, device=local_rank)
+            t0 = time.perf_counter()
+            pth = tod_b200.modify_path(sc1, device=local_rank)
+            line["path"] = {"ms_per_scene": 1e3 * (time.perf_counter() - t0), "directions": 0 if pth is None else int(len(pth.directions)),
+                            "call": "tod_path_modify (host Scene in: 13.5 MB; GPU relaxation to the fixed point; (magnitude, rotation) list out), intent mode - the reference function panics on every input"}
+            del sp1
+        except Exception as e:
+            line["path"] = {"error": str(e)[:200]}
+
     # ---- CPU baseline (oracle port of the reference's CPU path), rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle

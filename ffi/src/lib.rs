@@ -21,6 +21,8 @@ pub mod sys {
     pub struct tod_scene { _private: [u8; 0] }
     #[repr(C)]
     pub struct tod_yolact { _private: [u8; 0] }
+    #[repr(C)]
+    pub struct tod_pool { _private: [u8; 0] }
 
     #[repr(C)]
     #[derive(Clone, Copy)]
@@ -70,6 +72,18 @@ pub mod sys {
         pub fn tod_yolact_destroy(y: *mut tod_yolact);
         pub fn tod_yolact_classify(y: *mut tod_yolact, frame: *mut u32, width: c_int, height: c_int) -> c_int;
         pub fn tod_yolact_classify_batch(y: *mut tod_yolact, frames: *mut u32, n: c_int, width: c_int, height: c_int) -> c_int;
+        // frame sharder over every GPU of the box (include/tod.h "Pool")
+        pub fn tod_pool_create(path: *const c_char, devices: *const i32, n_devices: c_int, depth: c_int,
+                               opts: *const tod_yolact_options, out: *mut *mut tod_pool) -> c_int;
+        pub fn tod_pool_destroy(p: *mut tod_pool);
+        pub fn tod_pool_classify_batch(p: *mut tod_pool, frames: *mut u32, n: c_int, width: c_int, height: c_int) -> c_int;
+        pub fn tod_pool_rgbd_batch(p: *mut tod_pool, scene_params: *const tod_scene_params, frames: *mut u32, depth: *const u16, n: c_int,
+                                   map: *mut u32, world4: *mut f32, conn0: *mut f32, conn1: *mut f32, balls4: *mut f32) -> c_int;
+        // the Scene's consumer (path.rs)
+        pub fn tod_path_modify(device: c_int, width: c_int, height_px: c_int, height: *const f32, pos3: *const f32, balls2: *const i32,
+                               connections8: *const f32, cost_out: *mut f32, pred_out: *mut i32, directions: *mut f32, cap: c_int,
+                               n_directions: *mut i32) -> c_int;
+        pub fn tod_path_serialize(created_secs: u64, directions: *const f32, n: c_int, out: *mut u8, cap: usize, bytes: *mut usize) -> c_int;
     }
 }
 
@@ -154,17 +168,19 @@ impl SceneGpu {
         assert!(depth.len() == N && target.len() == N);
         let null = std::ptr::null_mut::<c_void>();
         let mut height = vec![0f32; N];
-        let mut pos = vec![(0f32, 0f32, 0f32); N];
-        let mut balls = vec![(0i32, 0i32); 100];
+        // The C side writes flat scalars.  Arrays have a guaranteed layout; Rust tuples do not (`repr(Rust)` may reorder
+        // or pad), so the tuple-typed `Scene` fields are filled by an explicit conversion, exactly as scene.rs:316-322 does.
+        let mut pos3 = vec![[0f32; 3]; N];
+        let mut balls2 = vec![[0i32; 2]; 100];
         let mut connections = vec![[0f32; 8]; N];
         unsafe {
             expect(sys::tod_scene_append_batch(self.handle, depth.as_ptr(), target.as_ptr(), 1, null as *mut u32, null as *mut f32,
                                                null as *mut f32, null as *mut f32, null as *mut f32), "append_scene");
-            // scene.rs:312-327, done on the device: (f32,f32,f32), (i32,i32) and [f32;8] are plain #[repr(Rust)] tuples /
-            // arrays of one scalar type, laid out as consecutive scalars
-            expect(sys::tod_scene_materialize(self.handle, 0, height.as_mut_ptr(), pos.as_mut_ptr() as *mut f32,
-                                              balls.as_mut_ptr() as *mut i32, connections.as_mut_ptr() as *mut f32), "append_scene");
+            expect(sys::tod_scene_materialize(self.handle, 0, height.as_mut_ptr(), pos3.as_mut_ptr() as *mut f32,
+                                              balls2.as_mut_ptr() as *mut i32, connections.as_mut_ptr() as *mut f32), "append_scene");
         }
+        let pos = pos3.iter().map(|p| (p[0], p[1], p[2])).collect();
+        let balls = balls2.iter().map(|b| (b[0], b[1])).collect();
         Scene { height, pos, balls, connections }
     }
 }
@@ -173,4 +189,41 @@ impl Drop for SceneGpu {
     fn drop(&mut self) {
         unsafe { sys::tod_scene_destroy(self.handle) }
     }
+}
+
+/// `path::Path` (src/path.rs:11-22) and the planner step `modify_path` (path.rs:25-120, intent mode: the reference
+/// function indexes 224*224-element arrays with 640x480 node numbers and panics on every input).
+pub struct Path {
+    pub created: std::time::SystemTime,
+    pub directions: Vec<(f32, f32)>,
+}
+
+impl Path {
+    /// path.rs:17-21: big-endian seconds since the epoch, then big-endian (magnitude, rotation) pairs.
+    pub fn serialize(&self) -> Vec<u8> {
+        let secs = self.created.duration_since(std::time::UNIX_EPOCH).expect("Incorrect System Time").as_secs();
+        let flat: Vec<[f32; 2]> = self.directions.iter().map(|d| [d.0, d.1]).collect();
+        let mut out = vec![0u8; 8 + 8 * flat.len()];
+        let mut n = 0usize;
+        expect(unsafe { sys::tod_path_serialize(secs, flat.as_ptr() as *const f32, flat.len() as c_int, out.as_mut_ptr(), out.len(), &mut n) },
+               "Path::serialize");
+        out.truncate(n);
+        out
+    }
+}
+
+/// `modify_path(path, scene)`: overwrites `path` with the route from the start node to the nearest ball.
+pub fn modify_path(path: &mut Path, scene: &Scene, device: i32) {
+    let pos3: Vec<[f32; 3]> = scene.pos.iter().map(|p| [p.0, p.1, p.2]).collect();
+    let balls2: Vec<[i32; 2]> = scene.balls.iter().map(|b| [b.0, b.1]).collect();
+    let cap = 640 * 480;
+    let mut dirs = vec![[0f32; 2]; cap];
+    let mut n: i32 = 0;
+    expect(unsafe {
+        sys::tod_path_modify(device, 640, 480, scene.height.as_ptr(), pos3.as_ptr() as *const f32, balls2.as_ptr() as *const i32,
+                             scene.connections.as_ptr() as *const f32, std::ptr::null_mut(), std::ptr::null_mut(),
+                             dirs.as_mut_ptr() as *mut f32, cap as c_int, &mut n)
+    }, "modify_path");
+    dirs.truncate(n.max(0) as usize);
+    *path = Path { created: std::time::SystemTime::now(), directions: dirs.iter().map(|d| (d[0], d[1])).collect() };
 }

@@ -72,51 +72,40 @@ __global__ void __launch_bounds__(256) land_kernel(const uint16_t* __restrict__ 
   const float cxv = valid ? cx_tab[x] : 0.f;
   const float fh = float(P.H);
   const unsigned full = 0xffffffffu;
+  const size_t ri0 = (size_t(f) * gridDim.x + blockIdx.x) * P.H;
+  uint16_t* lrow = land + fbase + size_t(y0) * P.W + x;
 #pragma unroll
   for (int r = 0; r < kLandRows; ++r) {
     const int y = y0 + r;
-    if (y >= P.H) break;  // warp-uniform
-    int kind = kKindNone, enc = 0;
-    if (valid) {
-      const int cls = tv[r] & 0xFF, id = tv[r] >> 8;  // R8G8 little-endian upload (scene.rs:198)
-      // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
-      const float de = __fmul_rn(__fmul_rn(float(dv[r]), cy_tab[y]), cxv);
-      // :98  int(float(height) * depth / max_depth_in)
-      const int dz = int(__fdiv_rn(__fmul_rn(fh, de), P.max_depth));
-      const int py = P.H - dz;  // :114
-      int action = cls;
-      if (action > 1) action -= 1;  // :108-111
-      if (action == 0) kind = kKindTerrain;
-      else if (action == 2) kind = kKindBall;
-      else kind = kKindRobot;
-      if (kind == kKindBall) {
-        if (id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums
-          unsigned long long* b = ball_sums + (size_t(f) * kMaxBalls + id) * 3;
-          atomicAdd(b + 0, (unsigned long long)(long long)x);
-          atomicAdd(b + 1, (unsigned long long)(long long)py);
-          atomicAdd(b + 2, 1ull);
-        }
-      } else {
-        const int s = kind == kKindTerrain ? P.s_t : P.s_b;
-        // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
-        if (py + s - 1 < 1 || py - s > P.H - 2) kind = kKindNone;
-      }
-      enc = max(0, min(py + P.py_bias, 0x3FFF));
-      land[fbase + size_t(y) * P.W + x] = uint16_t((kind << 14) | enc);
+    const bool live = valid && y < P.H;   // y < P.H is warp-uniform; no early exit: the loop body is straight-line code
+    const int cls = tv[r] & 0xFF, id = tv[r] >> 8;  // R8G8 little-endian upload (scene.rs:198)
+    // :93-95, evaluated left to right; the two cos(atan(tan)) factors come from the host tables
+    const float de = __fmul_rn(__fmul_rn(float(dv[r]), cy_tab[min(y, P.H - 1)]), cxv);
+    // :98  int(float(height) * depth / max_depth_in)
+    const int dz = int(__fdiv_rn(__fmul_rn(fh, de), P.max_depth));
+    const int py = P.H - dz;  // :114
+    const int action = cls > 1 ? cls - 1 : cls;  // :108-111
+    int kind = action == 0 ? kKindTerrain : (action == 2 ? kKindBall : kKindRobot);
+    const int s = kind == kKindTerrain ? P.s_t : P.s_b;
+    // rows touched: [py - s, py + s - 1]; only rows 1..H-2 are ever stored (pt_cloud.comp:67)
+    if (kind != kKindBall && (py + s - 1 < 1 || py - s > P.H - 2)) kind = kKindNone;
+    if (!live) kind = kKindNone;
+    if (live && kind == kKindBall && id < kMaxBalls) {  // SURVEY §9.3 deterministic store_ball: integer sums (rare)
+      unsigned long long* b = ball_sums + (size_t(f) * kMaxBalls + id) * 3;
+      atomicAdd(b + 0, (unsigned long long)(long long)x);
+      atomicAdd(b + 1, (unsigned long long)(long long)py);
+      atomicAdd(b + 2, 1ull);
     }
+    const int enc = max(0, min(py + P.py_bias, 0x3FFF));
+    if (live) lrow[size_t(r) * P.W] = uint16_t((kind << 14) | enc);
     const unsigned t_lo = __reduce_min_sync(full, kind == kKindTerrain ? unsigned(enc) : 0xFFFFu);
     const unsigned t_hi = __reduce_max_sync(full, kind == kKindTerrain ? unsigned(enc) : 0u);
-    const unsigned b_any = __ballot_sync(full, kind == kKindRobot);
-    unsigned b_lo = 0xFFFFu, b_hi = 0u;
-    if (b_any) {  // robot pixels are rare
-      b_lo = __reduce_min_sync(full, kind == kKindRobot ? unsigned(enc) : 0xFFFFu);
-      b_hi = __reduce_max_sync(full, kind == kKindRobot ? unsigned(enc) : 0u);
-    }
-    if (lane == 0) {
-      const size_t ri = (size_t(f) * gridDim.x + blockIdx.x) * P.H + y;
-      rowinfo_t[ri] = t_lo | (t_hi << 16);
-      rowinfo_b[ri] = b_lo | (b_hi << 16);
-      if (b_any) atomicOr(row_robot + size_t(f) * P.H + y, 1u);
+    const unsigned b_lo = __reduce_min_sync(full, kind == kKindRobot ? unsigned(enc) : 0xFFFFu);
+    const unsigned b_hi = __reduce_max_sync(full, kind == kKindRobot ? unsigned(enc) : 0u);
+    if (lane == 0 && y < P.H) {
+      rowinfo_t[ri0 + y] = t_lo | (t_hi << 16);
+      rowinfo_b[ri0 + y] = b_lo | (b_hi << 16);
+      if (b_lo <= b_hi) atomicOr(row_robot + size_t(f) * P.H + y, 1u);
     }
   }
 }
