@@ -58,6 +58,33 @@ int main() {
     const int32_t qq = rng() % 64 == 0 ? int32_t(rng() % (1u << 30)) : int32_t((1u << 30) + rng() % (1u << 30));
     check_tab(x, qq, 1 + int(rng() % 22), int(rng() % 257) - 128);
   }
+  // the ReLU form: equal to the literal result after the clamp whenever the activation floor is at or above the zero point
+  auto check_relu = [&](int32_t x, int32_t qq, int rs, int zp, int lo, int hi, int32_t bias) {
+    auto clamp = [&](int64_t v) { return int32_t(v < lo ? lo : (v > hi ? hi : v)); };
+    const int32_t want = clamp(int64_t(oracle::MBQM(x + bias, qq, -rs)) + zp);
+    const int32_t got = clamp(tod::requant_relu(x, qq, rs - 1, tod::relu_addend(qq, rs, zp, bias)));
+    ++n;
+    if (want != got) { if (bad < 5) std::printf("relu mismatch x=%d b=%d q=%d rs=%d zp=%d [%d,%d]: %d vs %d\n", x, bias, qq, rs, zp, lo, hi, want, got); ++bad; }
+  };
+  for (int32_t x : xe)
+    for (int32_t qq : qe)
+      for (int rs = 1; rs <= 22; ++rs)
+        for (int zp : {-128, -100, -3, 0, 5}) {
+          check_relu(x, qq, rs, zp, zp, 127, 0);                       // ReLU
+          check_relu(x, qq, rs, zp, zp, zp + 100 > 127 ? 127 : zp + 100, 0);   // ReLU6-style ceiling
+          check_relu(x, qq, rs, zp, zp + 3 > 127 ? 127 : zp + 3, 127, 17);     // floor above the zero point, with a bias
+        }
+  for (int rs = 1; rs <= 14; ++rs)  // exact .5 ties, both signs, around zero
+    for (int k = -5000; k <= 5000; ++k)
+      check_relu(k, 1 << 30, rs, -128, -128, 127, 0), check_relu(2 * k + 1, 1 << 30, rs, -7, -7, 127, -3), check_relu(k, (1 << 30) + (1 << 29), rs, 0, 0, 127, 1);
+  for (long long i = 0; i < 10000000; ++i) {
+    const int32_t x = int32_t(rng() % (1u << 29)) - (1 << 28);
+    const int32_t b = int32_t(rng() % (1u << 24)) - (1 << 23);
+    const int32_t qq = rng() % 64 == 0 ? int32_t(rng() % (1u << 30)) : int32_t((1u << 30) + rng() % (1u << 30));
+    const int zp = int(rng() % 200) - 128;
+    const int lo = zp + int(rng() % 3 == 0 ? rng() % 20 : 0);
+    check_relu(x, qq, 1 + int(rng() % 22), zp, lo > 127 ? 127 : lo, 127, b);
+  }
   int32_t q; int sh, q2, sh2;
   for (int i = 0; i < 200000; ++i) {
     const double m = std::ldexp(0.5 + (rng() % 1000000) / 2000000.0, -int(rng() % 40) + 3);

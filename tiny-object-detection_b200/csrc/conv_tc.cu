@@ -72,6 +72,7 @@ struct TcParams {
   // ---- fast epilogue (conv_tc_fast_kernel)
   const int4* qtab;            // [OCp] {Q31 multiplier, right shift, 2^31, rounding term with the output zero point folded in}
   const int32_t* b2tab;        // [ncls][OCp] 2 * (bias - zp * sum of in-image tap sums), compact border classes
+  const long long* a64tab;     // kEpiRelu: [ncls][OCp] bias_eff * q + 2^30 + halfp * 2^31 (qtab then holds {q, rs - 1, -, -})
   int ncls, ncls_x;            // compact border classes: cls = ymap[ymask] * ncls_x + xmap[xmask]
   uint8_t ymap[8], xmap[8];
   int wo;                      // TMA-store staging row bytes (16 / 32 / 64 / 128), 0 = manual stores
@@ -459,7 +460,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   * a full-range clamp is the saturation of cvt.pack.sat.s8.s32;
 //   * requantised bytes go to a swizzled staging tile and leave with ONE TMA store per 128-column pass (the TMA unit
 //     clips rows / columns outside the tensor), double-buffered so a pass needs a single CTA-wide barrier.
-enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4, kEpiAdd = 8 };
+// kEpiRelu: the layer's activation floor is at (or above) the output zero point (ReLU / ReLU6: act_min == quantised 0.0).
+// Every negative pre-activation then clamps to act_min whatever its rounding, so the sign correction of the rounding
+// right shift can go, and with it the doubling: with Y = acc*q + (bias*q + 2^30 + halfp*2^31) (one 64-bit
+// multiply-add against a per-(border class, channel) addend), floor(Y / 2^(31+rs)) == hi32(Y) >> (rs - 1) is the exact
+// result for acc + bias >= 0 and is <= zp (so clamps to act_min like the exact one) below: 2 ALU instructions per output
+// instead of 5.  tests/cpp/fixedpoint_check.cpp checks the identity against the literal gemmlowp form.
+enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4, kEpiAdd = 8, kEpiRelu = 16 };
 
 struct WorkItem { int n_tile, tx, ty, g; };
 __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles_x, int tiles_y) {
@@ -490,9 +497,66 @@ __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles
   return w;
 }
 
+// One 16-column chunk of one accumulator row: requantise (+ fused ADD / byte map / clamp) and pack to 16 output bytes.
+// kq / bq / aq point at this chunk's per-channel constants in shared memory (every load is base + immediate).
+template <uint32_t MODE>
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const int4* kq, const int4* bq, const longlong2* aq, const uint4& rres,
+                                            const SmemCtl* ctl, const TcParams& p, uint32_t (&packed)[4]) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    int o[4];
+    if (MODE & kEpiRelu) {
+      // kq is a table of int2 {q, rs - 1} here (two channels per 16-byte load): the shared-memory pipe, not the ALU, is the
+      // busiest unit of the epilogue (ncu: 61 % of its wavefront rate on the 112x112 expand layer)
+      const longlong2 a01 = aq[2 * q4], a23 = aq[2 * q4 + 1];
+      const int4 k01 = reinterpret_cast<const int4*>(kq)[2 * q4], k23 = reinterpret_cast<const int4*>(kq)[2 * q4 + 1];
+      o[0] = int((static_cast<long long>(int(v[4 * q4 + 0])) * k01.x + a01.x) >> 32) >> k01.y;
+      o[1] = int((static_cast<long long>(int(v[4 * q4 + 1])) * k01.z + a01.y) >> 32) >> k01.w;
+      o[2] = int((static_cast<long long>(int(v[4 * q4 + 2])) * k23.x + a23.x) >> 32) >> k23.y;
+      o[3] = int((static_cast<long long>(int(v[4 * q4 + 3])) * k23.z + a23.y) >> 32) >> k23.w;
+    } else {
+      const int4 b4 = bq[q4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int4 k = kq[4 * q4 + j];  // {q, rs, 2^31, half + (zp << rs)}: z:w is the 64-bit addend, in place
+        const int bj = j == 0 ? b4.x : (j == 1 ? b4.y : (j == 2 ? b4.z : b4.w));
+        int x2;  // 2 * acc + 2 * bias on the FMA pipe (IMAD): the ALU pipe is the epilogue's bottleneck
+        asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(x2) : "r"(int(v[4 * q4 + j])), "r"(bj));
+        const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
+        const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
+        o[j] = (t + (x2 >> 31)) >> k.y;  // sign(x2) == sign(v) wherever the rounding term can matter
+      }
+    }
+    if (MODE & kEpiAdd) {
+      const uint32_t rw = q4 == 0 ? rres.x : (q4 == 1 ? rres.y : (q4 == 2 ? rres.z : rres.w));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!(MODE & kEpiSat)) o[j] = max(p.act_min, min(p.act_max, o[j]));
+        else o[j] = max(-128, min(127, o[j]));
+        const int sum = ctl->add_tab[o[j] & 0xFF] + ctl->add_tab[256 + ((rw >> (8 * j)) & 0xFFu)];
+        o[j] = max(p.add_min, min(p.add_max, mul_by_quant_mult_fast(sum, p.add_mult, p.add_shift) + p.add_zp));
+      }
+      packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+    } else if ((MODE & kEpiSat) && !(MODE & kEpiLut)) {
+      packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = max(p.act_min, min(p.act_max, o[j]));
+        if (MODE & kEpiLut) o[j] = ctl->lut[o[j] & 0xFF];
+      }
+      packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+    }
+  }
+}
+
 // DIAG = true compiles in the clock64 stamps (TOD_TC_TRACE) and the timing-experiment switches (TOD_TC_DBG); the production
 // instantiations carry neither (predicated-off stamps inside the chunk loop alone were measurable).
-template <uint32_t MODE, bool DIAG = false>
+// FL = true: the flat-linear specialisation (p.flat && p.lin: a 1x1 layer seen as one [pixels][OC] matrix, one N tile,
+// linear staging, one 1-D bulk store per tile).  ncu on the 112x112 32 -> 96 layer showed the epilogue warps spending as
+// many stall samples in the ~200 instructions of per-tile bookkeeping of the general path (work decode, border class,
+// patch coordinates, run set-up, pass loop) as in the six 16-column chunks themselves; here a tile costs a handful.
+template <uint32_t MODE, bool DIAG = false, bool FL = false>
 __global__ void __launch_bounds__(kFastThreads, 1)
 conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
@@ -505,7 +569,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   int* s_runlen = reinterpret_cast<int*>(s_rowoff + 4 * kBM);   // [4 groups][128 runs]
   int4* s_qtab = reinterpret_cast<int4*>(s_runlen + 4 * kBM);
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
+  const long long* s_a64 = reinterpret_cast<const long long*>(s_b2);   // kEpiRelu: the same region holds 64-bit addends
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp * ((MODE & kEpiRelu) ? 2 : 1));
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -528,7 +593,10 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.OCp; i += kFastThreads) s_qtab[i] = p.qtab[i];
-  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kFastThreads) s_b2[i] = p.b2tab[i];
+  if (MODE & kEpiRelu)
+    for (int i = threadIdx.x; i < 2 * p.ncls * p.OCp; i += kFastThreads) s_b2[i] = reinterpret_cast<const int32_t*>(p.a64tab)[i];
+  else
+    for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kFastThreads) s_b2[i] = p.b2tab[i];
   if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
   if (MODE & kEpiAdd)
     for (int i = threadIdx.x; i < 512; i += kFastThreads) ctl->add_tab[i] = p.add_tab[i];
@@ -662,6 +730,54 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
     }
+  } else if (FL && warp >= 4) {
+    // ===================== epilogue, flat-linear layers =====================
+    // group g owns accumulator stage g and takes this CTA's tiles g, g + 2, ...; tile = rows [128 work, 128 work + 128)
+    constexpr int wpg = kEpiWarps / kAccStages;
+    constexpr int gthreads = 32 * wpg;
+    const int ew = warp & 3, grp = (warp - 4) / wpg;
+    const int r = ew * 32 + lane;
+    const int eg = threadIdx.x - 128 - grp * gthreads;
+    const uint32_t oc = uint32_t(p.OC);
+    const uint32_t buf_bytes = uint32_t(kBM) * oc;
+    uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes / uint32_t(kAccStages));
+    const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(grp) * uint32_t(kTmemCols / kAccStages);
+    const int4* bq0 = reinterpret_cast<const int4*>(s_b2);
+    const longlong2* aq0 = reinterpret_cast<const longlong2*>(s_a64);
+    const int bar_id = 1 + grp;
+    uint32_t use = 0;
+    for (int work = blockIdx.x + grp * int(gridDim.x); work < total_work; work += kAccStages * int(gridDim.x), ++use) {
+      const long long row0 = (long long)work * kBM;
+      const int rows_ok = int(min((long long)kBM, (long long)Wd - row0));
+      const int8_t* rrow = nullptr;
+      if ((MODE & kEpiAdd) && r < rows_ok) rrow = p.resid + (row0 + r) * (long long)oc;
+      uint8_t* sbuf = grp_buf + (use & 1u) * buf_bytes;
+      uint8_t* srow = sbuf + uint32_t(r) * oc;
+      mbar_wait(&ctl->acc_full[grp], use & 1);
+      tc_fence_after();
+      for (uint32_t c0 = 0; c0 < oc; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        uint4 rres = make_uint4(0u, 0u, 0u, 0u);
+        if ((MODE & kEpiAdd) && rrow) rres = *reinterpret_cast<const uint4*>(rrow + c0);
+        tmem_wait_ld();
+        uint32_t packed[4];
+        const int4* kq = (MODE & kEpiRelu) ? reinterpret_cast<const int4*>(reinterpret_cast<const int2*>(s_qtab) + c0) : s_qtab + c0;
+        epi_chunk16<MODE>(v, kq, bq0 + (c0 >> 2), aq0 + (c0 >> 1), rres, ctl, p, packed);
+        *reinterpret_cast<uint4*>(srow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      tc_fence_before();   // accumulator fully read: hand the TMEM stage back before the store
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[grp]);
+      if (eg == 0) tma_store_wait_read();   // this group's previous store has drained the other buffer
+      fence_async_smem();
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
+      if (eg == 0) {
+        bulk_store_1d(p.out + row0 * (long long)oc, sbuf, uint32_t(rows_ok) * oc);
+        tma_store_commit();
+      }
+    }
+    if (eg == 0) tma_store_wait_read();  // staging must outlive the last store's reads
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // kEpiWarps warps in acc_stages groups take tiles round-robin: group g owns accumulator stage g, its own staging
@@ -724,6 +840,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       const int ocb = w.n_tile * p.BN;
       const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
+      const longlong2* a2row = reinterpret_cast<const longlong2*>(s_a64 + size_t(cls) * p.OCp + ocb);
       const int4* qrow = s_qtab + ocb;
       const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
       uint32_t soff = 0;  // manual mode: this row's byte offset inside the group's staging buffer
@@ -773,42 +890,9 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           TOD_TR(3);
           uint32_t packed[4];
           const int4* bq = b2row + ((pass0 + c0) >> 2);  // chunk bases: every table load below is base + immediate
-          const int4* kq = qrow + (pass0 + c0);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int4 b4 = bq[q4];
-            int o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int4 k = kq[4 * q4 + j];  // {q, rs, 2^31, half + (zp << rs)}: z:w is the 64-bit addend, in place
-              const int bj = j == 0 ? b4.x : (j == 1 ? b4.y : (j == 2 ? b4.z : b4.w));
-              int x2;  // 2 * acc + 2 * bias on the FMA pipe (IMAD): the ALU pipe is the epilogue's bottleneck
-              asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(x2) : "r"(int(v[4 * q4 + j])), "r"(bj));
-              const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
-              const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
-              o[j] = (t + (x2 >> 31)) >> k.y;  // sign(x2) == sign(v) wherever the rounding term can matter
-            }
-            if (MODE & kEpiAdd) {
-              const uint32_t rw = q4 == 0 ? rres.x : (q4 == 1 ? rres.y : (q4 == 2 ? rres.z : rres.w));
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (!(MODE & kEpiSat)) o[j] = max(p.act_min, min(p.act_max, o[j]));
-                else o[j] = max(-128, min(127, o[j]));
-                const int sum = ctl->add_tab[o[j] & 0xFF] + ctl->add_tab[256 + ((rw >> (8 * j)) & 0xFFu)];
-                o[j] = max(p.add_min, min(p.add_max, mul_by_quant_mult_fast(sum, p.add_mult, p.add_shift) + p.add_zp));
-              }
-              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
-            } else if ((MODE & kEpiSat) && !(MODE & kEpiLut)) {
-              packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                o[j] = max(p.act_min, min(p.act_max, o[j]));
-                if (MODE & kEpiLut) o[j] = ctl->lut[o[j] & 0xFF];
-              }
-              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
-            }
-          }
+          const int4* kq = (MODE & kEpiRelu) ? reinterpret_cast<const int4*>(reinterpret_cast<const int2*>(s_qtab) + ocb + pass0 + c0) : qrow + (pass0 + c0);
+          const longlong2* aq = a2row + ((pass0 + c0) >> 1);
+          epi_chunk16<MODE>(v, kq, bq, aq, rres, ctl, p, packed);
           if (MODE & kEpiTma) {
             uint32_t off = row_base + uint32_t(c0);
             off ^= ((off >> 7) & swz_mask) << 4;
@@ -938,7 +1022,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* stage_buf = smem_b + size_t(p.stages) * p.b_stage;
   int4* s_qtab = reinterpret_cast<int4*>(stage_buf + p.stage_bytes);
   int32_t* s_b2 = reinterpret_cast<int32_t*>(s_qtab + p.OCp);
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp);
+  const long long* s_a64 = reinterpret_cast<const long long*>(s_b2);   // kEpiRelu: 64-bit addends
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp * ((MODE & kEpiRelu) ? 2 : 1));
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -964,7 +1049,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
-  for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
+  if (MODE & kEpiRelu)
+    for (int i = threadIdx.x; i < 2 * p.ncls * p.OCp; i += kTcThreads) s_b2[i] = reinterpret_cast<const int32_t*>(p.a64tab)[i];
+  else
+    for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -1089,6 +1177,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       const int ocb = n_tile * p.BN;
       const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
+      const longlong2* a2row = reinterpret_cast<const longlong2*>(s_a64 + size_t(cls) * p.OCp + ocb);
       const int4* qrow = s_qtab + ocb;
       const int ncols_tile = min(p.BN, p.OC - ocb);
       mbar_wait(&ctl->acc_full[as], use & 1);
@@ -1105,10 +1194,20 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint32_t packed[4];
           const int4* bq = b2row + ((pass0 + c0) >> 2);  // chunk bases: every table load below is base + immediate
           const int4* kq = qrow + (pass0 + c0);
+          const longlong2* aq = a2row + ((pass0 + c0) >> 1);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const int4 b4 = bq[q4];
             int o[4];
+            if (MODE & kEpiRelu) {
+              const longlong2 a01 = aq[2 * q4], a23 = aq[2 * q4 + 1];
+              const int4* k2 = reinterpret_cast<const int4*>(reinterpret_cast<const int2*>(s_qtab) + ocb + pass0 + c0);   // int2 {q, rs - 1} per channel
+              const int4 k01 = k2[2 * q4], k23 = k2[2 * q4 + 1];
+              o[0] = int((static_cast<long long>(int(v[4 * q4 + 0])) * k01.x + a01.x) >> 32) >> k01.y;
+              o[1] = int((static_cast<long long>(int(v[4 * q4 + 1])) * k01.z + a01.y) >> 32) >> k01.w;
+              o[2] = int((static_cast<long long>(int(v[4 * q4 + 2])) * k23.x + a23.x) >> 32) >> k23.y;
+              o[3] = int((static_cast<long long>(int(v[4 * q4 + 3])) * k23.z + a23.y) >> 32) >> k23.w;
+            } else {
+            const int4 b4 = bq[q4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int4 k = kq[4 * q4 + j];
@@ -1118,6 +1217,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const long long addend = static_cast<long long>((static_cast<unsigned long long>(uint32_t(k.w)) << 32) | uint32_t(k.z));
               const int t = int((static_cast<long long>(x2) * k.x + addend) >> 32);
               o[j] = (t + (x2 >> 31)) >> k.y;
+            }
             }
             if (MODE & kEpiSat) {
               packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
@@ -1217,6 +1317,7 @@ struct ConvTc {
   int pair = 0;        // conv_tc_pair_kernel (cta_group::2): map_bh loads half of the weight rows per CTA
   TcParams p{};
   int32_t *d_bias_eff = nullptr, *d_mult = nullptr, *d_shift = nullptr, *d_b2 = nullptr;
+  long long* d_a64 = nullptr;
   int4* d_qtab = nullptr;
   int32_t* d_add_tab = nullptr;
   size_t smem_bytes = 0;
@@ -1242,6 +1343,7 @@ void conv_tc_destroy(ConvTc* c) {
   cudaFree(c->d_mult);
   cudaFree(c->d_shift);
   cudaFree(c->d_b2);
+  cudaFree(c->d_a64);
   cudaFree(c->d_qtab);
   cudaFree(c->d_add_tab);
   delete c;
@@ -1384,7 +1486,10 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     for (size_t i = 0; i < ymasks.size(); ++i) p.ymap[ymasks[i] & 7] = uint8_t(i);
   if (c->fast)
     for (size_t i = 0; i < xmasks.size(); ++i) p.xmap[xmasks[i] & 7] = uint8_t(i);
-  const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * 4 : 0;
+  // ReLU-type activation (floor at or above the output zero point): the two-instruction requantisation (kEpiRelu)
+  static const int relu_env = std::getenv("TOD_TC_RELU") ? std::atoi(std::getenv("TOD_TC_RELU")) : -1;
+  const bool relu = c->fast && !a.add && !a.rq.post_lut && a.rq.act_min >= a.rq.out_zp && p.vec_store && relu_env != 0;
+  const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * (relu ? 8 : 4) : 0;
   if (table_bytes > 40 * 1024) c->fast = 0;
   if (!p.vec_store && p.n_tiles > 1) c->fast = 0;  // run staging needs whole rows (every output channel) in one tile
   if (p.a_cp && !c->fast) {  // the general-epilogue kernel only has the TMA producer: back to a K chunk that TMA can serve
@@ -1403,6 +1508,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     if (a.rq.post_lut) c->mode |= kEpiLut;
     if (p.vec_store) c->mode |= kEpiTma;
     if (a.add) c->mode |= kEpiAdd;
+    if (relu) c->mode |= kEpiRelu;
   }
   if (a.add && (!c->fast || (c->mode & kEpiLut) || !p.vec_store))
     return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: a fused residual ADD needs the fast epilogue, 16-byte rows and no byte map"));
@@ -1486,20 +1592,38 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   cudaError_t ce;
   if (c->fast) {
     std::vector<int32_t> qt(size_t(p.OCp) * 4, 0), b2(size_t(p.ncls) * p.OCp, 0);
+    const bool relu_mode = (c->mode & kEpiRelu) != 0;
     for (int oc = 0; oc < g.OC; ++oc) {
       const int rs = -a.h_shift[oc];
+      if (relu_mode) {   // int2 {q, rs - 1} per channel, packed (the kernel still copies OCp int4 entries: the tail is padding)
+        qt[size_t(oc) * 2 + 0] = a.h_mult[oc];
+        qt[size_t(oc) * 2 + 1] = rs - 1;
+        continue;
+      }
       qt[size_t(oc) * 4 + 0] = a.h_mult[oc];
       qt[size_t(oc) * 4 + 1] = rs;
       qt[size_t(oc) * 4 + 2] = int32_t(0x80000000u);
       qt[size_t(oc) * 4 + 3] = (1 << (rs - 1)) + a.rq.out_zp * (1 << rs);
     }
+    std::vector<long long> a64(relu_mode ? size_t(p.ncls) * p.OCp : 0, 0);
     for (size_t yi = 0; yi < ymasks.size(); ++yi)
       for (size_t xi = 0; xi < xmasks.size(); ++xi) {
         const int code = p.taps == 1 ? ((1 << g.KW) + 1) : (ymasks[yi] * (1 << g.KW) + xmasks[xi]);
         const int32_t* src = &be[size_t(code) * p.OCp];
         int32_t* dst = &b2[(yi * xmasks.size() + xi) * p.OCp];
         for (int oc = 0; oc < g.OC; ++oc) dst[oc] = 2 * src[oc];
+        if (relu_mode)
+          for (int oc = 0; oc < g.OC; ++oc) {
+            const int rs = -a.h_shift[oc];
+            const long long halfp = (1ll << (rs - 1)) + (long long)a.rq.out_zp * (1ll << rs);
+            a64[(yi * xmasks.size() + xi) * p.OCp + oc] = (long long)src[oc] * a.h_mult[oc] + (1ll << 30) + halfp * (1ll << 31);
+          }
       }
+    if (relu_mode) {
+      if ((ce = cudaMalloc(&c->d_a64, a64.size() * 8)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
+      cudaMemcpy(c->d_a64, a64.data(), a64.size() * 8, cudaMemcpyHostToDevice);
+      p.a64tab = c->d_a64;
+    }
     if ((ce = cudaMalloc(&c->d_qtab, qt.size() * 4)) != cudaSuccess || (ce = cudaMalloc(&c->d_b2, b2.size() * 4)) != cudaSuccess)
       return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
     cudaMemcpy(c->d_qtab, qt.data(), qt.size() * 4, cudaMemcpyHostToDevice);
@@ -1596,6 +1720,11 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
                              (const void*)conv_tc_fast_kernel<3>, (const void*)conv_tc_fast_kernel<4>, (const void*)conv_tc_fast_kernel<5>,
                              (const void*)conv_tc_fast_kernel<6>, (const void*)conv_tc_fast_kernel<7>,
                              (const void*)conv_tc_fast_kernel<12>, (const void*)conv_tc_fast_kernel<13>,
+                             (const void*)conv_tc_fast_kernel<20>, (const void*)conv_tc_fast_kernel<21>,
+                             (const void*)conv_tc_fast_kernel<4, false, true>, (const void*)conv_tc_fast_kernel<5, false, true>,
+                             (const void*)conv_tc_fast_kernel<12, false, true>, (const void*)conv_tc_fast_kernel<13, false, true>,
+                             (const void*)conv_tc_fast_kernel<20, false, true>, (const void*)conv_tc_fast_kernel<21, false, true>,
+                             (const void*)conv_tc_pair_kernel<20>, (const void*)conv_tc_pair_kernel<21>,
                              (const void*)conv_tc_fast_kernel<3, true>, (const void*)conv_tc_fast_kernel<5, true>,
                              (const void*)conv_tc_pair_kernel<4>, (const void*)conv_tc_pair_kernel<5>};
     for (const void* k : kernels) {
@@ -1626,7 +1755,11 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
     const long long m_tiles = (long long)groups * p.tiles_y * tiles_x;
     const long long pair_items = ((m_tiles + 1) / 2) * p.n_tiles;
     const int pairs = int(std::min<long long>(pair_items, sm_count() / 2));
-    if (c->mode & kEpiSat)
+    if (c->mode == 21)
+      TOD_CUDA(launch_k(conv_tc_pair_kernel<21>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
+    else if (c->mode == 20)
+      TOD_CUDA(launch_k(conv_tc_pair_kernel<20>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
+    else if (c->mode & kEpiSat)
       TOD_CUDA(launch_k(conv_tc_pair_kernel<5>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
     else
       TOD_CUDA(launch_k(conv_tc_pair_kernel<4>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
@@ -1641,10 +1774,19 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
       TOD_CUDA(cudaGetLastError());
       return TOD_OK;
     }
+    static const int fl_env = std::getenv("TOD_TC_FL") ? std::atoi(std::getenv("TOD_TC_FL")) : -1;
+    if (p.flat && p.lin && p.n_tiles == 1 && fl_env != 0) {
+      switch (c->mode) {
+#define TOD_TC_FL(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M, false, true>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); TOD_CUDA(cudaGetLastError()); return TOD_OK;
+        TOD_TC_FL(4) TOD_TC_FL(5) TOD_TC_FL(12) TOD_TC_FL(13) TOD_TC_FL(20) TOD_TC_FL(21)
+#undef TOD_TC_FL
+        default: break;
+      }
+    }
     switch (c->mode) {
 #define TOD_TC_CASE(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); break;
       TOD_TC_CASE(0) TOD_TC_CASE(1) TOD_TC_CASE(2) TOD_TC_CASE(3) TOD_TC_CASE(4) TOD_TC_CASE(5) TOD_TC_CASE(6) TOD_TC_CASE(7)
-      TOD_TC_CASE(12) TOD_TC_CASE(13)
+      TOD_TC_CASE(12) TOD_TC_CASE(13) TOD_TC_CASE(20) TOD_TC_CASE(21)
       default: return fail(TOD_ERR_UNSUPPORTED, "conv_tc: no kernel for epilogue mode %u", c->mode);
 #undef TOD_TC_CASE
     }

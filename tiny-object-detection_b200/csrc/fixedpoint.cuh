@@ -72,6 +72,22 @@ TOD_HD int32_t requant_tab(int32_t x, int32_t q, int rs, int32_t halfp) {
   return (t + (x2 >> 31)) >> rs;
 }
 
+// The form for layers whose activation floor sits at or above the output zero point (ReLU / ReLU6: act_min is the
+// quantised 0.0), after the clamp:
+//   clamp(requant_relu(x, q, rs - 1, relu_addend(q, rs, zp)), act_min, act_max) == clamp(mul_by_quant_mult(x, q, -rs) + zp, ...)
+// for q >= 0, 1 <= rs <= 22, |x| < 2^29, act_min >= zp.  With Y = x*q + 2^30 + halfp*2^31 (halfp as in requant_tab),
+// requant_tab's value for x >= 0 is floor(2Y / 2^(32+rs)) = floor(Y / 2^(31+rs)) = hi32(Y) >> (rs - 1): exact.  For x < 0
+// the exact result is <= zp (a negative value never rounds above zero) and so is this one (SRDHM's v <= 0 gives
+// hi32-term <= half, and half >> rs == 0): both clamp to act_min.  One 64-bit multiply-add and one shift instead of five
+// instructions; a per-channel bias folds into the addend as + bias * q.  tests/cpp/fixedpoint_check.cpp checks it.
+TOD_HD int64_t relu_addend(int32_t q, int rs, int32_t zp, int64_t bias = 0) {
+  const int64_t halfp = (int64_t(1) << (rs - 1)) + int64_t(zp) * (int64_t(1) << rs);
+  return bias * int64_t(q) + (int64_t(1) << 30) + halfp * (int64_t(1) << 31);
+}
+TOD_HD int32_t requant_relu(int32_t x, int32_t q, int rs_minus_1, int64_t addend) {
+  return int32_t((int64_t(x) * int64_t(q) + addend) >> 32) >> rs_minus_1;
+}
+
 // host only: real multiplier -> (Q31 mantissa, exponent)
 inline void quantize_multiplier(double m, int32_t* q, int* shift) {
   if (m == 0.0) {

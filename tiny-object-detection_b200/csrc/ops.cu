@@ -280,7 +280,7 @@ constexpr int kStemThreads = 128;
 constexpr int kStemOct = 16;
 constexpr int kStemIters = 8;
 
-template <bool SAT>
+template <bool SAT, bool RELU>
 __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* __restrict__ in, int64_t in_ts,
                                                                 const int8_t* __restrict__ w, const int32_t* __restrict__ bias,
                                                                 int32_t in_zp, ConvGeom g, Requant rq, int8_t* __restrict__ out,
@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int4 k = s_k[oc0 + 4 * q + j];
-      o[j] = requant_tab(acc[4 * q + j], k.x, k.y, k.w);
+      if (RELU) o[j] = requant_relu(acc[4 * q + j], k.x, k.y, (int64_t(k.w) << 32) | int64_t(uint32_t(k.z)));
+      else o[j] = requant_tab(acc[4 * q + j], k.x, k.y, k.w);
     }
     if (SAT) {
       unsigned hi;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(256, 2) depthwise_reg_kernel(const int8_t* __r
 // with the bias pre-folded as bias - zp * sum(w): no branches in the arithmetic.  Requantisation: Requant::fast_tab.
 constexpr int kDwThreads = 128;
 
-template <int STRIDE, bool SAT>
+template <int STRIDE, bool SAT, bool RELU>
 __global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const int8_t* __restrict__ in, int64_t in_ts,
                                                                        const int8_t* __restrict__ w,
                                                                        const int32_t* __restrict__ bias, int32_t in_zp,
@@ -573,7 +574,8 @@ __global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const
       int a = __dp4a(int(ra[q]), int(wt[0][q]), bs[q]);
       a = __dp4a(int(rb[q]), int(wt[1][q]), a);
       a = __dp4a(int(rc[q]), int(wt[2][q]), a);
-      o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
+      if (RELU) o[q] = requant_relu(a, k[q].x, k[q].y, (int64_t(k[q].w) << 32) | int64_t(uint32_t(k[q].z)));
+      else o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
     }
     unsigned packed;
     if (SAT) {
@@ -864,9 +866,11 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
     dim3 grid(unsigned((total + kStemThreads * kStemIters - 1) / (kStemThreads * kStemIters)));
     if (rq.act_min == -128 && rq.act_max == 127)
-      launch_k(stem3x3s2_kernel<true>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+      rq.relu_tab ? launch_k(stem3x3s2_kernel<true, true>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
+                  : launch_k(stem3x3s2_kernel<true, false>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
     else
-      launch_k(stem3x3s2_kernel<false>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+      rq.relu_tab ? launch_k(stem3x3s2_kernel<false, true>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
+                  : launch_k(stem3x3s2_kernel<false, false>, grid, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
     return;
   }
   // preferred CUDA-core path: shared-memory weight slab, one thread per pixel x 16 channels
@@ -908,13 +912,15 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
     rpb = std::min(rpb, 16);
     dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
     const bool sat = rq.act_min == -128 && rq.act_max == 127;
+#define TOD_DW(ST, SA, RE) launch_k(depthwise3x3_slide_kernel<ST, SA, RE>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb)
     if (g.stride_h == 1) {
-      if (sat) launch_k(depthwise3x3_slide_kernel<1, true>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
-      else launch_k(depthwise3x3_slide_kernel<1, false>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      if (rq.relu_tab) { if (sat) TOD_DW(1, true, true); else TOD_DW(1, false, true); }
+      else { if (sat) TOD_DW(1, true, false); else TOD_DW(1, false, false); }
     } else {
-      if (sat) launch_k(depthwise3x3_slide_kernel<2, true>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
-      else launch_k(depthwise3x3_slide_kernel<2, false>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb);
+      if (rq.relu_tab) { if (sat) TOD_DW(2, true, true); else TOD_DW(2, false, true); }
+      else { if (sat) TOD_DW(2, true, false); else TOD_DW(2, false, false); }
     }
+#undef TOD_DW
     return;
   }
   if (vec && g.KH == 3 && g.KW == 3 && g.dil_h == 1 && g.dil_w == 1 && int64_t(tiles) * g.OH * g.OW < (int64_t(1) << 31)) {

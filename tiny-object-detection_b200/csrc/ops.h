@@ -24,6 +24,9 @@ struct Requant {          // per-output-channel fixed point requantisation + act
   // optional [OC] {q, rs, 0x80000000, (1 << (rs-1)) + (out_zp << rs)}: present when every channel has shift in [-22,-1]
   // and q >= 0, so  out = (hi32(2*acc*q + 2^31 + (w << 32)) + (acc >> 31)) >> rs  equals the reference form
   const int4* fast_tab = nullptr;
+  // fast_tab holds the ReLU form instead: {q, rs - 1, lo32(A), hi32(A)} with A = relu_addend(q, rs, out_zp), for
+  // fixedpoint.cuh::requant_relu.  Only when act_min >= out_zp (every negative pre-activation clamps to act_min anyway).
+  bool relu_tab = false;
 };
 
 // CONV_2D, any geometry.  w: [OC][KH][KW][IC] int8.  bias: [OC] int32 (may be null).

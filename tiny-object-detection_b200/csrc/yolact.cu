@@ -62,6 +62,7 @@ struct Step {
   int64_t post_lut_off = -1;
   bool out_moved = false;  // the conv writes where a fused byte-map chain's last output (or a fused ADD's output) lives
   bool fused_add = false;  // `add` holds a residual ADD applied in this conv's epilogue; in1 = the ADD's other input
+  bool relu_tab = false;   // the table at fast_off holds the ReLU form (Requant::relu_tab)
   bool add_conv_is_a = true;
   Place out_place;
 };
@@ -773,6 +774,23 @@ int plan(tod_yolact* y, ConstArena* arena) {
   }
   for (Step& st : y->steps)
     if ((st.kind == kStepConvDirect || st.kind == kStepDepthwise) && !st.lut_host.empty()) st.post_lut_off = arena->add(st.lut_host.data(), 256);
+  // ---- ReLU-type layers (activation floor at or above the output zero point, no byte map / ADD behind them): the CUDA-core
+  // kernels that read Requant::fast_tab (depthwise, RGB stem) get the two-instruction form (fixedpoint.cuh::requant_relu)
+  if (y->opt.conv_impl != 2 && !(std::getenv("TOD_RELU_TAB") && std::atoi(std::getenv("TOD_RELU_TAB")) == 0))
+    for (Step& st : y->steps) {
+      if ((st.kind != kStepConvDirect && st.kind != kStepDepthwise) || st.fast_off < 0 || !st.lut_host.empty() || st.fused_add) continue;
+      if (st.act_min < st.out_zp) continue;
+      int32_t* ft = reinterpret_cast<int32_t*>(arena->host.data() + st.fast_off);
+      const int n = st.kind == kStepDepthwise ? st.g.OC : st.g.OC;
+      for (int c = 0; c < n; ++c) {
+        const int32_t q = ft[4 * c], rs = ft[4 * c + 1];
+        const int64_t A = relu_addend(q, rs, st.out_zp);
+        ft[4 * c + 1] = rs - 1;
+        ft[4 * c + 2] = int32_t(uint32_t(uint64_t(A) & 0xFFFFFFFFull));
+        ft[4 * c + 3] = int32_t(uint32_t(uint64_t(A) >> 32));
+      }
+      st.relu_tab = true;
+    }
   // ---- data dependencies between steps
   std::vector<std::vector<int>> op_steps(G.ops.size());  // steps generated for an op (its kernel, or a concat's copies)
   for (size_t i = 0; i < y->steps.size(); ++i) op_steps[y->steps[i].op].push_back(int(i));
@@ -892,7 +910,10 @@ int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
     case kStepDepthwise: {
       Requant rq{reinterpret_cast<const int32_t*>(y->d_const + st.mult_off), reinterpret_cast<const int32_t*>(y->d_const + st.shift_off),
                  st.out_zp, st.act_min, st.act_max, st.post_lut_off >= 0 ? y->d_const + st.post_lut_off : nullptr};
-      if (st.fast_off >= 0 && y->opt.conv_impl != 2) rq.fast_tab = reinterpret_cast<const int4*>(y->d_const + st.fast_off);
+      if (st.fast_off >= 0 && y->opt.conv_impl != 2) {
+        rq.fast_tab = reinterpret_cast<const int4*>(y->d_const + st.fast_off);
+        rq.relu_tab = st.relu_tab;
+      }
       const int8_t* w = reinterpret_cast<const int8_t*>(y->d_const + st.w_off);
       const int32_t* bias = st.bias_off >= 0 ? reinterpret_cast<const int32_t*>(y->d_const + st.bias_off) : nullptr;
       if (st.kind == kStepDepthwise)
