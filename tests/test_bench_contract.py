@@ -10,7 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _latest_line():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r1_v*.json")), key=lambda p: int("".join(c for c in os.path.basename(p).split("_v")[1].split(".")[0].split("_")[0] if c.isdigit())))
+    def key(p):
+        b = os.path.basename(p)
+        return (int(b.split("_r")[1].split("_")[0]), int("".join(c for c in b.split("_v")[1].split(".")[0].split("_")[0] if c.isdigit())))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r*_v*.json")), key=key)
     full = [f for f in files if "_n" not in os.path.basename(f) and "noscene" not in f]
     return json.load(open(full[-1]))
 
@@ -30,6 +33,8 @@ def test_committed_line_has_every_contract_key():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] in ("port", "reference")
     assert d["gpu_launches"] > 0 and d["steps"] >= 1 and d["warmup"] >= 3
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if "check" in d:   # round 2: the line carries the verdict of its own bytes against the oracle's committed CRCs
+        assert d["check"]["ok"] is True and d["check"]["timed_step_tiles_differing_from_oracle"] == 0 and d["check"]["timed_step_tiles_checked"] == 64
 
 
 def test_reference_arm_one_step():
