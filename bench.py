@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--no-scene", action="store_true", help="skip the point-cloud side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0)
-    ap.add_argument("--pipeline", type=int, default=3,
+    ap.add_argument("--pipeline", type=int, default=4,
                     help="batches in flight: handles that take alternate steps on their own streams (1 = one handle, steps back to back)")
     ap.add_argument("--fused", type=int, default=512, help="frames of the fused 320x240 RGB-D side measurement (0 = skip)")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained side figure (0 = skip)")

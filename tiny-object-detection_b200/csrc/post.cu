@@ -686,8 +686,10 @@ int detect_setup_kernels(const DetectCfg& c) {
   if (c.K != 32) return fail(TOD_ERR_UNSUPPORTED, "mask assembly is built for 32 coefficients, model has %d", c.K);
   if (detect_select_smem(c) > 200 * 1024 || nms_smem(c) > 200 * 1024)
     return fail(TOD_ERR_UNSUPPORTED, "detection head does not fit shared memory (P=%d, C=%d, top_k=%d)", c.P, c.C, c.top_k);
-  TOD_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(detect_select_smem(c))));
-  TOD_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(nms_smem(c))));
+  // the opt-in limit is per function and per device, not per handle: always the fixed ceiling the check above enforces, so a
+  // handle with a smaller head created later cannot lower it under an existing one
+  TOD_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TOD_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return TOD_OK;
 }
 
