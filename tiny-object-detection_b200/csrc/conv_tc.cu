@@ -81,6 +81,9 @@ struct TcParams {
   // whatever its length, so 32-byte pixels starve it; 96 threads issuing 16-byte cp.async do not care)
   int dbg;                     // TOD_TC_DBG timing experiments: 1 = skip the output store
   int b_res;                   // fast kernel: the weights of the (single) N tile stay resident in shared memory, stages hold A only
+  int wide;                    // epilogue: 1 = all eight warps convert every tile (two warps per TMEM lane quarter take alternate 16-column
+                               // chunks; tiles alternate accumulator stages), 0 = two groups of four warps take alternate tiles.  Chosen per
+                               // launch: with 1 - 3 tiles per CTA the last tile's epilogue is the CTA's tail, and eight warps halve it
   int lin;                     // fast kernel, TMA mode: tile rows are contiguous in global memory, staged linearly, one 1-D bulk store
   int run_w;                   // manual stores: pixels per staged run (pw, or pw * ph when the patch spans the image width)
   long long* trace;            // TOD_TC_TRACE: clock64 stamps of CTA 0 (epilogue warp 4 / MMA warp / producer), 16 per tile
@@ -587,7 +590,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], kEpiWarps / kAccStages);  // one epilogue group owns each accumulator stage
+      mbar_init(&ctl->acc_empty[s], p.wide ? kEpiWarps : kEpiWarps / kAccStages);  // the warps that read each accumulator stage
     }
     mbar_init(&ctl->b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -733,29 +736,35 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (FL && warp >= 4) {
     // ===================== epilogue, flat-linear layers =====================
     // group g owns accumulator stage g and takes this CTA's tiles g, g + 2, ...; tile = rows [128 work, 128 work + 128)
-    constexpr int wpg = kEpiWarps / kAccStages;
-    constexpr int gthreads = 32 * wpg;
+    // (p.wide: one group of eight warps takes every tile, the two warps of a lane quarter alternate 16-column chunks)
+    const int wpg = p.wide ? kEpiWarps : kEpiWarps / kAccStages;
+    const int gthreads = 32 * wpg;
     const int ew = warp & 3, grp = (warp - 4) / wpg;
+    const uint32_t chunk0 = uint32_t(((warp - 4) % wpg) >> 2) * 16u, cstep = uint32_t(4 * wpg);
     const int r = ew * 32 + lane;
     const int eg = threadIdx.x - 128 - grp * gthreads;
     const uint32_t oc = uint32_t(p.OC);
     const uint32_t buf_bytes = uint32_t(kBM) * oc;
     uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes / uint32_t(kAccStages));
-    const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(grp) * uint32_t(kTmemCols / kAccStages);
+    const uint32_t taddr0 = tmem_base + (uint32_t(ew * 32) << 16);
     const int4* bq0 = reinterpret_cast<const int4*>(s_b2);
     const longlong2* aq0 = reinterpret_cast<const longlong2*>(s_a64);
     const int bar_id = 1 + grp;
-    uint32_t use = 0;
-    for (int work = blockIdx.x + grp * int(gridDim.x); work < total_work; work += kAccStages * int(gridDim.x), ++use) {
+    const int it_step = p.wide ? 1 : kAccStages;
+    uint32_t use = 0;   // tiles this group has taken: staging buffer parity
+    for (int it = grp; blockIdx.x + (long long)it * gridDim.x < total_work; it += it_step, ++use) {
+      const int work = blockIdx.x + it * int(gridDim.x);
+      const int as = it & (kAccStages - 1);
+      const uint32_t taddr = taddr0 + uint32_t(as) * uint32_t(kTmemCols / kAccStages);
       const long long row0 = (long long)work * kBM;
       const int rows_ok = int(min((long long)kBM, (long long)Wd - row0));
       const int8_t* rrow = nullptr;
       if ((MODE & kEpiAdd) && r < rows_ok) rrow = p.resid + (row0 + r) * (long long)oc;
       uint8_t* sbuf = grp_buf + (use & 1u) * buf_bytes;
       uint8_t* srow = sbuf + uint32_t(r) * oc;
-      mbar_wait(&ctl->acc_full[grp], use & 1);
+      mbar_wait(&ctl->acc_full[as], (uint32_t(it) / uint32_t(kAccStages)) & 1u);
       tc_fence_after();
-      for (uint32_t c0 = 0; c0 < oc; c0 += 16) {
+      for (uint32_t c0 = chunk0; c0 < oc; c0 += cstep) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         uint4 rres = make_uint4(0u, 0u, 0u, 0u);
@@ -768,10 +777,10 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       tc_fence_before();   // accumulator fully read: hand the TMEM stage back before the store
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->acc_empty[grp]);
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[as]);
       if (eg == 0) tma_store_wait_read();   // this group's previous store has drained the other buffer
       fence_async_smem();
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
       if (eg == 0) {
         bulk_store_1d(p.out + row0 * (long long)oc, sbuf, uint32_t(rows_ok) * oc);
         tma_store_commit();
@@ -786,13 +795,13 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // warps per group (two warps sharing a TMEM lane quarter take alternate 16-column chunks), but measured on the
     // MobileNet expand layers the step is bound by the integer instruction count of the requantisation (about 5100
     // warp instructions per 128 x 96 tile, IPC 0.65): 16 warps in 2 or 4 groups did not move the per-tile time.
-    constexpr int wpg = kEpiWarps / kAccStages;  // warps per group
+    const int wpg = p.wide ? kEpiWarps : kEpiWarps / kAccStages;  // warps per group (p.wide: one group takes every tile)
     const int ew = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int grp = (warp - 4) / wpg;        // epilogue group == accumulator stage
+    const int grp = (warp - 4) / wpg;        // epilogue group (== accumulator stage with two groups)
     const int wg = (warp - 4) % wpg;         // warp inside the group
     const int half = wg >> 2;                // 8-warp groups: which 16-column chunks of a pass this warp takes (even / odd)
-    constexpr int cstep = 4 * wpg;           // columns between this warp's chunks (16 or 32)
-    constexpr int gthreads = 32 * wpg;
+    const int cstep = 4 * wpg;               // columns between this warp's chunks (16 or 32)
+    const int gthreads = 32 * wpg;
     const uint32_t acc_stride = uint32_t(kTmemCols / kAccStages);
     const int r = ew * 32 + lane;            // accumulator row == pixel of the tile
     const int eg = threadIdx.x - 128 - grp * gthreads;  // 0..gthreads-1 inside the group
@@ -817,8 +826,8 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t pass_count = 0;
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      if ((it & (kAccStages - 1)) != grp) continue;
-      const int as = grp;
+      if (!p.wide && (it & (kAccStages - 1)) != grp) continue;
+      const int as = it & (kAccStages - 1);
       const uint32_t use = uint32_t(it) / uint32_t(kAccStages);
       const bool tr = DIAG && p.trace && blockIdx.x == 0 && threadIdx.x == 128 && use < 32;
 #define TOD_TR(slot) do { if (DIAG && tr) p.trace[use * 16 + (slot)] = clock64(); } while (0)
@@ -917,7 +926,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           TOD_TR(6);
           fence_async_smem();
           TOD_TR(7);
-          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
           TOD_TR(8);
           if (eg == 0 && !(DIAG && (p.dbg & 1))) {
             if (p.lin) {  // the tile's rows are one contiguous block: a single 1-D bulk store instead of 128 box rows
@@ -929,7 +938,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         } else {
           TOD_TR(5);
-          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
           TOD_TR(6);
           // one warp per run: the per-run address set-up is a dependent chain of shared loads, so the eight warps walk
           // different runs; lanes stride the run's aligned 16-byte chunks and the first lanes carry the head / tail bytes
@@ -948,7 +957,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (lane < tail) gdst[head + 16 * body + lane] = int8_t(ssrc[head + 16 * body + lane]);
           }
           TOD_TR(7);
-          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(gthreads) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
           TOD_TR(8);
         }
       }
@@ -1044,7 +1053,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->acc_full[s], 1);
-      mbar_init(&ctl->acc_empty[s], 8);  // four epilogue warps of each CTA (used in the even CTA only)
+      mbar_init(&ctl->acc_empty[s], p.wide ? 16 : 8);  // the epilogue warps of both CTAs that read the stage (used in the even CTA only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1143,7 +1152,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs; same scheme as conv_tc_fast_kernel) =====================
     const int ew = warp & 3;
-    const int grp = (warp - 4) >> 2;
+    const int grp = p.wide ? 0 : (warp - 4) >> 2;
+    const int c_first = p.wide ? ((warp - 4) >> 2) * 16 : 0, cstep = p.wide ? 32 : 16;
+    const int gthreads = p.wide ? 256 : 128;
     const int r = ew * 32 + lane;
     const int eg = threadIdx.x - 128 - grp * 128;
     const int wx = r % p.pw;
@@ -1156,8 +1167,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t pass_count = 0;
     int it = 0;
     for (int item = pair; item < pair_items; item += npairs, ++it) {
-      if ((it & 1) != grp) continue;
-      const int as = grp;
+      if (!p.wide && (it & 1) != grp) continue;
+      const int as = it & 1;
       const uint32_t use = uint32_t(it >> 1);
       int n_tile, tx, ty, g;
       const bool real_tile = my_tile(item, &n_tile, &tx, &ty, &g);
@@ -1187,7 +1198,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int pass_cols = min(p.sc, ncols_tile - pass0);
         uint8_t* sbuf = grp_buf + (pass_count & 1u) * buf_bytes;
         ++pass_count;
-        for (int c0 = 0; c0 < pass_cols; c0 += 16) {
+        for (int c0 = c_first; c0 < pass_cols; c0 += cstep) {
           uint32_t v[16];
           tmem_ld16(taddr + pass0 + c0, v);
           tmem_wait_ld();
@@ -1238,7 +1249,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if (eg == 0) tma_store_wait_read();
         fence_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
         if (eg == 0 && real_tile) {
           if (p.flat) tma_store_4d(&map_o, sbuf, ocb + pass0, tx * kBM, 0, 0);
           else tma_store_4d(&map_o, sbuf, ocb + pass0, tx * p.pw, ty * p.ph, g * p.pn);
@@ -1746,15 +1757,19 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
 
 int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   if (tiles < 1 || tiles > c->max_tiles) return fail(TOD_ERR_CAPACITY, "conv_tc_launch: tiles=%d outside [1,%d]", tiles, c->max_tiles);
-  const TcParams& p = c->p;
+  TcParams p = c->p;
   const int tiles_x = p.flat ? (tiles * p.HW + kBM - 1) / kBM : p.tiles_x;
   const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
   const long long work = (long long)groups * p.tiles_y * tiles_x * p.n_tiles;
   const int grid = int(std::min<long long>(work, sm_count()));
+  // eight-warp epilogue when a CTA has only a few tiles (TOD_TC_WIDE: 0 = never, 1 = always, N > 1 = up to N tiles per CTA)
+  static const int wide_env = std::getenv("TOD_TC_WIDE") ? std::atoi(std::getenv("TOD_TC_WIDE")) : -1;
+  const int wide_max = wide_env < 0 ? 5 : (wide_env == 1 ? (1 << 30) : wide_env);
   if (c->pair) {
     const long long m_tiles = (long long)groups * p.tiles_y * tiles_x;
     const long long pair_items = ((m_tiles + 1) / 2) * p.n_tiles;
     const int pairs = int(std::min<long long>(pair_items, sm_count() / 2));
+    p.wide = (pair_items + pairs - 1) / pairs <= wide_max ? 1 : 0;
     if (c->mode == 21)
       TOD_CUDA(launch_k(conv_tc_pair_kernel<21>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
     else if (c->mode == 20)
@@ -1765,6 +1780,7 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
       TOD_CUDA(launch_k(conv_tc_pair_kernel<4>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));
     return TOD_OK;
   }
+  p.wide = (c->fast && (work + grid - 1) / grid <= wide_max) ? 1 : 0;
   if (!c->fast) {
     TOD_CUDA(launch_k(conv_tc_kernel, dim3(grid), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_b, p, tiles));
   } else {

@@ -9,6 +9,7 @@
 #include "common.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "fixedpoint.cuh"
 
@@ -636,6 +637,280 @@ __global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const
   }
 }
 
+// ------------------------------------------------------------------ depthwise 3x3, burst form
+// The sliding kernel above keeps one input row (three 4-byte loads) in flight per thread and walks 7 - 16 rows: a chain of
+// 7 - 16 dependent memory round trips, ~1.4 - 2.4 TB/s whatever the layer (round-2 layer table: 10.5 us for the 9.6 MB of a
+// 14 x 14 x 384 layer, 29 us for the 51 MB of the 112 x 112 x 32 one).  Here a thread owns R consecutive output rows of its
+// (column, channel word) and issues ALL (R - 1) * STRIDE + 3 input rows before any arithmetic - one round trip per thread,
+// 15 - 18 independent loads in flight - and the parallelism comes from OH / R times more threads.  Rows shared between
+// vertically adjacent threads are re-read from L1 / L2 ((R + 2) / R input reads per byte).  Same arithmetic, same bytes.
+template <int STRIDE, bool SAT, bool RELU, int R>
+__global__ void __launch_bounds__(kDwThreads, 6) depthwise3x3_burst_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                                        const int8_t* __restrict__ w,
+                                                                        const int32_t* __restrict__ bias, int32_t in_zp,
+                                                                        ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                                        int64_t out_ts) {
+  pdl_trigger();
+  constexpr int NR = (R - 1) * STRIDE + 3;
+  const int C = g.OC, CW = C >> 2;
+  const int j = blockIdx.x * kDwThreads + threadIdx.x;
+  if (j >= g.OW * CW) return;
+  const int ox = j / CW, c = (j - ox * CW) * 4;
+  auto transpose = [](unsigned a0, unsigned a1, unsigned a2, unsigned (&t)[4]) {
+    const unsigned lo = __byte_perm(a0, a1, 0x5140);
+    const unsigned hi = __byte_perm(a0, a1, 0x7362);
+    t[0] = __byte_perm(lo, a2, 0x4410);
+    t[1] = __byte_perm(lo, a2, 0x5532);
+    t[2] = __byte_perm(hi, a2, 0x6610);
+    t[3] = __byte_perm(hi, a2, 0x7732);
+  };
+  const unsigned zp4 = unsigned(in_zp & 0xFF) * 0x01010101u;
+  const int ix0 = ox * STRIDE - g.pad_left;
+  const bool vx0 = ix0 >= 0 && ix0 < g.IW, vx1 = ix0 + 1 >= 0 && ix0 + 1 < g.IW, vx2 = ix0 + 2 >= 0 && ix0 + 2 < g.IW;
+  const int oy0 = blockIdx.y * R;
+  const int iy0 = oy0 * STRIDE - g.pad_top;
+  const int64_t row_pitch = int64_t(g.IW) * C;
+  const int8_t* base = in + int64_t(blockIdx.z) * in_ts + int64_t(iy0) * row_pitch + int64_t(ix0) * C + c;
+  // filters and constants first (they do not depend on the previous kernel)
+  unsigned wv[3][3];
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy)
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) wv[fy][fx] = unsigned(__ldg(reinterpret_cast<const int*>(w + int64_t(fy * 3 + fx) * C + c)));
+  int4 k[4];
+  int bs[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    k[q] = __ldg(rq.fast_tab + c + q);
+    bs[q] = bias ? __ldg(bias + c + q) : 0;
+  }
+  pdl_wait();
+  unsigned raw[NR][3];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int iy = iy0 + r;
+    const bool vy = iy >= 0 && iy < g.IH;
+    const int8_t* p = base + int64_t(r) * row_pitch;
+    raw[r][0] = raw[r][1] = raw[r][2] = zp4;
+    if (vy && vx0) raw[r][0] = *reinterpret_cast<const unsigned*>(p);
+    if (vy && vx1) raw[r][1] = *reinterpret_cast<const unsigned*>(p + C);
+    if (vy && vx2) raw[r][2] = *reinterpret_cast<const unsigned*>(p + 2 * C);
+  }
+  unsigned wt[3][4];
+  int wall[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wall[q] += int(wv[fy][fx] << (24 - 8 * q)) >> 24;
+    transpose(wv[fy][0], wv[fy][1], wv[fy][2], wt[fy]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wt[fy][q] &= 0x00FFFFFFu;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bs[q] -= in_zp * wall[q];
+  int8_t* op = out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c;
+  const int64_t ostep = int64_t(g.OW) * C;
+  unsigned t[NR][4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) transpose(raw[r][0], raw[r][1], raw[r][2], t[r]);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (oy0 + r >= g.OH) break;
+    int o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int a = __dp4a(int(t[r * STRIDE][q]), int(wt[0][q]), bs[q]);
+      a = __dp4a(int(t[r * STRIDE + 1][q]), int(wt[1][q]), a);
+      a = __dp4a(int(t[r * STRIDE + 2][q]), int(wt[2][q]), a);
+      if (RELU) o[q] = requant_relu(a, k[q].x, k[q].y, (int64_t(k[q].w) << 32) | int64_t(uint32_t(k[q].z)));
+      else o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
+    }
+    unsigned packed;
+    if (SAT) {
+      unsigned hi;
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o[3]), "r"(o[2]), "r"(0u));
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(packed) : "r"(o[1]), "r"(o[0]), "r"(hi));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = max(rq.act_min, min(rq.act_max, o[q]));
+      packed = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
+    }
+    *reinterpret_cast<unsigned*>(op + r * ostep) = packed;
+  }
+}
+
+// ------------------------------------------------------------------ depthwise 3x3, lean form (default)
+// ncu on the sliding kernel above (round 2, whole-step capture): 107 SASS instructions per output word of which ~32 are
+// the arithmetic (3 loads, 6 PRMT, 12 dp4a, 8 requantisation, 2 pack, 1 store); issue 57 - 67 %, ALU pipe 45 - 54 %,
+// "not selected" / "math pipe throttle" on top - the rest was 64-bit address arithmetic recomputed per load, per-load
+// column / row predicates with their zero-point moves, and weight masking inside the loop.  Same dataflow here, with
+//   * the channel count as a template parameter (CWT = channels / 4; 0 = any): the three taps of a row are
+//     [p], [p + C], [p + 2C] off ONE pointer that advances by the row pitch;
+//   * no column predicates: a thread on the left / right image border shifts its three columns into the image and
+//     permutes its filter columns to match (the column that left the window gets zero weights, and the bias term
+//     bias - zp * sum(w) only sums the taps that are inside), so every load is unconditional in x;
+//   * rows outside the image read as the zero point behind a warp-uniform test (the row index depends on blockIdx.y and
+//     the loop counter only).
+// Bytes are identical to the sliding kernel (tests/test_gpu_graph.py, test_gpu_property.py run both against the oracle).
+template <int STRIDE, bool SAT, bool RELU, int CWT>
+__global__ void __launch_bounds__(kDwThreads, STRIDE == 1 ? 7 : 8) depthwise3x3_lean_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                                      const int8_t* __restrict__ w,
+                                                                      const int32_t* __restrict__ bias, int32_t in_zp,
+                                                                      ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                                      int64_t out_ts, int rows_per_block) {
+  pdl_trigger();
+  const int CW = CWT ? CWT : (g.OC >> 2);
+  const int C = CW * 4;
+  const int j = blockIdx.x * kDwThreads + threadIdx.x;
+  if (j >= g.OW * CW) return;
+  const int ox = j / CW, c = (j - ox * CW) * 4;
+  auto transpose = [](unsigned a0, unsigned a1, unsigned a2, unsigned (&t)[4]) {
+    const unsigned lo = __byte_perm(a0, a1, 0x5140);
+    const unsigned hi = __byte_perm(a0, a1, 0x7362);
+    t[0] = __byte_perm(lo, a2, 0x4410);
+    t[1] = __byte_perm(lo, a2, 0x5532);
+    t[2] = __byte_perm(hi, a2, 0x6610);
+    t[3] = __byte_perm(hi, a2, 0x7732);
+  };
+  // window columns ix0 .. ix0 + 2; a border thread shifts them into the image (the host guarantees IW >= 3 and at most one
+  // column outside on either side) and reads its filter columns through the same shift
+  int ix0 = ox * STRIDE - g.pad_left;
+  const int shift = ix0 < 0 ? 1 : (ix0 + 2 >= g.IW ? -1 : 0);
+  ix0 += shift;
+  unsigned wt[3][4];  // wt[fy][q] = {w(fy, col 0, q), w(fy, col 1, q), w(fy, col 2, q), 0} for the shifted columns
+  int wall[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+    unsigned wv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int fx = k + shift;
+      wv[k] = (fx >= 0 && fx < 3) ? unsigned(__ldg(reinterpret_cast<const int*>(w + int64_t(fy * 3 + fx) * C + c))) : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wall[q] += int(wv[k] << (24 - 8 * q)) >> 24;
+    }
+    transpose(wv[0], wv[1], wv[2], wt[fy]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wt[fy][q] &= 0x00FFFFFFu;
+  }
+  int4 k[4];
+  int bs[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    k[q] = __ldg(rq.fast_tab + c + q);
+    bs[q] = (bias ? __ldg(bias + c + q) : 0) - in_zp * wall[q];
+  }
+  const unsigned zp4 = unsigned(in_zp & 0xFF) * 0x01010101u;
+  const int oy0 = blockIdx.y * rows_per_block;
+  int n = min(g.OH, oy0 + rows_per_block) - oy0;   // output rows of this thread
+  int iy = oy0 * STRIDE - g.pad_top;               // first input row of the window
+  const int pitch = g.IW * CW;                     // input row pitch in words
+  const unsigned* p = reinterpret_cast<const unsigned*>(in + int64_t(blockIdx.z) * in_ts + int64_t(ix0) * C + c) + int64_t(iy) * pitch;
+  unsigned* op = reinterpret_cast<unsigned*>(out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c);
+  const int ostep = g.OW * CW;                     // output row pitch in words
+  const int IH = g.IH;
+  auto load_raw = [&](int row, const unsigned* q, unsigned (&a)[3]) {  // `row` is warp-uniform
+    if (unsigned(row) < unsigned(IH)) {
+      a[0] = q[0];
+      a[1] = q[CW];
+      a[2] = q[2 * CW];
+    } else {
+      a[0] = a[1] = a[2] = zp4;
+    }
+  };
+  auto emit = [&](const unsigned (&ra)[4], const unsigned (&rb)[4], const unsigned (&rc)[4], unsigned* dst) {
+    int o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int a = __dp4a(int(ra[q]), int(wt[0][q]), bs[q]);
+      a = __dp4a(int(rb[q]), int(wt[1][q]), a);
+      a = __dp4a(int(rc[q]), int(wt[2][q]), a);
+      if (RELU) o[q] = requant_relu(a, k[q].x, k[q].y, (int64_t(k[q].w) << 32) | int64_t(uint32_t(k[q].z)));
+      else o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
+    }
+    unsigned packed;
+    if (SAT) {
+      unsigned hi;
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o[3]), "r"(o[2]), "r"(0u));
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(packed) : "r"(o[1]), "r"(o[0]), "r"(hi));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = max(rq.act_min, min(rq.act_max, o[q]));
+      packed = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
+    }
+    *dst = packed;
+  };
+  pdl_wait();  // filters / requantisation constants are in registers; the activations come next
+  unsigned nx[3];
+  if (STRIDE == 1) {
+    unsigned ra[4], rb[4], rc[4], rd[4];
+    load_raw(iy, p, nx);
+    transpose(nx[0], nx[1], nx[2], ra);
+    load_raw(iy + 1, p + pitch, nx);
+    transpose(nx[0], nx[1], nx[2], rb);
+    load_raw(iy + 2, p + 2 * pitch, nx);
+    transpose(nx[0], nx[1], nx[2], rc);
+    p += 3 * int64_t(pitch);
+    iy += 3;  // the next row to load
+    // four register rows rotate through the roles (top, middle, bottom, incoming); the next row's loads are issued before
+    // the current row's arithmetic and transposed after it.  (A row past the thread's last window is loaded and dropped.)
+    for (; n >= 4; n -= 4) {
+      load_raw(iy, p, nx);
+      emit(ra, rb, rc, op);
+      transpose(nx[0], nx[1], nx[2], rd);
+      load_raw(iy + 1, p + pitch, nx);
+      emit(rb, rc, rd, op + ostep);
+      transpose(nx[0], nx[1], nx[2], ra);
+      load_raw(iy + 2, p + 2 * pitch, nx);
+      emit(rc, rd, ra, op + 2 * ostep);
+      transpose(nx[0], nx[1], nx[2], rb);
+      load_raw(iy + 3, p + 3 * pitch, nx);
+      emit(rd, ra, rb, op + 3 * ostep);
+      transpose(nx[0], nx[1], nx[2], rc);
+      p += 4 * int64_t(pitch);
+      op += 4 * int64_t(ostep);
+      iy += 4;
+    }
+    for (; n > 0; --n) {
+      load_raw(iy, p, nx);
+      emit(ra, rb, rc, op);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ra[q] = rb[q];
+        rb[q] = rc[q];
+      }
+      transpose(nx[0], nx[1], nx[2], rc);
+      p += pitch;
+      op += ostep;
+      ++iy;
+    }
+  } else {
+    unsigned r0[4], r1[4], r2[4], n2[3];
+    load_raw(iy, p, nx);
+    transpose(nx[0], nx[1], nx[2], r0);
+    load_raw(iy + 1, p + pitch, nx);
+    transpose(nx[0], nx[1], nx[2], r1);
+    load_raw(iy + 2, p + 2 * pitch, nx);
+    transpose(nx[0], nx[1], nx[2], r2);
+    p += 3 * int64_t(pitch);
+    iy += 3;
+    for (; n > 0; --n) {
+      load_raw(iy, p, nx);
+      load_raw(iy + 1, p + pitch, n2);
+      emit(r0, r1, r2, op);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r0[q] = r2[q];
+      transpose(nx[0], nx[1], nx[2], r1);
+      transpose(n2[0], n2[1], n2[2], r2);
+      p += 2 * int64_t(pitch);
+      op += ostep;
+      iy += 2;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ ADD (residual / FPN merge)
 // The two input rescales depend on one byte each, so they are tabulated per CTA (256 entries each, built with
 // the literal arithmetic); the output rescale uses the fast exact form (|ya + yb| < 2^29).
@@ -906,12 +1181,64 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
       (g.stride_h == 1 || g.stride_h == 2) && tiles <= 65535) {
     const int words = g.OW * (g.OC / 4);
     const int gx = (words + kDwThreads - 1) / kDwThreads;
+    const bool sat = rq.act_min == -128 && rq.act_max == 127;
+    // TOD_DW_IMPL: 0 (default) = lean kernel (sliding kernel where it does not apply), 2 = sliding kernel, 1 = burst kernel (all of
+    // a thread's input rows in flight at once; measured 2 % slower per step)
+    static const int dw_impl = std::getenv("TOD_DW_IMPL") ? std::atoi(std::getenv("TOD_DW_IMPL")) : 0;
+    static const int dw_r1 = std::getenv("TOD_DW_R1") ? std::atoi(std::getenv("TOD_DW_R1")) : 4;
+    static const int dw_r2 = std::getenv("TOD_DW_R2") ? std::atoi(std::getenv("TOD_DW_R2")) : 2;
+    // lean kernel: ReLU-form table, at most one window column outside the image on either side, tile fits 32-bit word offsets
+    const bool lean_ok = rq.relu_tab && g.IW >= 3 && g.pad_left <= 1 && (g.OW - 1) * g.stride_w - g.pad_left + 2 <= g.IW &&
+                         int64_t(g.IH + 4) * g.IW * g.OC < (int64_t(1) << 31);
+    if (dw_impl == 0 && lean_ok) {
+      int rpb = g.OH;
+      while (rpb > 4 && int64_t(gx) * ((g.OH + rpb - 1) / rpb) * tiles < 148 * 8) rpb = (rpb + 1) / 2;
+      rpb = std::min(rpb, 16);
+      dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
+      const int cw = g.OC / 4;
+#define TOD_DWL(ST, SA, CWT) launch_k(depthwise3x3_lean_kernel<ST, SA, true, CWT>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb)
+#define TOD_DWL_C(CWT)                                                              \
+  do {                                                                              \
+    if (g.stride_h == 1) { if (sat) TOD_DWL(1, true, CWT); else TOD_DWL(1, false, CWT); } \
+    else { if (sat) TOD_DWL(2, true, CWT); else TOD_DWL(2, false, CWT); }           \
+  } while (0)
+      switch (cw) {  // MobileNetV2's depthwise widths (32 ... 960 channels); anything else takes the runtime-width build
+        case 8: TOD_DWL_C(8); break;
+        case 24: TOD_DWL_C(24); break;
+        case 36: TOD_DWL_C(36); break;
+        case 48: TOD_DWL_C(48); break;
+        case 96: TOD_DWL_C(96); break;
+        case 144: TOD_DWL_C(144); break;
+        case 240: TOD_DWL_C(240); break;
+        default: TOD_DWL_C(0); break;
+      }
+#undef TOD_DWL_C
+#undef TOD_DWL
+      return;
+    }
+    if (dw_impl == 1) {
+      const int R = g.stride_h == 1 ? dw_r1 : dw_r2;
+      dim3 grid(gx, (g.OH + R - 1) / R, tiles);
+#define TOD_DWB(ST, SA, RE, RR) launch_k(depthwise3x3_burst_kernel<ST, SA, RE, RR>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts)
+#define TOD_DWB_R(ST, RR)                                                                   \
+  do {                                                                                      \
+    if (rq.relu_tab) { if (sat) TOD_DWB(ST, true, true, RR); else TOD_DWB(ST, false, true, RR); } \
+    else { if (sat) TOD_DWB(ST, true, false, RR); else TOD_DWB(ST, false, false, RR); }     \
+  } while (0)
+      if (g.stride_h == 1) {
+        if (R == 2) TOD_DWB_R(1, 2); else if (R == 3) TOD_DWB_R(1, 3); else TOD_DWB_R(1, 4);
+      } else {
+        if (R == 1) TOD_DWB_R(2, 1); else if (R == 3) TOD_DWB_R(2, 3); else TOD_DWB_R(2, 2);
+      }
+#undef TOD_DWB_R
+#undef TOD_DWB
+      return;
+    }
     // rows per block: long enough to amortise the two warm-up rows, short enough for >= ~4 CTAs per SM
     int rpb = g.OH;
     while (rpb > 4 && int64_t(gx) * ((g.OH + rpb - 1) / rpb) * tiles < 148 * 8) rpb = (rpb + 1) / 2;
     rpb = std::min(rpb, 16);
     dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
-    const bool sat = rq.act_min == -128 && rq.act_max == 127;
 #define TOD_DW(ST, SA, RE) launch_k(depthwise3x3_slide_kernel<ST, SA, RE>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb)
     if (g.stride_h == 1) {
       if (rq.relu_tab) { if (sat) TOD_DW(1, true, true); else TOD_DW(1, false, true); }

@@ -903,6 +903,15 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
 int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
   const Place& pi = y->place[st.in0];
   const Place& po = st.out_moved ? st.out_place : y->place[st.out];
+  // TOD_DIAG_SKIP (timing attribution only, results are garbage): 1 = no depthwise, 2 = no resize, 4 = no tcgen05 convs, 8 = no detection tail,
+  // 16 = no stem / direct conv
+  static const int diag_skip = std::getenv("TOD_DIAG_SKIP") ? std::atoi(std::getenv("TOD_DIAG_SKIP")) : 0;
+  if (diag_skip) {
+    if ((diag_skip & 1) && st.kind == kStepDepthwise) return TOD_OK;
+    if ((diag_skip & 2) && st.kind == kStepResize) return TOD_OK;
+    if ((diag_skip & 4) && st.kind == kStepConvTc) return TOD_OK;
+    if ((diag_skip & 16) && st.kind == kStepConvDirect) return TOD_OK;
+  }
   switch (st.kind) {
     case kStepConvTc:
       return conv_tc_launch(st.tc, n, s);
@@ -1551,7 +1560,8 @@ int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int
   const Place& pin = y->place[y->graph.inputs[0]];
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), d_rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n),
                              cudaMemcpyDeviceToDevice, s));
-  const bool dets = y->det_ready && y->have_priors;
+  static const bool diag_nodets = std::getenv("TOD_DIAG_SKIP") && (std::atoi(std::getenv("TOD_DIAG_SKIP")) & 8);
+  const bool dets = y->det_ready && y->have_priors && !diag_nodets;
   y->last_mask_mode = dets ? 2 : 0;
   TOD_TRY(run_pipeline(y, n, dets, dets ? 2 : 0, s));
   return order_after_caller(y, s);

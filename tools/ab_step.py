@@ -34,4 +34,27 @@ for rep in range(3):
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1) / steps)
 print("%s: %.4f ms/step (%d tiles, best of 3 x %d)" % (os.environ.get("TOD_B200_LIB", "default"), best, tiles, steps))
+depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+if depth > 1:  # batches in flight, as bench.py's headline: `depth` handles take alternate steps on their own streams
+    ys = [y] + [tod_b200.Yolact.init(full, max_tiles=tiles) for _ in range(depth - 1)]
+    pst = [torch.cuda.Stream() for _ in range(depth)]
+    for k in range(4 * depth):
+        ys[k % depth].infer_tiles_device(d.data_ptr(), tiles, pst[k % depth].cuda_stream)
+    torch.cuda.synchronize()
+    pbest = 1e9
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for ps in pst:
+            ps.wait_event(e0)
+        for k in range(steps):
+            ys[k % depth].infer_tiles_device(d.data_ptr(), tiles, pst[k % depth].cuda_stream)
+        for ps in pst:
+            ts.wait_stream(ps)
+        e1.record()
+        torch.cuda.synchronize()
+        pbest = min(pbest, e0.elapsed_time(e1) / steps)
+    print("%s: %.4f ms/step with %d batches in flight" % (os.environ.get("TOD_B200_LIB", "default"), pbest, depth))
+    for yy in ys[1:]:
+        yy.close()
 y.close()
