@@ -471,6 +471,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // instead of 5.  tests/cpp/fixedpoint_check.cpp checks the identity against the literal gemmlowp form.
 enum : uint32_t { kEpiSat = 1, kEpiLut = 2, kEpiTma = 4, kEpiAdd = 8, kEpiRelu = 16 };
 
+// n 16-byte words global -> shared, four loads per thread in flight per round
+__device__ __forceinline__ void copy_table16(int4* dst, const int4* __restrict__ src, int n, int nthreads) {
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * nthreads) {
+    int4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * nthreads < n) v[u] = __ldg(src + i0 + u * nthreads);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * nthreads < n) dst[i0 + u * nthreads] = v[u];
+  }
+}
+
 struct WorkItem { int n_tile, tx, ty, g; };
 __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles_x, int tiles_y) {
   WorkItem w;
@@ -595,11 +608,11 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     mbar_init(&ctl->b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.OCp; i += kFastThreads) s_qtab[i] = p.qtab[i];
-  if (MODE & kEpiRelu)
-    for (int i = threadIdx.x; i < 2 * p.ncls * p.OCp; i += kFastThreads) s_b2[i] = reinterpret_cast<const int32_t*>(p.a64tab)[i];
-  else
-    for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kFastThreads) s_b2[i] = p.b2tab[i];
+  // epilogue tables -> shared memory with 16-byte loads, all of a thread's loads in flight at once (a 3x3 ReLU layer's
+  // nine border classes are 18 KB: the word-by-word loop was twelve dependent round trips of prologue per CTA)
+  copy_table16(s_qtab, p.qtab, p.OCp, kFastThreads);
+  if (MODE & kEpiRelu) copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.a64tab), p.ncls * p.OCp / 2, kFastThreads);
+  else copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.b2tab), p.ncls * p.OCp / 4, kFastThreads);
   if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
   if (MODE & kEpiAdd)
     for (int i = threadIdx.x; i < 512; i += kFastThreads) ctl->add_tab[i] = p.add_tab[i];
@@ -1057,11 +1070,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.OCp; i += kTcThreads) s_qtab[i] = p.qtab[i];
-  if (MODE & kEpiRelu)
-    for (int i = threadIdx.x; i < 2 * p.ncls * p.OCp; i += kTcThreads) s_b2[i] = reinterpret_cast<const int32_t*>(p.a64tab)[i];
-  else
-    for (int i = threadIdx.x; i < p.ncls * p.OCp; i += kTcThreads) s_b2[i] = p.b2tab[i];
+  copy_table16(s_qtab, p.qtab, p.OCp, kTcThreads);
+  if (MODE & kEpiRelu) copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.a64tab), p.ncls * p.OCp / 2, kTcThreads);
+  else copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.b2tab), p.ncls * p.OCp / 4, kTcThreads);
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
