@@ -355,56 +355,84 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const 
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmall = 512;
 constexpr int kNmsRank = 256;   // lists up to this long are rank-sorted (needs top_k <= sort_cap / 2, checked per launch)
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_lo, int n_hi) {
-  extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k]
+
+// One (class, tile) list.  All threads of the CTA call it with the same arguments.
+//  * sort: lists of <= kNmsRank candidates are rank-sorted (keys are unique - the prior index is part of the key - so a
+//    key's position in the descending order is the number of larger keys: one pass over the list per thread and one
+//    barrier, against 28 - 36 barrier-separated compare-exchange rounds of the bitonic network).  A thread issues the load
+//    of its candidate's box before it counts, so the gather's latency hides behind the rank loop and the box lands at its
+//    sorted position directly.
+//  * Fast-NMS: keep[j] <=> no row i < j of the upper-triangular IoU matrix exceeds the threshold.  Column j costs j tests,
+//    so one lane per column (round 1) left the warp of the last columns walking ~m rows alone (ncu: 21 - 39 % of the warps
+//    active, the kernel pair 14 % of all instructions of the step).  Here columns are paired (q, m - 1 - q): every pair costs
+//    m - 1 tests, and S = 256 / pairs threads share a pair's rows; a suppressed column is a flag in shared memory.
+__device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers& b, unsigned long long* s_keys, int sort_cap, int k, int t, int n) {
   float4* s_box = reinterpret_cast<float4*>(s_keys + sort_cap);
   float* s_area = reinterpret_cast<float*>(s_box + c.top_k);
-  const int k = blockIdx.x;  // foreground class
-  const int t = blockIdx.y;
-  const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
-  if (n <= n_lo || n > n_hi) return;
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
+  int* s_sup = reinterpret_cast<int*>(s_area + c.top_k);
   const unsigned long long* src = b.cand + (int64_t(t) * (c.C - 1) + k) * c.P;
   const int m = min(n, c.top_k);
+  const float4* boxes = reinterpret_cast<const float4*>(b.boxes) + int64_t(t) * c.P;
+  for (int i = threadIdx.x; i < m; i += kNmsThreads) s_sup[i] = 0;
   if (n <= kNmsRank && n <= sort_cap / 2) {
-    // short lists: rank sort.  Keys are unique (the prior index is part of the key), so a key's position in the descending
-    // order is the number of larger keys: one pass over the list per thread, one barrier, against 28..36 barrier-separated
-    // compare-exchange rounds of the bitonic network.  Only the top_k ranks are written (into the upper half of s_keys).
-    for (int i = threadIdx.x; i < n; i += kNmsThreads) s_keys[i] = src[i];
+    unsigned long long key = 0ull;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (int(threadIdx.x) < n) {   // n <= kNmsRank == kNmsThreads: one candidate per thread
+      key = src[threadIdx.x];
+      s_keys[threadIdx.x] = key;
+      bx = boxes[int(0xFFFFFFFFu - unsigned(key & 0xFFFFFFFFull))];
+    }
     __syncthreads();
-    unsigned long long* s_sorted = s_keys + sort_cap / 2;
-    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
-      const unsigned long long key = s_keys[i];
+    if (int(threadIdx.x) < n) {
       int rank = 0;
 #pragma unroll 8
       for (int q = 0; q < n; ++q) rank += s_keys[q] > key ? 1 : 0;
-      if (rank < m) s_sorted[rank] = key;
+      if (rank < m) {
+        s_keys[sort_cap / 2 + rank] = key;
+        s_box[rank] = bx;
+        s_area[rank] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+      }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += kNmsThreads) s_keys[i] = s_sorted[i];
-    __syncthreads();
+    s_keys += sort_cap / 2;   // the sorted keys
   } else {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
     for (int i = threadIdx.x; i < np2; i += kNmsThreads) s_keys[i] = i < n ? src[i] : 0ull;
     bitonic_sort_desc(s_keys, np2);
+    for (int i = threadIdx.x; i < m; i += kNmsThreads) {
+      const float4 bx = boxes[int(0xFFFFFFFFu - unsigned(s_keys[i] & 0xFFFFFFFFull))];
+      s_box[i] = bx;
+      s_area[i] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < m; i += kNmsThreads) {
-    const int prior = int(0xFFFFFFFFu - unsigned(s_keys[i] & 0xFFFFFFFFull));
-    const float4 bx = reinterpret_cast<const float4*>(b.boxes)[int64_t(t) * c.P + prior];
-    s_box[i] = bx;
-    s_area[i] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+  // column pairs (q, m - 1 - q), S threads per pair taking interleaved rows
+  const int pairs = (m + 1) >> 1;
+  const int S = max(1, kNmsThreads / max(pairs, 1));
+  for (int u = threadIdx.x; u < pairs * S; u += kNmsThreads) {
+    const int q = u % pairs, sub = u / pairs;
+    const int ja = q, jb = m - 1 - q;
+    {
+      const float4 bj = s_box[jb];
+      const float aj = s_area[jb];
+      bool sup = false;
+      for (int i = sub; i < jb && !sup; i += S) sup = iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
+      if (sup) s_sup[jb] = 1;
+    }
+    if (ja != jb) {
+      const float4 bj = s_box[ja];
+      const float aj = s_area[ja];
+      bool sup = false;
+      for (int i = S - 1 - sub; i < ja && !sup; i += S) sup = iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
+      if (sup) s_sup[ja] = 1;
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   for (int j0 = (threadIdx.x >> 5) * 32; j0 < m; j0 += kNmsThreads) {
     const int j = j0 + lane;
-    bool keep = false;
-    if (j < m) {
-      const float4 bj = s_box[j];
-      const float aj = s_area[j];
-      keep = true;  // column max of the upper-triangular IoU matrix <= thresh  <=>  no row i < j exceeds it
-      for (int i = 0; i < j && keep; ++i) keep = !iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
-    }
+    const bool keep = j < m && !s_sup[j];
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     int base = 0;
     if (lane == 0 && bal) base = atomicAdd(b.surv_count + t, __popc(bal));
@@ -416,6 +444,56 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuf
       b.surv[int64_t(t) * (c.C - 1) * c.top_k + base + __popc(bal & ((1u << lane) - 1))] =
           (key & 0xFFFFFFFF00000000ull) | (static_cast<unsigned long long>(order) << 16) | prior;
     }
+  }
+}
+
+// Fast-NMS, one CTA per (class, tile) whose list has at most n_hi candidates (8 KB of shared memory: the whole grid is
+// resident at once).  Longer lists belong to nms_long_kernel.
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_hi) {
+  extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k], int suppressed[top_k]
+  const int k = blockIdx.x, t = blockIdx.y;
+  const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
+  if (n <= 0 || n > n_hi) return;
+  nms_one(c, b, s_keys, sort_cap, k, t, n);
+}
+
+// The lists above n_lo candidates (worst case: every prior a candidate, 36 KB of sort buffer).  A few persistent CTAs instead
+// of one CTA per list (5120 CTAs of 36 KB each, most of which only found out that they had nothing to do): every CTA reads
+// the whole count array once (all loads in flight), builds the same ordered list of the long lists - a bitmap in shared
+// memory, then a prefix over its words - and takes the entries blockIdx.x, blockIdx.x + gridDim.x, ...
+constexpr int kNmsLongMaxLists = 16384;   // bitmap capacity: (C - 1) * tiles
+__global__ void __launch_bounds__(kNmsThreads) nms_long_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_lo, int lists) {
+  extern __shared__ unsigned long long s_keys[];
+  __shared__ unsigned s_bits[kNmsLongMaxLists / 32];
+  __shared__ int s_pref[kNmsLongMaxLists / 32 + 1];
+  const int words = (lists + 31) >> 5;
+  for (int w = threadIdx.x; w < words; w += kNmsThreads) s_bits[w] = 0u;
+  __syncthreads();
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < lists; idx += kNmsThreads)
+    if (b.cand_count[idx] > n_lo) atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int w = 0; w < words; ++w) {
+      s_pref[w] = acc;
+      acc += __popc(s_bits[w]);
+    }
+    s_pref[words] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[words];
+  for (int e = blockIdx.x; e < total; e += gridDim.x) {
+    // the e-th long list: the word whose prefix range holds e, then the (e - prefix)-th set bit of that word
+    int w = 0;
+    while (s_pref[w + 1] <= e) ++w;
+    unsigned bits = s_bits[w];
+    for (int r = e - s_pref[w]; r > 0; --r) bits &= bits - 1;
+    const int idx = (w << 5) + __ffs(int(bits)) - 1;
+    const int n = b.cand_count[idx];
+    const int t = idx / (c.C - 1), k = idx - t * (c.C - 1);
+    __syncthreads();           // the previous list's shared-memory readers are done
+    nms_one(c, b, s_keys, sort_cap, k, t, n);
   }
 }
 
@@ -676,7 +754,7 @@ void launch_classify_post(const uint32_t* tile_px, int n, int W, int H, const Re
 }
 
 size_t detect_select_smem(const DetectCfg& c) { return size_t(next_pow2((c.C - 1) * c.top_k)) * 8 + size_t(kSelCap) * 8 + size_t(kSelBins) * 4; }
-static size_t nms_smem_for(const DetectCfg& c, int cap) { return size_t(cap) * 8 + size_t(c.top_k) * 20; }
+static size_t nms_smem_for(const DetectCfg& c, int cap) { return size_t(cap) * 8 + size_t(c.top_k) * 24; }
 static size_t nms_smem(const DetectCfg& c) { return nms_smem_for(c, next_pow2(c.P)); }
 static size_t mask_smem(const DetectCfg& c) { return size_t(c.max_dets) * (c.K + 4 + 16); }
 
@@ -690,6 +768,7 @@ int detect_setup_kernels(const DetectCfg& c) {
   // handle with a smaller head created later cannot lower it under an existing one
   TOD_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   TOD_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TOD_CUDA(cudaFuncSetAttribute(nms_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return TOD_OK;
 }
 
@@ -705,14 +784,17 @@ int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_
   // while the small one fills the machine, so with a second stream they run side by side
   const bool large = next_pow2(c.P) > small_cap;
   const bool split = large && aux && ev_fork && ev_join;
+  const int lists = (c.C - 1) * tiles;
+  const int long_grid = std::min(lists, 4 * 148);
+  if (lists > kNmsLongMaxLists) return fail(TOD_ERR_CAPACITY, "detection: %d (class, tile) lists exceed the Fast-NMS scan capacity %d", lists, kNmsLongMaxLists);
   if (split) {
     TOD_CUDA(cudaEventRecord(ev_fork, s));
     TOD_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
-    nms_kernel<<<g2, kNmsThreads, nms_smem(c), aux>>>(c, b, next_pow2(c.P), small_cap, c.P);
+    nms_long_kernel<<<long_grid, kNmsThreads, nms_smem(c), aux>>>(c, b, next_pow2(c.P), small_cap, lists);
     TOD_CUDA(cudaEventRecord(ev_join, aux));
   }
-  nms_kernel<<<g2, kNmsThreads, nms_smem_for(c, small_cap), s>>>(c, b, small_cap, 0, small_cap);
-  if (large && !split) nms_kernel<<<g2, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P), small_cap, c.P);
+  nms_kernel<<<g2, kNmsThreads, nms_smem_for(c, small_cap), s>>>(c, b, small_cap, small_cap);
+  if (large && !split) nms_long_kernel<<<long_grid, kNmsThreads, nms_smem(c), s>>>(c, b, next_pow2(c.P), small_cap, lists);
   if (split) TOD_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
   select_kernel<<<tiles, kSelThreads, detect_select_smem(c), s>>>(c, b, next_pow2((c.C - 1) * c.top_k));
   TOD_CUDA(cudaGetLastError());

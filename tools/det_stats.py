@@ -25,3 +25,6 @@ cand = (p[:, :, 1:] > 0.05).sum(axis=1)  # [tile, class]
 print("candidates per (tile, class): mean %.1f max %d; classes with >0: %.1f / 80; per tile total: %s" % (
     cand.mean(), cand.max(), (cand > 0).sum(axis=1).mean(), cand.sum(axis=1)[:8]))
 print("detections per tile:", {k: (v["count"][:8] if isinstance(v, dict) and "count" in v else None) for k, v in res.items() if k.startswith("det")})
+hist = np.histogram(cand.reshape(-1), bins=[0, 1, 16, 32, 64, 128, 200, 256, 512, 1024, 4096, 1 << 20])[0]
+print("list-length histogram [0,1,16,32,64,128,200,256,512,1024,4096,inf):", hist.tolist())
+print("sum n^2/2 over lists: %.0f per tile; sum min(n,200)^2/2: %.0f per tile" % ((cand.astype(np.float64) ** 2 / 2).sum() / n, (np.minimum(cand, 200).astype(np.float64) ** 2 / 2).sum() / n))
