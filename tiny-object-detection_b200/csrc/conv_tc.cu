@@ -84,6 +84,8 @@ struct TcParams {
   int wide;                    // epilogue: 1 = all eight warps convert every tile (two warps per TMEM lane quarter take alternate 16-column
                                // chunks; tiles alternate accumulator stages), 0 = two groups of four warps take alternate tiles.  Chosen per
                                // launch: with 1 - 3 tiles per CTA the last tile's epilogue is the CTA's tail, and eight warps halve it
+  int late_trig;               // 1 = griddepcontrol.launch_dependents when the CTA starts its LAST work item (the dependent grid's CTAs then
+                               // wait one tile on their SMs, not the whole launch), 0 = at kernel start
   int lin;                     // fast kernel, TMA mode: tile rows are contiguous in global memory, staged linearly, one 1-D bulk store
   int run_w;                   // manual stores: pixels per staged run (pw, or pw * ph when the patch spans the image width)
   long long* trace;            // TOD_TC_TRACE: clock64 stamps of CTA 0 (epilogue warp 4 / MMA warp / producer), 16 per tile
@@ -588,7 +590,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const long long* s_a64 = reinterpret_cast<const long long*>(s_b2);   // kEpiRelu: the same region holds 64-bit addends
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp * ((MODE & kEpiRelu) ? 2 : 1));
 
-  pdl_trigger();
+  if (!p.late_trig) pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = p.flat ? tiles * p.HW : p.Wd;
   const int tiles_x = p.flat ? (Wd + kBM - 1) / kBM : p.tiles_x;
@@ -642,6 +644,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
     }
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      if (p.late_trig && pt == 0 && work + int(gridDim.x) >= total_work) pdl_trigger();
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
       const long long row0 = (long long)w.tx * kBM;
       for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -687,6 +690,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
       }
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        if (p.late_trig && work + int(gridDim.x) >= total_work) pdl_trigger();
         const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
         const int x0 = w.tx * p.pw, y0 = w.ty * p.ph, n0 = w.g * p.pn;
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -1047,7 +1051,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const long long* s_a64 = reinterpret_cast<const long long*>(s_b2);   // kEpiRelu: 64-bit addends
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b2 + size_t(p.ncls) * p.OCp * ((MODE & kEpiRelu) ? 2 : 1));
 
-  pdl_trigger();
+  if (!p.late_trig) pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -1106,6 +1110,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < pair_items; item += npairs) {
+        if (p.late_trig && item + npairs >= pair_items) pdl_trigger();
         int n_tile, tx, ty, g;
         my_tile(item, &n_tile, &tx, &ty, &g);
         const int x0 = p.flat ? tx * kBM : tx * p.pw, y0 = ty * p.ph, n0 = g * p.pn;
@@ -1772,14 +1777,31 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   const int tiles_x = p.flat ? (tiles * p.HW + kBM - 1) / kBM : p.tiles_x;
   const int groups = p.flat ? 1 : (tiles + p.pn - 1) / p.pn;
   const long long work = (long long)groups * p.tiles_y * tiles_x * p.n_tiles;
-  const int grid = int(std::min<long long>(work, sm_count()));
+  // balanced grid: the launch takes ceil(work / SMs) rounds whatever the grid, so it only asks for the CTAs that keep every
+  // round full (392 tiles: 131 CTAs x 3 instead of 148 CTAs of which 96 do 3 and 52 do 2) and leaves the other SMs to the
+  // batches in flight beside this one (TOD_TC_BALANCE=0: one CTA per SM)
+  static const int balance_env = std::getenv("TOD_TC_BALANCE") ? std::atoi(std::getenv("TOD_TC_BALANCE")) : 1;
+  // TOD_TC_MINROUNDS (default 2): a launch whose work fits one round still gives every CTA at least this many tiles.  A CTA's
+  // fixed cost (prologue, pipeline fill, last tile's epilogue, drain: ~5 us of an SM that no other convolution CTA can share)
+  // is then paid by half as many CTAs; with batches in flight the freed SMs run the other batches' kernels (3 in flight:
+  // 1.015 -> 0.987 ms per step; one handle alone: 1.153 -> 1.169 ms, the latency side of the trade)
+  static const int min_rounds_env = std::getenv("TOD_TC_MINROUNDS") ? std::max(1, std::atoi(std::getenv("TOD_TC_MINROUNDS"))) : 2;
+  auto balanced = [](long long items, int max_ctas) {
+    const long long full = std::min<long long>(items, max_ctas);
+    if (!balance_env || (items <= max_ctas && min_rounds_env <= 1)) return int(full);
+    const long long rounds = std::max<long long>((items + max_ctas - 1) / max_ctas, min_rounds_env);
+    return int((items + rounds - 1) / rounds);
+  };
+  const int grid = balanced(work, sm_count());
   // eight-warp epilogue when a CTA has only a few tiles (TOD_TC_WIDE: 0 = never, 1 = always, N > 1 = up to N tiles per CTA)
+  static const int late_env = std::getenv("TOD_TC_LATE") ? std::atoi(std::getenv("TOD_TC_LATE")) : 0;  // measured: +0.4 % per pipelined step, -0.6 % single stream
+  p.late_trig = late_env ? 1 : 0;
   static const int wide_env = std::getenv("TOD_TC_WIDE") ? std::atoi(std::getenv("TOD_TC_WIDE")) : -1;
   const int wide_max = wide_env < 0 ? 5 : (wide_env == 1 ? (1 << 30) : wide_env);
   if (c->pair) {
     const long long m_tiles = (long long)groups * p.tiles_y * tiles_x;
     const long long pair_items = ((m_tiles + 1) / 2) * p.n_tiles;
-    const int pairs = int(std::min<long long>(pair_items, sm_count() / 2));
+    const int pairs = balanced(pair_items, sm_count() / 2);
     p.wide = (pair_items + pairs - 1) / pairs <= wide_max ? 1 : 0;
     if (c->mode == 21)
       TOD_CUDA(launch_k(conv_tc_pair_kernel<21>, dim3(2 * pairs), dim3(kTcThreads), c->smem_bytes, s, c->map_a, c->map_bh, c->map_o, p, tiles));

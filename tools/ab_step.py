@@ -16,7 +16,8 @@ from tests import synth  # noqa: E402
 tiles = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 full, _ = synth_model.ensure_models()
-y = tod_b200.Yolact.init(full, max_tiles=tiles)
+OPTS = {k[8:].lower(): int(v) for k, v in os.environ.items() if k.startswith("TOD_OPT_")}  # e.g. TOD_OPT_USE_PDL=0
+y = tod_b200.Yolact.init(full, max_tiles=tiles, **OPTS)
 d = torch.from_numpy(synth.rgb_tiles(tiles)).cuda()
 ts = torch.cuda.Stream()  # events must sit on the stream the library launches on (a NULL stream means the handle's own)
 torch.cuda.set_stream(ts)
@@ -36,7 +37,7 @@ for rep in range(3):
 print("%s: %.4f ms/step (%d tiles, best of 3 x %d)" % (os.environ.get("TOD_B200_LIB", "default"), best, tiles, steps))
 depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 if depth > 1:  # batches in flight, as bench.py's headline: `depth` handles take alternate steps on their own streams
-    ys = [y] + [tod_b200.Yolact.init(full, max_tiles=tiles) for _ in range(depth - 1)]
+    ys = [y] + [tod_b200.Yolact.init(full, max_tiles=tiles, **OPTS) for _ in range(depth - 1)]
     pst = [torch.cuda.Stream() for _ in range(depth)]
     for k in range(4 * depth):
         ys[k % depth].infer_tiles_device(d.data_ptr(), tiles, pst[k % depth].cuda_stream)
