@@ -6,6 +6,7 @@
 #include "post.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -346,6 +347,29 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const 
   return __fdiv_rn(inter, uni) > thresh;
 }
 
+// The scan's form of the same decision, ~15 instructions: with s = area_a + area_b (the rounded sum iou_exceeds uses),
+// inter / (s - inter) > t  <=>  (1 + t) * inter > t * s in the reals; the two sides are compared with a 1e-6 margin (the roundings
+// of either formulation are below 3e-7 relative) and only the sliver in between runs the exact iou_exceeds.
+struct IouTest {
+  float k1, k2_hi, k2_lo, thresh;
+  __device__ __forceinline__ void init(float t) {
+    k1 = __fadd_rn(1.0f, t);
+    k2_hi = __fmul_rn(t, 1.000001f);
+    k2_lo = __fmul_rn(t, 0.999999f);
+    thresh = t;
+  }
+  __device__ __forceinline__ bool exceeds(const float4 a, float area_a, const float4 b, float area_b) const {
+    const float ix = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float iy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    const float inter = __fmul_rn(fmaxf(ix, 0.f), fmaxf(iy, 0.f));
+    const float s = __fadd_rn(area_a, area_b);
+    const float lhs = __fmul_rn(k1, inter);
+    if (lhs < __fmul_rn(k2_lo, s)) return false;   // includes inter == 0 against any positive s
+    if (thresh > 0.f && lhs > __fmul_rn(k2_hi, s) && s > 0.f) return true;
+    return iou_exceeds(a, area_a, b, area_b, thresh);
+  }
+};
+
 // Fast-NMS for one (class, tile): sort the class' candidates, keep top_k, then each warp lane owns a
 // column j of the IoU matrix and scans the rows i < j (upper triangle); survivors are compacted with
 // ballot/popc and appended to the tile's survivor list.
@@ -410,6 +434,8 @@ __device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers&
   // column pairs (q, m - 1 - q), S threads per pair taking interleaved rows
   const int pairs = (m + 1) >> 1;
   const int S = max(1, kNmsThreads / max(pairs, 1));
+  IouTest iou;
+  iou.init(c.nms_thresh);
   for (int u = threadIdx.x; u < pairs * S; u += kNmsThreads) {
     const int q = u % pairs, sub = u / pairs;
     const int ja = q, jb = m - 1 - q;
@@ -417,14 +443,14 @@ __device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers&
       const float4 bj = s_box[jb];
       const float aj = s_area[jb];
       bool sup = false;
-      for (int i = sub; i < jb && !sup; i += S) sup = iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
+      for (int i = sub; i < jb && !sup; i += S) sup = iou.exceeds(s_box[i], s_area[i], bj, aj);
       if (sup) s_sup[jb] = 1;
     }
     if (ja != jb) {
       const float4 bj = s_box[ja];
       const float aj = s_area[ja];
       bool sup = false;
-      for (int i = S - 1 - sub; i < ja && !sup; i += S) sup = iou_exceeds(s_box[i], s_area[i], bj, aj, c.nms_thresh);
+      for (int i = S - 1 - sub; i < ja && !sup; i += S) sup = iou.exceeds(s_box[i], s_area[i], bj, aj);
       if (sup) s_sup[ja] = 1;
     }
   }
@@ -449,7 +475,7 @@ __device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers&
 
 // Fast-NMS, one CTA per (class, tile) whose list has at most n_hi candidates (8 KB of shared memory: the whole grid is
 // resident at once).  Longer lists belong to nms_long_kernel.
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_hi) {
+__global__ void __launch_bounds__(kNmsThreads, 8) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_hi) {
   extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k], int suppressed[top_k]
   const int k = blockIdx.x, t = blockIdx.y;
   const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
@@ -776,8 +802,13 @@ int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_
                         int64_t box_ts, int tiles, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   TOD_CUDA(cudaMemsetAsync(b.cand_count, 0, sizeof(int) * size_t(tiles) * (c.C - 1), s));
   TOD_CUDA(cudaMemsetAsync(b.surv_count, 0, sizeof(int) * size_t(tiles), s));
+  static const int diag_skip = std::getenv("TOD_DIAG_SKIP") ? std::atoi(std::getenv("TOD_DIAG_SKIP")) : 0;  // timing attribution only
   dim3 g1((c.P + kDecodeThreads - 1) / kDecodeThreads, tiles);
-  decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
+  if (!(diag_skip & 128)) decode_kernel<<<g1, kDecodeThreads, size_t(kDecodeThreads) * c.C, s>>>(c, b, cls, cls_ts, box, box_ts);
+  if (diag_skip & 64) {
+    select_kernel<<<tiles, kSelThreads, detect_select_smem(c), s>>>(c, b, next_pow2((c.C - 1) * c.top_k));
+    return TOD_OK;
+  }
   dim3 g2(c.C - 1, tiles);
   const int small_cap = std::min(kNmsSmall, next_pow2(c.P));
   // the two NMS launches touch disjoint (class, tile) lists; the worst-case one is a handful of long CTAs (latency-bound)
@@ -803,6 +834,8 @@ int launch_detect_boxes(const DetectCfg& c, const DetectBuffers& b, const uint8_
 
 int launch_detect_masks(const DetectCfg& c, const DetectBuffers& b, const uint8_t* coef, int64_t coef_ts, const uint8_t* proto,
                         int64_t proto_ts, int tiles, cudaStream_t s) {
+  static const int diag_skip = std::getenv("TOD_DIAG_SKIP") ? std::atoi(std::getenv("TOD_DIAG_SKIP")) : 0;
+  if (diag_skip & 32) return TOD_OK;
   dim3 g4((c.ph * c.pw + kMaskThreads - 1) / kMaskThreads, tiles);
   mask_kernel<32><<<g4, kMaskThreads, mask_smem(c), s>>>(c, b, coef, coef_ts, proto, proto_ts);
   TOD_CUDA(cudaGetLastError());
