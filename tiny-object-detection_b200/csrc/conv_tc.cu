@@ -574,10 +574,21 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const int4*
 // linear staging, one 1-D bulk store per tile).  ncu on the 112x112 32 -> 96 layer showed the epilogue warps spending as
 // many stall samples in the ~200 instructions of per-tile bookkeeping of the general path (work decode, border class,
 // patch coordinates, run set-up, pass loop) as in the six 16-column chunks themselves; here a tile costs a handful.
-template <uint32_t MODE, bool DIAG = false, bool FL = false>
-__global__ void __launch_bounds__(kFastThreads, 1)
-conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
+// OCT > 0 (flat-linear ReLU layers only): the layer's output channel count at compile time and its per-channel requantisation
+// constants as a kernel parameter (FlTab, constant bank).  With the chunk loop fully unrolled every constant is a
+// constant-bank operand of the multiply-add / shift itself: no table loads on the shared-memory pipe, which - with the
+// accumulator read - is what bounds these layers (~600 of the ~1100 wavefronts per 128 x 96 tile were
+// the broadcast loads of the constants).
+constexpr int kFlTabMax = 192;
+struct FlTab {
+  long long a64[kFlTabMax];  // bias * q + 2^30 + halfp * 2^31 (fixedpoint.cuh::relu_addend)
+  int32_t q[kFlTabMax];
+  uint8_t rs1[kFlTabMax];    // right shift - 1 (bytes: the whole parameter block stays below 4 KB)
+};
+
+template <uint32_t MODE, bool DIAG, bool FL, int OCT>
+__device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_o, const TcParams& p,
+                                                  const int tiles, const FlTab* tab) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible to the compiler
   uint8_t* smem_a = smem;
@@ -612,9 +623,11 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   // epilogue tables -> shared memory with 16-byte loads, all of a thread's loads in flight at once (a 3x3 ReLU layer's
   // nine border classes are 18 KB: the word-by-word loop was twelve dependent round trips of prologue per CTA)
-  copy_table16(s_qtab, p.qtab, p.OCp, kFastThreads);
-  if (MODE & kEpiRelu) copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.a64tab), p.ncls * p.OCp / 2, kFastThreads);
-  else copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.b2tab), p.ncls * p.OCp / 4, kFastThreads);
+  if constexpr (OCT == 0) {
+    copy_table16(s_qtab, p.qtab, p.OCp, kFastThreads);
+    if (MODE & kEpiRelu) copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.a64tab), p.ncls * p.OCp / 2, kFastThreads);
+    else copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.b2tab), p.ncls * p.OCp / 4, kFastThreads);
+  }
   if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
   if (MODE & kEpiAdd)
     for (int i = threadIdx.x; i < 512; i += kFastThreads) ctl->add_tab[i] = p.add_tab[i];
@@ -760,7 +773,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t chunk0 = uint32_t(((warp - 4) % wpg) >> 2) * 16u, cstep = uint32_t(4 * wpg);
     const int r = ew * 32 + lane;
     const int eg = threadIdx.x - 128 - grp * gthreads;
-    const uint32_t oc = uint32_t(p.OC);
+    const uint32_t oc = OCT > 0 ? uint32_t(OCT) : uint32_t(p.OC);
     const uint32_t buf_bytes = uint32_t(kBM) * oc;
     uint8_t* grp_buf = stage_buf + size_t(grp) * (p.stage_bytes / uint32_t(kAccStages));
     const uint32_t taddr0 = tmem_base + (uint32_t(ew * 32) << 16);
@@ -781,6 +794,35 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint8_t* srow = sbuf + uint32_t(r) * oc;
       mbar_wait(&ctl->acc_full[as], (uint32_t(it) / uint32_t(kAccStages)) & 1u);
       tc_fence_after();
+      if constexpr (OCT > 0) {
+        static_assert(OCT % 16 == 0 && OCT <= kFlTabMax, "flat-linear constant table");
+        static_assert((MODE & kEpiRelu) && !(MODE & (kEpiAdd | kEpiLut)), "constant-table epilogue: ReLU form only");
+#pragma unroll
+        for (int ch = 0; ch < OCT / 16; ++ch) {
+          if (cstep == 32u && uint32_t(ch & 1) * 16u != chunk0) continue;  // wide mode: the lane quarter's other warp takes this chunk
+          uint32_t v[16];
+          tmem_ld16(taddr + uint32_t(ch * 16), v);
+          tmem_wait_ld();
+          uint32_t packed[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = ch * 16 + q4 * 4 + j;
+              o[j] = int((static_cast<long long>(int(v[4 * q4 + j])) * tab->q[col] + tab->a64[col]) >> 32) >> int(tab->rs1[col]);
+            }
+            if (MODE & kEpiSat) {
+              packed[q4] = pack_sat_s8(o[1], o[0], pack_sat_s8(o[3], o[2], 0u));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = max(p.act_min, min(p.act_max, o[j]));
+              packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
+            }
+          }
+          *reinterpret_cast<uint4*>(srow + ch * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+      } else {
       for (uint32_t c0 = chunk0; c0 < oc; c0 += cstep) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -791,6 +833,7 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int4* kq = (MODE & kEpiRelu) ? reinterpret_cast<const int4*>(reinterpret_cast<const int2*>(s_qtab) + c0) : s_qtab + c0;
         epi_chunk16<MODE>(v, kq, bq0 + (c0 >> 2), aq0 + (c0 >> 1), rres, ctl, p, packed);
         *reinterpret_cast<uint4*>(srow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
       }
       tc_fence_before();   // accumulator fully read: hand the TMEM stage back before the store
       __syncwarp();
@@ -988,6 +1031,20 @@ conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
+}
+
+template <uint32_t MODE, bool DIAG = false, bool FL = false>
+__global__ void __launch_bounds__(kFastThreads, 1)
+conv_tc_fast_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles) {
+  conv_tc_fast_body<MODE, DIAG, FL, 0>(map_a, map_b, map_o, p, tiles, nullptr);
+}
+
+template <uint32_t MODE, int OCT>
+__global__ void __launch_bounds__(kFastThreads, 1)
+conv_tc_flc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_o, const TcParams p, const int tiles, const __grid_constant__ FlTab tab) {
+  conv_tc_fast_body<MODE, false, true, OCT>(map_a, map_b, map_o, p, tiles, &tab);
 }
 
 // ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
@@ -1351,6 +1408,8 @@ struct ConvTc {
   int max_tiles = 0;
   int fast = 0;        // conv_tc_fast_kernel is eligible
   uint32_t mode = 0;   // kEpi* bits
+  int fl_oct = 0;      // conv_tc_flc_kernel<mode, fl_oct>: per-channel constants as a kernel parameter (0 = not eligible)
+  FlTab fl_tab{};
 };
 
 bool conv_tc_supported(const ConvGeom& g, int64_t in_ts, const void* in, const void* w) {
@@ -1646,6 +1705,16 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
             a64[(yi * xmasks.size() + xi) * p.OCp + oc] = (long long)src[oc] * a.h_mult[oc] + (1ll << 30) + halfp * (1ll << 31);
           }
       }
+    static const int flc_env = std::getenv("TOD_TC_FLC") ? std::atoi(std::getenv("TOD_TC_FLC")) : 1;
+    if (relu_mode && p.flat && p.lin && p.n_tiles == 1 && p.ncls == 1 && !(c->mode & (kEpiAdd | kEpiLut)) && flc_env &&
+        (g.OC == 96 || g.OC == 144 || g.OC == 192)) {
+      c->fl_oct = g.OC;
+      for (int oc = 0; oc < g.OC; ++oc) {
+        c->fl_tab.a64[oc] = a64[oc];
+        c->fl_tab.q[oc] = a.h_mult[oc];
+        c->fl_tab.rs1[oc] = uint8_t(-a.h_shift[oc] - 1);
+      }
+    }
     if (relu_mode) {
       if ((ce = cudaMalloc(&c->d_a64, a64.size() * 8)) != cudaSuccess) return bail(fail(TOD_ERR_CUDA, "conv_tc: cudaMalloc: %s", cudaGetErrorString(ce)));
       cudaMemcpy(c->d_a64, a64.data(), a64.size() * 8, cudaMemcpyHostToDevice);
@@ -1751,6 +1820,8 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
                              (const void*)conv_tc_fast_kernel<4, false, true>, (const void*)conv_tc_fast_kernel<5, false, true>,
                              (const void*)conv_tc_fast_kernel<12, false, true>, (const void*)conv_tc_fast_kernel<13, false, true>,
                              (const void*)conv_tc_fast_kernel<20, false, true>, (const void*)conv_tc_fast_kernel<21, false, true>,
+                             (const void*)conv_tc_flc_kernel<20, 96>, (const void*)conv_tc_flc_kernel<20, 144>, (const void*)conv_tc_flc_kernel<20, 192>,
+                             (const void*)conv_tc_flc_kernel<21, 96>, (const void*)conv_tc_flc_kernel<21, 144>, (const void*)conv_tc_flc_kernel<21, 192>,
                              (const void*)conv_tc_pair_kernel<20>, (const void*)conv_tc_pair_kernel<21>,
                              (const void*)conv_tc_fast_kernel<3, true>, (const void*)conv_tc_fast_kernel<5, true>,
                              (const void*)conv_tc_pair_kernel<4>, (const void*)conv_tc_pair_kernel<5>};
@@ -1824,6 +1895,11 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
       return TOD_OK;
     }
     static const int fl_env = std::getenv("TOD_TC_FL") ? std::atoi(std::getenv("TOD_TC_FL")) : -1;
+    if (c->fl_oct && fl_env != 0) {
+#define TOD_TC_FLC(M, O) if (c->mode == M && c->fl_oct == O) { TOD_CUDA(launch_k(conv_tc_flc_kernel<M, O>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles, c->fl_tab)); TOD_CUDA(cudaGetLastError()); return TOD_OK; }
+      TOD_TC_FLC(20, 96) TOD_TC_FLC(20, 144) TOD_TC_FLC(20, 192) TOD_TC_FLC(21, 96) TOD_TC_FLC(21, 144) TOD_TC_FLC(21, 192)
+#undef TOD_TC_FLC
+    }
     if (p.flat && p.lin && p.n_tiles == 1 && fl_env != 0) {
       switch (c->mode) {
 #define TOD_TC_FL(M) case M: TOD_CUDA(launch_k(conv_tc_fast_kernel<M, false, true>, dim3(grid), dim3(kFastThreads), c->smem_bytes, s, c->map_a, c->map_b, c->map_o, p, tiles)); TOD_CUDA(cudaGetLastError()); return TOD_OK;
