@@ -149,6 +149,7 @@ using namespace tod;
 
 struct tod_yolact {
   int device = 0;
+  int diag_skip = 0;   // TOD_DIAG_SKIP at creation: step classes left out of the pipeline (timing attribution; bench.py's conv-only leg)
   tod_yolact_options opt{};
   Graph graph;
   std::vector<Step> steps;
@@ -905,7 +906,7 @@ int run_step(tod_yolact* y, const Step& st, int n, cudaStream_t s) {
   const Place& po = st.out_moved ? st.out_place : y->place[st.out];
   // TOD_DIAG_SKIP (timing attribution only, results are garbage): 1 = no depthwise, 2 = no resize, 4 = no tcgen05 convs, 8 = no detection tail,
   // 16 = no stem / direct conv
-  static const int diag_skip = std::getenv("TOD_DIAG_SKIP") ? std::atoi(std::getenv("TOD_DIAG_SKIP")) : 0;
+  const int diag_skip = y->diag_skip;  // read from the environment when the handle is created
   if (diag_skip) {
     if ((diag_skip & 1) && st.kind == kStepDepthwise) return TOD_OK;
     if ((diag_skip & 2) && st.kind == kStepResize) return TOD_OK;
@@ -1490,6 +1491,7 @@ int tod_yolact_create(const char* tflite_path, int device, const tod_yolact_opti
       raw->seg_out = 4;
   }
   const size_t mt = size_t(o.max_tiles);
+  raw->diag_skip = std::getenv("TOD_DIAG_SKIP") ? std::atoi(std::getenv("TOD_DIAG_SKIP")) : 0;
   raw->spin_sync = std::getenv("TOD_SPIN_SYNC") && std::atoi(std::getenv("TOD_SPIN_SYNC")) != 0;
   if ((ce = cudaEventCreateWithFlags(&raw->caller_done, cudaEventDisableTiming)) != cudaSuccess ||
       (ce = cudaEventCreateWithFlags(&raw->done_ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess ||
@@ -1560,7 +1562,7 @@ int tod_yolact_infer_tiles_device(tod_yolact* y, const uint8_t* d_rgb_tiles, int
   const Place& pin = y->place[y->graph.inputs[0]];
   TOD_CUDA(cudaMemcpy2DAsync(pin.base, size_t(pin.tile_stride), d_rgb_tiles, size_t(pin.bytes), size_t(pin.bytes), size_t(n),
                              cudaMemcpyDeviceToDevice, s));
-  static const bool diag_nodets = std::getenv("TOD_DIAG_SKIP") && (std::atoi(std::getenv("TOD_DIAG_SKIP")) & 8);
+  const bool diag_nodets = (y->diag_skip & 8) != 0;
   const bool dets = y->det_ready && y->have_priors && !diag_nodets;
   y->last_mask_mode = dets ? 2 : 0;
   TOD_TRY(run_pipeline(y, n, dets, dets ? 2 : 0, s));
