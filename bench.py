@@ -631,7 +631,8 @@ def main():
             del y4, sb4, o_w, o_c0, o_c1, o_map, work
             # end to end behind the C ABI: tod_pool_rgbd_batch on this rank's GPU (3 handles, chunks of 32 frames), host frames + depth in,
             # classified frames + map + world + conn0 + conn1 out
-            pool = tod_b200.Pool(full, devices=[local_rank], depth=3, max_tiles=64)
+            pool_depth = 4
+            pool = tod_b200.Pool(full, devices=[local_rank], depth=pool_depth, max_tiles=64)
             pn = 192
             sp = tod_b200.default_params(width=W4, height=H4)
             pf = torch.from_numpy(np.tile(synth.rgb_frames(8, W=W4, H=H4, seed=5 + rank), (pn // 8, 1)).view(np.int32)).pin_memory()
@@ -646,7 +647,7 @@ def main():
             es = host_timed(rgbd_e2e, 3, warm=1)
             line["fused_rgbd"]["e2e"] = {"value": world * pn * 3 / es, "unit": "frames/s", "h2d_bytes_per_step": int(pn * W4 * H4 * 6),
                                          "d2h_bytes_per_step": int(pn * W4 * H4 * (4 + 52)),
-                                         "call": "tod_pool_rgbd_batch: 192 host frames + depth per call, 3 handles behind the C ABI; 4.3 MB of read-back per frame (PCIe-bound)"}
+                                         "call": "tod_pool_rgbd_batch: 192 host frames + depth per call, %d handles behind the C ABI; 4.3 MB of read-back per frame (PCIe-bound)" % pool_depth}
             # the reference's own call: Yolact::classify on 640x480 frames, in place, host buffer (yolact.rs:39)
             cn = 96
             cf = torch.from_numpy(np.tile(synth.rgb_frames(8, seed=5 + rank), (cn // 8, 1)).view(np.int32)).pin_memory()
@@ -656,10 +657,10 @@ def main():
 
             es = host_timed(classify_e2e, 3, warm=1)
             line["classify_e2e"] = {"value": world * cn * 3 / es, "unit": "frames/s", "h2d_bytes_per_step": int(cn * 640 * 480 * 4), "d2h_bytes_per_step": int(cn * 640 * 480 * 4),
-                                    "call": "tod_pool_classify_batch: 96 frames of 640x480 u32 per call, classified in place (Yolact::classify for every frame), 3 handles behind the C ABI"}
+                                    "call": "tod_pool_classify_batch: 96 frames of 640x480 u32 per call, classified in place (Yolact::classify for every frame), %d handles behind the C ABI" % pool_depth}
             # one synchronous caller, tiles: the pooled form of tod_yolact_infer_tiles_cells
-            tn = 3 * n
-            pt = torch.from_numpy(np.tile(synth.rgb_tiles(n, seed=2 + rank), (3, 1, 1, 1))).pin_memory()
+            tn = 8 * n
+            pt = torch.from_numpy(np.tile(synth.rgb_tiles(n, seed=2 + rank), (8, 1, 1, 1))).pin_memory()
             pdet, pkeep = y._alloc_dets(tn, True)
             ppin = {}
             for kk in ("count", "boxes", "scores", "classes", "priors", "masks_bits"):
@@ -673,10 +674,10 @@ def main():
             def pool_tiles():
                 tod_b200._lib.check(lib.tod_pool_infer_tiles(pool._h, pt.data_ptr(), tn, None, None, pcells.data_ptr(), C.byref(pdet)))
 
-            reps = max(3, args.steps // 3)
+            reps = max(3, args.steps // 8)
             es = host_timed(pool_tiles, reps, warm=2)
             line["e2e"]["one_caller"] = {"value": world * (tn // TILES_PER_FRAME) * reps / es, "unit": "frames/s",
-                                         "call": "tod_pool_infer_tiles: %d tiles per blocking call, the library's own 3 handles / host threads (no Python threads)" % tn}
+                                         "call": "tod_pool_infer_tiles: %d tiles per blocking call, the library's own %d handles / host threads (no Python threads)" % (tn, pool_depth)}
             del pool
         except Exception as e:  # never let the side measurement break the headline line
             line.setdefault("fused_rgbd", {})["error"] = str(e)[:200]
