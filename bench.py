@@ -315,9 +315,10 @@ def main():
     depth = max(1, args.pipeline)
     if depth > 1:
         import threading
-        ys = [y] + [tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl) for _ in range(depth - 1)]
+        # handles that share the GPU say so (tod_yolact_options::batches_in_flight): their convolution launches give up SMs to each other
+        ys = [tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl, batches_in_flight=depth) for _ in range(depth)]
         pstreams = [torch.cuda.Stream() for _ in range(depth)]
-        ptiles = [tiles_d] + [torch.from_numpy(synth.rgb_tiles(n, seed=100 + 7 * k + rank)).cuda() for k in range(1, depth)]
+        ptiles = [tiles_d] + [torch.from_numpy(synth.rgb_tiles(n, seed=100 + 7 * k + rank)).cuda() for k in range(1, depth)]  # ys[0] runs the golden input
 
         def pstep(k):
             h = k % depth
@@ -344,6 +345,11 @@ def main():
         barrier()
         ms = pms
         value = world * frames_per_step * args.steps / (pms * 1e-3)
+        # the bytes of the headline region: ys[0] ran the golden input in every one of its timed steps
+        check_single = check
+        check = self_check(tod_b200, ys[0], full, n, rank, world, timed_is_golden_input=(n == 64))
+        check["single_stream_ok"] = bool(check_single.get("ok"))
+        barrier()
 
         # sustained side figure: the same pipelined steps for >= 2 s under its own clock / power record (the headline region is
         # only steps x ~1 ms long)
@@ -374,7 +380,7 @@ def main():
         # end to end: one host thread per handle, each with its own pinned buffers
         e2e_depth = max(depth, args.e2e_pipeline)
         for k in range(depth, e2e_depth):
-            ys.append(tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl))
+            ys.append(tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl, batches_in_flight=e2e_depth))
             ptiles.append(torch.from_numpy(synth.rgb_tiles(n, seed=100 + 7 * k + rank)).cuda())
         ctx = []
         for h in range(e2e_depth):
@@ -445,7 +451,7 @@ def main():
     conc_ms = None
     try:
         os.environ["TOD_DIAG_SKIP"] = "27"
-        cys = [tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl) for _ in range(depth)]
+        cys = [tod_b200.Yolact.init(full, device=local_rank, max_tiles=n, conv_impl=args.conv_impl, batches_in_flight=depth) for _ in range(depth)]
     finally:
         os.environ.pop("TOD_DIAG_SKIP", None)
     cstreams = [torch.cuda.Stream() for _ in range(depth)]

@@ -54,6 +54,7 @@ pub mod sys {
         pub conv_impl: i32,
         pub fusion: i32,
         pub use_pdl: i32,
+        pub batches_in_flight: i32,
     }
 
     extern "C" {

@@ -48,7 +48,7 @@ class SceneParams(C.Structure):
 class YolactOptions(C.Structure):
     _fields_ = [("max_tiles", C.c_int32), ("id_mode", C.c_int32), ("conf_thresh", C.c_float), ("nms_thresh", C.c_float),
                 ("top_k", C.c_int32), ("max_dets", C.c_int32), ("use_cuda_graph", C.c_int32), ("conv_impl", C.c_int32),
-                ("fusion", C.c_int32), ("use_pdl", C.c_int32)]
+                ("fusion", C.c_int32), ("use_pdl", C.c_int32), ("batches_in_flight", C.c_int32)]
 
 
 class Detections(C.Structure):

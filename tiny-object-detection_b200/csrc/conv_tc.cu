@@ -1408,6 +1408,7 @@ struct ConvTc {
   int max_tiles = 0;
   int fast = 0;        // conv_tc_fast_kernel is eligible
   uint32_t mode = 0;   // kEpi* bits
+  int min_rounds = 1;  // ConvTcArgs::min_rounds
   int fl_oct = 0;      // conv_tc_flc_kernel<mode, fl_oct>: per-channel constants as a kernel parameter (0 = not eligible)
   FlTab fl_tab{};
 };
@@ -1445,6 +1446,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   };
   TcParams& p = c->p;
   c->max_tiles = a.max_tiles;
+  c->min_rounds = a.min_rounds;
   p.OC = g.OC;
   p.KH = g.KH;
   p.KW = g.KW;
@@ -1852,15 +1854,17 @@ int conv_tc_launch(ConvTc* c, int tiles, cudaStream_t s) {
   // round full (392 tiles: 131 CTAs x 3 instead of 148 CTAs of which 96 do 3 and 52 do 2) and leaves the other SMs to the
   // batches in flight beside this one (TOD_TC_BALANCE=0: one CTA per SM)
   static const int balance_env = std::getenv("TOD_TC_BALANCE") ? std::atoi(std::getenv("TOD_TC_BALANCE")) : 1;
-  // TOD_TC_MINROUNDS (default 2): a launch whose work fits one round still gives every CTA at least this many tiles.  A CTA's
-  // fixed cost (prologue, pipeline fill, last tile's epilogue, drain: ~5 us of an SM that no other convolution CTA can share)
-  // is then paid by half as many CTAs; with batches in flight the freed SMs run the other batches' kernels (3 in flight:
-  // 1.015 -> 0.987 ms per step; one handle alone: 1.153 -> 1.169 ms, the latency side of the trade)
-  static const int min_rounds_env = std::getenv("TOD_TC_MINROUNDS") ? std::max(1, std::atoi(std::getenv("TOD_TC_MINROUNDS"))) : 2;
-  auto balanced = [](long long items, int max_ctas) {
+  // Tiles per CTA at least (ConvTcArgs::min_rounds <- tod_yolact_options::batches_in_flight; TOD_TC_MINROUNDS overrides): a launch
+  // whose work fits one round still gives every CTA this many tiles.  A CTA's fixed cost (prologue, pipeline fill, last tile's
+  // epilogue, drain: ~5 us of an SM that no other convolution CTA can share) is then paid by half as many CTAs; with batches in
+  // flight the freed SMs run the other batches' kernels (3 in flight: 1.015 -> 0.987 ms per step; one handle alone: 1.153 ->
+  // 1.169 ms, which is why a handle that has the GPU to itself keeps one tile per CTA)
+  static const int min_rounds_env = std::getenv("TOD_TC_MINROUNDS") ? std::max(1, std::atoi(std::getenv("TOD_TC_MINROUNDS"))) : 0;
+  const int min_rounds = min_rounds_env ? min_rounds_env : std::max(1, c->min_rounds);
+  auto balanced = [min_rounds](long long items, int max_ctas) {
     const long long full = std::min<long long>(items, max_ctas);
-    if (!balance_env || (items <= max_ctas && min_rounds_env <= 1)) return int(full);
-    const long long rounds = std::max<long long>((items + max_ctas - 1) / max_ctas, min_rounds_env);
+    if (!balance_env || (items <= max_ctas && min_rounds <= 1)) return int(full);
+    const long long rounds = std::max<long long>((items + max_ctas - 1) / max_ctas, min_rounds);
     return int((items + rounds - 1) / rounds);
   };
   const int grid = balanced(work, sm_count());

@@ -39,6 +39,7 @@ struct ConvTcArgs {
   const int32_t* h_shift = nullptr;  // (null: general epilogue)
   int fast_epilogue = 1;             // 0 forces the general epilogue (cross-check)
   const ConvTcAdd* add = nullptr;    // fused ADD (requires the fast epilogue + TMA-storable output)
+  int min_rounds = 1;                // tiles per CTA a launch gives at least (tod_yolact_options::batches_in_flight >= 2: two)
 };
 
 // shape / alignment test only (no CUDA calls)

@@ -191,6 +191,7 @@ int tod_pool_create(const char* tflite_path, const int32_t* devices, int n_devic
   tod_yolact_options o;
   tod_yolact_default_options(&o);
   if (opts) o = *opts;
+  if (!opts || o.batches_in_flight < depth) o.batches_in_flight = depth;  // the pool's handles share their GPU
   tod_pool* p = new tod_pool();
   if (n_devices <= 0)   // every visible device
     for (int d = 0; d < avail; ++d) p->devices.push_back(d);

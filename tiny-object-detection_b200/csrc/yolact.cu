@@ -859,6 +859,7 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
       continue;
     }
     ConvTcArgs a{};
+    a.min_rounds = y->opt.batches_in_flight >= 2 ? 2 : 1;
     a.g = st.g;
     a.in = reinterpret_cast<const int8_t*>(pi.base);
     a.in_tile_stride = pi.tile_stride;
@@ -1396,6 +1397,7 @@ void tod_yolact_default_options(tod_yolact_options* o) {
   o->conv_impl = 0;
   o->fusion = 1;
   o->use_pdl = 1;
+  o->batches_in_flight = 1;
 }
 
 int tod_model_inspect(const char* tflite_path, int32_t* num_ops, int32_t* num_tensors, int64_t* macs) {

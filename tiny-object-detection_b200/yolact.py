@@ -223,6 +223,7 @@ class YolactPool:
 
     def __init__(self, model_path=DEFAULT_MODEL, device=0, depth=3, **options):
         from concurrent.futures import ThreadPoolExecutor
+        options.setdefault("batches_in_flight", max(1, depth))  # the handles share the GPU (tod_yolact_options::batches_in_flight)
         self.handles = [Yolact(model_path, device, **options) for _ in range(max(1, depth))]
         self._workers = [ThreadPoolExecutor(1) for _ in self.handles]  # one thread per handle: a handle runs one batch at a time
         self._next = 0

@@ -37,7 +37,10 @@ for rep in range(3):
 print("%s: %.4f ms/step (%d tiles, best of 3 x %d)" % (os.environ.get("TOD_B200_LIB", "default"), best, tiles, steps))
 depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 if depth > 1:  # batches in flight, as bench.py's headline: `depth` handles take alternate steps on their own streams
-    ys = [y] + [tod_b200.Yolact.init(full, max_tiles=tiles, **OPTS) for _ in range(depth - 1)]
+    y.close()
+    popts = dict(OPTS)
+    popts.setdefault("batches_in_flight", depth)
+    ys = [tod_b200.Yolact.init(full, max_tiles=tiles, **popts) for _ in range(depth)]
     pst = [torch.cuda.Stream() for _ in range(depth)]
     for k in range(4 * depth):
         ys[k % depth].infer_tiles_device(d.data_ptr(), tiles, pst[k % depth].cuda_stream)
@@ -56,6 +59,7 @@ if depth > 1:  # batches in flight, as bench.py's headline: `depth` handles take
         torch.cuda.synchronize()
         pbest = min(pbest, e0.elapsed_time(e1) / steps)
     print("%s: %.4f ms/step with %d batches in flight" % (os.environ.get("TOD_B200_LIB", "default"), pbest, depth))
-    for yy in ys[1:]:
+    for yy in ys:
         yy.close()
-y.close()
+else:
+    y.close()
