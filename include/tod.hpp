@@ -71,6 +71,7 @@ class YolactPool {
     tod_yolact_options o;
     tod_yolact_default_options(&o);
     o.max_tiles = max_tiles;
+    o.batches_in_flight = depth < 1 ? 1 : depth;  // the handles share the GPU: convolution launches sized for throughput
     for (int i = 0; i < (depth < 1 ? 1 : depth); ++i) {
       slots_.emplace_back(new Slot());
       expect(tod_yolact_create(model, device, &o, &slots_.back()->h), "YolactPool");
