@@ -84,6 +84,11 @@ struct TcParams {
   int wide;                    // epilogue: 1 = all eight warps convert every tile (two warps per TMEM lane quarter take alternate 16-column
                                // chunks; tiles alternate accumulator stages), 0 = two groups of four warps take alternate tiles.  Chosen per
                                // launch: with 1 - 3 tiles per CTA the last tile's epilogue is the CTA's tail, and eight warps halve it
+  int OCm;                     // accumulator columns to convert (== OC, or OC + one 16-column chunk of a sibling layer's channels)
+  int x_c0, x_cols;            // sibling output: its chunk's first column (== OC) and its real channel count (0 = none)
+  int8_t* x_out;               // [tile][Hd][Wd][x_cols]
+  long long x_out_ts;
+  const uint8_t* x_lut;        // sibling byte map (kEpiLut; null = the conv's own map is not applied to the sibling either)
   int late_trig;               // 1 = griddepcontrol.launch_dependents when the CTA starts its LAST work item (the dependent grid's CTAs then
                                // wait one tile on their SMs, not the whole launch), 0 = at kernel start
   int lin;                     // fast kernel, TMA mode: tile rows are contiguous in global memory, staged linearly, one 1-D bulk store
@@ -224,6 +229,7 @@ struct SmemCtl {
   uint64_t b_full;   // resident weights have landed (TcParams::b_res)
   uint32_t tmem_base;
   uint8_t lut[256];
+  uint8_t lut2[256];           // sibling output's byte map
   int32_t add_tab[512];
 };
 
@@ -519,7 +525,8 @@ __device__ __forceinline__ WorkItem decode_work(int work, int n_tiles, int tiles
 // kq / bq / aq point at this chunk's per-channel constants in shared memory (every load is base + immediate).
 template <uint32_t MODE>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const int4* kq, const int4* bq, const longlong2* aq, const uint4& rres,
-                                            const SmemCtl* ctl, const TcParams& p, uint32_t (&packed)[4]) {
+                                            const SmemCtl* ctl, const TcParams& p, uint32_t (&packed)[4], const uint8_t* lut = nullptr) {
+  if (!lut) lut = ctl->lut;
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
     int o[4];
@@ -561,7 +568,7 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], const int4*
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         o[j] = max(p.act_min, min(p.act_max, o[j]));
-        if (MODE & kEpiLut) o[j] = ctl->lut[o[j] & 0xFF];
+        if (MODE & kEpiLut) o[j] = lut[o[j] & 0xFF];
       }
       packed[q4] = (uint32_t(o[0]) & 0xFFu) | ((uint32_t(o[1]) & 0xFFu) << 8) | ((uint32_t(o[2]) & 0xFFu) << 16) | (uint32_t(o[3]) << 24);
     }
@@ -628,7 +635,10 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
     if (MODE & kEpiRelu) copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.a64tab), p.ncls * p.OCp / 2, kFastThreads);
     else copy_table16(reinterpret_cast<int4*>(s_b2), reinterpret_cast<const int4*>(p.b2tab), p.ncls * p.OCp / 4, kFastThreads);
   }
-  if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
+  if ((MODE & kEpiLut) && threadIdx.x >= 128 && threadIdx.x < 384) {
+    ctl->lut[threadIdx.x - 128] = p.post_lut[threadIdx.x - 128];
+    if (p.x_cols) ctl->lut2[threadIdx.x - 128] = p.x_lut ? p.x_lut[threadIdx.x - 128] : uint8_t(threadIdx.x - 128);
+  }
   if (MODE & kEpiAdd)
     for (int i = threadIdx.x; i < 512; i += kFastThreads) ctl->add_tab[i] = p.add_tab[i];
   if (warp == 2) {
@@ -911,8 +921,13 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
       const int4* b2row = reinterpret_cast<const int4*>(s_b2 + size_t(cls) * p.OCp + ocb);
       const longlong2* a2row = reinterpret_cast<const longlong2*>(s_a64 + size_t(cls) * p.OCp + ocb);
       const int4* qrow = s_qtab + ocb;
-      const int ncols_tile = min(p.BN, p.OC - ocb);   // real output channels of this N tile
+      const int ncols_tile = min(p.BN, p.OCm - ocb);  // accumulator columns of this N tile that hold channels (a sibling's chunk included)
       uint32_t soff = 0;  // manual mode: this row's byte offset inside the group's staging buffer
+      int8_t* xrow = nullptr;                         // this pixel's bytes in the sibling output (TMA mode only)
+      if ((MODE & kEpiTma) && p.x_cols) {
+        const bool valid = r < p.rows && x < Wd && yy < p.Hd && (p.flat || n < tiles);
+        if (valid) xrow = p.x_out + (p.flat ? 0ll : (long long)n * p.x_out_ts) + ((long long)yy * Wd + x) * p.x_cols;
+      }
       if (!(MODE & kEpiTma)) {
         // a run = one patch row; patches as wide as the image (run_w = pw * ph) are contiguous across their rows too
         const int x0 = w.tx * p.pw;
@@ -961,7 +976,15 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
           const int4* bq = b2row + ((pass0 + c0) >> 2);  // chunk bases: every table load below is base + immediate
           const int4* kq = (MODE & kEpiRelu) ? reinterpret_cast<const int4*>(reinterpret_cast<const int2*>(s_qtab) + ocb + pass0 + c0) : qrow + (pass0 + c0);
           const longlong2* aq = a2row + ((pass0 + c0) >> 1);
-          epi_chunk16<MODE>(v, kq, bq, aq, rres, ctl, p, packed);
+          const bool sibling = (MODE & kEpiTma) && p.x_cols && pass0 + c0 == p.x_c0;
+          epi_chunk16<MODE>(v, kq, bq, aq, rres, ctl, p, packed, sibling ? ctl->lut2 : nullptr);
+          if (sibling) {   // the sibling layer's bytes of this pixel leave straight from the registers (x_cols <= 16, 4-byte rows)
+            if (xrow) {
+#pragma unroll
+              for (int wq = 0; wq < 4; ++wq)
+                if (4 * wq < p.x_cols) reinterpret_cast<uint32_t*>(xrow)[wq] = packed[wq];
+            }
+          }
           if (MODE & kEpiTma) {
             uint32_t off = row_base + uint32_t(c0);
             off ^= ((off >> 7) & swz_mask) << 4;
@@ -1447,7 +1470,17 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   TcParams& p = c->p;
   c->max_tiles = a.max_tiles;
   c->min_rounds = a.min_rounds;
-  p.OC = g.OC;
+  const int out_oc = a.out_oc > 0 ? a.out_oc : g.OC;   // channels of the output tensor (a sibling layer's chunk follows them in the accumulator)
+  if (a.out_oc > 0 && (a.out_oc % 16 != 0 || a.x_cols < 4 || a.x_cols % 4 != 0 || a.x_cols > 16 || g.OC != a.out_oc + 16 || g.OC > 256 || !a.x_out ||
+                       (reinterpret_cast<uintptr_t>(a.x_out) & 3) || (a.x_out_tile_stride & 3) || a.add))
+    return bail(fail(TOD_ERR_INVALID_ARG, "conv_tc: malformed sibling output (out_oc=%d, x_cols=%d, OC=%d)", a.out_oc, a.x_cols, g.OC));
+  p.OC = out_oc;
+  p.OCm = g.OC;
+  p.x_c0 = a.out_oc > 0 ? a.out_oc : 0;
+  p.x_cols = a.out_oc > 0 ? a.x_cols : 0;
+  p.x_out = a.x_out;
+  p.x_out_ts = a.x_out_tile_stride;
+  p.x_lut = a.x_lut;
   p.KH = g.KH;
   p.KW = g.KW;
   p.taps = g.KH * g.KW;
@@ -1524,7 +1557,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   p.a_stage = uint32_t((kBM * p.BK + 1023) / 1024 * 1024);
   p.b_stage = uint32_t((p.BN * p.BK + 1023) / 1024 * 1024);
   p.tx_bytes = uint32_t(p.rows * p.BK + p.BN * p.BK);
-  p.vec_store = (g.OC % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.out_tile_stride & 15) == 0) ? 1 : 0;
+  p.vec_store = (out_oc % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.out_tile_stride & 15) == 0) ? 1 : 0;
   // ---- fast epilogue eligibility: every channel requantises with a right shift in [1, 22], a non-negative multiplier,
   // and 2 * (accumulator + bias) stays inside int32
   const int ncls_full = (1 << g.KH) * (1 << g.KW);
@@ -1576,7 +1609,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     for (size_t i = 0; i < xmasks.size(); ++i) p.xmap[xmasks[i] & 7] = uint8_t(i);
   // ReLU-type activation (floor at or above the output zero point): the two-instruction requantisation (kEpiRelu)
   static const int relu_env = std::getenv("TOD_TC_RELU") ? std::atoi(std::getenv("TOD_TC_RELU")) : -1;
-  const bool relu = c->fast && !a.add && !a.rq.post_lut && a.rq.act_min >= a.rq.out_zp && p.vec_store && relu_env != 0;
+  const bool relu = c->fast && !a.add && !a.rq.post_lut && !p.x_cols && a.rq.act_min >= a.rq.out_zp && p.vec_store && relu_env != 0;
   const size_t table_bytes = c->fast ? size_t(p.OCp) * 16 + size_t(p.ncls) * p.OCp * (relu ? 8 : 4) : 0;
   if (table_bytes > 40 * 1024) c->fast = 0;
   if (!p.vec_store && p.n_tiles > 1) c->fast = 0;  // run staging needs whole rows (every output channel) in one tile
@@ -1598,6 +1631,8 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     if (a.add) c->mode |= kEpiAdd;
     if (relu) c->mode |= kEpiRelu;
   }
+  if (p.x_cols && (!c->fast || !(c->mode & kEpiTma) || p.n_tiles != 1))
+    return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: a sibling output needs the fast epilogue, a 16-byte-row host output and one N tile"));
   if (a.add && (!c->fast || (c->mode & kEpiLut) || !p.vec_store))
     return bail(fail(TOD_ERR_UNSUPPORTED, "conv_tc: a fused residual ADD needs the fast epilogue, 16-byte rows and no byte map"));
   // CTA pairs (cta_group::2) for the MMA-heavy layers: see conv_tc_pair_kernel
@@ -1605,7 +1640,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   {
     const int groups_max = p.flat ? 1 : (a.max_tiles + p.pn - 1) / p.pn;
     const long long m_tiles_max = p.flat ? ((long long)a.max_tiles * p.HW + kBM - 1) / kBM : (long long)groups_max * p.tiles_y * p.tiles_x;
-    c->pair = (c->fast && (c->mode & kEpiTma) && !(c->mode & (kEpiLut | kEpiAdd)) && !p.a_cp && p.BN % 32 == 0 && p.BN >= 64 &&
+    c->pair = (c->fast && !p.x_cols && (c->mode & kEpiTma) && !(c->mode & (kEpiLut | kEpiAdd)) && !p.a_cp && p.BN % 32 == 0 && p.BN >= 64 &&
                p.taps * p.kchunks >= 8 && m_tiles_max >= 64 && pair_env != 0) ? 1 : 0;
   }
   if (c->pair) {
@@ -1626,7 +1661,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
     // stores conflict gcd(OC / 16, 8) ways, so rows of 128 / 256 bytes keep the swizzled tensor store
     const int u = g.OC / 16;
     const int conflict = (u % 8 == 0) ? 8 : ((u % 4 == 0) ? 4 : ((u % 2 == 0) ? 2 : 1));
-    if (c->fast && !c->pair && (c->mode & kEpiTma) && p.flat && p.n_tiles == 1 && p.BN == g.OC && conflict <= 4 && lin_env != 0) p.lin = 1;
+    if (c->fast && !c->pair && !p.x_cols && (c->mode & kEpiTma) && p.flat && p.n_tiles == 1 && p.BN == g.OC && conflict <= 4 && lin_env != 0) p.lin = 1;
   }
   if (p.lin) {
     p.wo = 16;  // unused by the linear path (the tensor map is still encoded, with its smallest box)
@@ -1691,7 +1726,7 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
       qt[size_t(oc) * 4 + 0] = a.h_mult[oc];
       qt[size_t(oc) * 4 + 1] = rs;
       qt[size_t(oc) * 4 + 2] = int32_t(0x80000000u);
-      qt[size_t(oc) * 4 + 3] = (1 << (rs - 1)) + a.rq.out_zp * (1 << rs);
+      qt[size_t(oc) * 4 + 3] = (1 << (rs - 1)) + (oc >= out_oc ? a.x_out_zp : a.rq.out_zp) * (1 << rs);
     }
     std::vector<long long> a64(relu_mode ? size_t(p.ncls) * p.OCp : 0, 0);
     for (size_t yi = 0; yi < ymasks.size(); ++yi)
@@ -1794,18 +1829,18 @@ int conv_tc_create(const ConvTcArgs& a, ConvTc** out) {
   if (c->mode & kEpiTma) {
     // the output seen through the same patch tiling as the A operand; the box is [wo channels x patch]
     if (p.flat) {
-      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(a.max_tiles) * p.HW, 1, 1};
-      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(a.max_tiles) * p.HW * g.OC, uint64_t(a.max_tiles) * p.HW * g.OC};
+      const uint64_t dims[4] = {uint64_t(out_oc), uint64_t(a.max_tiles) * p.HW, 1, 1};
+      const uint64_t str[3] = {uint64_t(out_oc), uint64_t(a.max_tiles) * p.HW * out_oc, uint64_t(a.max_tiles) * p.HW * out_oc};
       const uint32_t box[4] = {uint32_t(p.wo), uint32_t(kBM), 1, 1};
       rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
     } else if (one) {
-      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(p.Wd), 1, uint64_t(a.max_tiles)};
-      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(a.out_tile_stride), uint64_t(a.out_tile_stride)};
+      const uint64_t dims[4] = {uint64_t(out_oc), uint64_t(p.Wd), 1, uint64_t(a.max_tiles)};
+      const uint64_t str[3] = {uint64_t(out_oc), uint64_t(a.out_tile_stride), uint64_t(a.out_tile_stride)};
       const uint32_t box[4] = {uint32_t(p.wo), uint32_t(p.pw), 1, uint32_t(p.pn)};
       rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
     } else {
-      const uint64_t dims[4] = {uint64_t(g.OC), uint64_t(g.OW), uint64_t(g.OH), uint64_t(a.max_tiles)};
-      const uint64_t str[3] = {uint64_t(g.OC), uint64_t(g.OW) * g.OC, uint64_t(a.out_tile_stride)};
+      const uint64_t dims[4] = {uint64_t(out_oc), uint64_t(g.OW), uint64_t(g.OH), uint64_t(a.max_tiles)};
+      const uint64_t str[3] = {uint64_t(out_oc), uint64_t(g.OW) * out_oc, uint64_t(a.out_tile_stride)};
       const uint32_t box[4] = {uint32_t(p.wo), uint32_t(p.pw), uint32_t(p.ph), uint32_t(p.pn)};
       rc = encode(&c->map_o, a.out, 4, dims, str, box, p.wo);
     }

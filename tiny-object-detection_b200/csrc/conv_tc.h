@@ -40,6 +40,16 @@ struct ConvTcArgs {
   int fast_epilogue = 1;             // 0 forces the general epilogue (cross-check)
   const ConvTcAdd* add = nullptr;    // fused ADD (requires the fast epilogue + TMA-storable output)
   int min_rounds = 1;                // tiles per CTA a launch gives at least (tod_yolact_options::batches_in_flight >= 2: two)
+  // ---- sibling output (a second, narrow convolution over the same input computed in the same launch: the box head riding the
+  // coefficient head, see yolact.cu "sibling-head fusion").  g.OC counts BOTH layers' channels: the host layer's `out_oc`
+  // (a multiple of 16) first, then `x_cols` sibling channels padded to a 16-column chunk; weights / bias / wsum / mult / shift
+  // cover all g.OC rows.  The host layer's output tensor has `out_oc` channels; the sibling's `x_cols` bytes per pixel go to x_out.
+  int out_oc = 0;                    // 0 = no sibling (the output has g.OC channels)
+  int x_cols = 0;                    // sibling channels (multiple of 4, <= 16)
+  int8_t* x_out = nullptr;           // device, [tile][OH][OW][x_cols]
+  int64_t x_out_tile_stride = 0;
+  int32_t x_out_zp = 0;              // the sibling's output zero point (rq.out_zp is the host layer's)
+  const uint8_t* x_lut = nullptr;    // device: the sibling's fused byte map (null: none)
 };
 
 // shape / alignment test only (no CUDA calls)

@@ -65,6 +65,13 @@ struct Step {
   bool relu_tab = false;   // the table at fast_off holds the ReLU form (Requant::relu_tab)
   bool add_conv_is_a = true;
   Place out_place;
+  // sibling-head fusion: a second, narrow convolution over the same input rides this one's launch (ConvTcArgs::out_oc ...)
+  int sib_out = -1;        // tensor the sibling's bytes are written to (its possibly moved output)
+  int sib_cols = 0, sib_host_oc = 0;
+  int32_t sib_zp = 0;
+  Place sib_place;
+  int64_t sib_lut_off = -1;
+  std::vector<uint8_t> sib_lut_host;
 };
 
 void conv_out_pad(int padding, int in, int k, int stride, int dil, int* out, int* pad) {
@@ -773,8 +780,82 @@ int plan(tod_yolact* y, ConstArena* arena) {
       --ai;
     }
   }
-  for (Step& st : y->steps)
+  // ---- sibling-head fusion: two convolutions over the SAME input with the same geometry, one of them at most 16 channels wide
+  // (the 12-column box head beside the 96-column coefficient head of every pyramid level).  The narrow one's time is all
+  // A-operand traffic - 3x3 x 256 channels re-read per tap for a 16-column MMA - so its weights become one more 16-column chunk
+  // of the wide one's accumulator: one launch, one pass over the activations, and the narrow layer's bytes leave from the
+  // epilogue registers into its own output (conv_tc.cu, TcParams::x_*).  Needs the tcgen05 fast epilogue for both (checked
+  // here with the planner's own criteria) and 16-byte rows for the wide one.
+  if (fuse && y->opt.conv_impl == 0 && !(std::getenv("TOD_HEAD_MERGE") && std::atoi(std::getenv("TOD_HEAD_MERGE")) == 0)) {
+    auto full_range = [](const Step& s) { return s.act_min == -128 && s.act_max == 127; };
+    for (size_t hi = 0; hi < y->steps.size(); ++hi) {
+      Step& H = y->steps[hi];
+      if (H.kind != kStepConvDirect || H.fused_add || H.fast_off < 0 || H.sib_cols || !full_range(H)) continue;
+      if (H.g.OC % 16 != 0 || H.g.OC + 16 > 256 || H.g.OC < 32) continue;
+      const Place hp = H.out_moved ? H.out_place : y->place[H.out];
+      if ((reinterpret_cast<uintptr_t>(hp.base) & 15) || (hp.tile_stride & 15) || (!H.out_moved && hp.c_store != H.g.OC)) continue;
+      const Place& hin = y->place[H.in0];
+      if (!conv_tc_supported(H.g, hin.tile_stride, hin.base, reinterpret_cast<const void*>(uintptr_t(256)))) continue;
+      if (H.g.KH * H.g.KW == 1 && hin.tile_stride == int64_t(H.g.IH) * H.g.IW * H.g.IC) continue;  // flat 1x1 layers take the flat-linear kernels
+      int pick = -1;
+      for (size_t bi = 0; bi < y->steps.size() && pick < 0; ++bi) {
+        const Step& B = y->steps[bi];
+        if (bi == hi || B.kind != kStepConvDirect || B.in0 != H.in0 || B.fused_add || B.fast_off < 0 || B.sib_cols || !full_range(B)) continue;
+        if (B.g.OC > 16 || B.g.OC % 4 != 0 || B.g.OC < 4) continue;
+        const ConvGeom &a = H.g, &b = B.g;
+        if (a.KH != b.KH || a.KW != b.KW || a.stride_h != b.stride_h || a.stride_w != b.stride_w || a.dil_h != b.dil_h || a.dil_w != b.dil_w ||
+            a.pad_top != b.pad_top || a.pad_left != b.pad_left || a.IH != b.IH || a.IW != b.IW || a.IC != b.IC || a.OH != b.OH || a.OW != b.OW || a.in_xor != b.in_xor)
+          continue;
+        const Place bp = B.out_moved ? B.out_place : y->place[B.out];
+        if ((reinterpret_cast<uintptr_t>(bp.base) & 3) || (bp.tile_stride & 3) || (!B.out_moved && bp.c_store != B.g.OC)) continue;
+        pick = int(bi);
+      }
+      if (pick < 0) continue;
+      const Step B = y->steps[pick];
+      const int OCh = H.g.OC, OCb = B.g.OC, OCt = OCh + 16, taps = H.g.KH * H.g.KW, IC = H.g.IC;
+      auto host = [&](int64_t off) { return arena->host.data() + off; };
+      // concatenated constants: host rows, sibling rows, zero rows (padding lanes copy the sibling's channel 0 requantisation)
+      std::vector<int8_t> w(size_t(OCt) * taps * IC, 0);
+      std::memcpy(w.data(), host(H.w_off), size_t(OCh) * taps * IC);
+      std::memcpy(w.data() + size_t(OCh) * taps * IC, host(B.w_off), size_t(OCb) * taps * IC);
+      std::vector<int32_t> bias(OCt, 0), wsum(size_t(OCt) * taps, 0), mult(OCt), shift(OCt);
+      if (H.bias_off >= 0) std::memcpy(bias.data(), host(H.bias_off), size_t(OCh) * 4);
+      if (B.bias_off >= 0) std::memcpy(bias.data() + OCh, host(B.bias_off), size_t(OCb) * 4);
+      std::memcpy(wsum.data(), host(H.wsum_off), size_t(OCh) * taps * 4);
+      std::memcpy(wsum.data() + size_t(OCh) * taps, host(B.wsum_off), size_t(OCb) * taps * 4);
+      const int32_t *hm = reinterpret_cast<const int32_t*>(host(H.mult_off)), *hs = reinterpret_cast<const int32_t*>(host(H.shift_off));
+      const int32_t *bm = reinterpret_cast<const int32_t*>(host(B.mult_off)), *bs = reinterpret_cast<const int32_t*>(host(B.shift_off));
+      for (int c = 0; c < OCt; ++c) {
+        mult[c] = c < OCh ? hm[c] : bm[c - OCh < OCb ? c - OCh : 0];
+        shift[c] = c < OCh ? hs[c] : bs[c - OCh < OCb ? c - OCh : 0];
+      }
+      Step M = H;
+      M.w_off = arena->add(w.data(), w.size());
+      M.bias_off = arena->add(bias.data(), bias.size() * 4);
+      M.wsum_off = arena->add(wsum.data(), wsum.size() * 4);
+      M.mult_off = arena->add(mult.data(), mult.size() * 4);
+      M.shift_off = arena->add(shift.data(), shift.size() * 4);
+      M.g.OC = OCt;
+      M.macs = H.macs + B.macs;
+      M.sib_out = B.out;
+      M.sib_cols = OCb;
+      M.sib_host_oc = OCh;
+      M.sib_zp = B.out_zp;
+      M.sib_place = B.out_moved ? B.out_place : y->place[B.out];
+      M.sib_lut_host = B.lut_host;
+      if (M.lut_host.empty() && !B.lut_host.empty()) {   // the epilogue applies byte maps per chunk: the host layer then needs one too
+        M.lut_host.resize(256);
+        for (int b = 0; b < 256; ++b) M.lut_host[b] = uint8_t(b);
+      }
+      y->steps[hi] = M;
+      y->steps.erase(y->steps.begin() + pick);
+      if (size_t(pick) < hi) --hi;
+    }
+  }
+  for (Step& st : y->steps) {
     if ((st.kind == kStepConvDirect || st.kind == kStepDepthwise) && !st.lut_host.empty()) st.post_lut_off = arena->add(st.lut_host.data(), 256);
+    if (st.sib_cols && !st.sib_lut_host.empty()) st.sib_lut_off = arena->add(st.sib_lut_host.data(), 256);
+  }
   // ---- ReLU-type layers (activation floor at or above the output zero point, no byte map / ADD behind them): the CUDA-core
   // kernels that read Requant::fast_tab (depthwise, RGB stem) get the two-instruction form (fixedpoint.cuh::requant_relu)
   if (y->opt.conv_impl != 2 && !(std::getenv("TOD_RELU_TAB") && std::atoi(std::getenv("TOD_RELU_TAB")) == 0))
@@ -796,8 +877,10 @@ int plan(tod_yolact* y, ConstArena* arena) {
   std::vector<std::vector<int>> op_steps(G.ops.size());  // steps generated for an op (its kernel, or a concat's copies)
   for (size_t i = 0; i < y->steps.size(); ++i) op_steps[y->steps[i].op].push_back(int(i));
   std::vector<std::vector<int>> writers(nt);  // steps whose (possibly moved) output is tensor t
-  for (size_t i = 0; i < y->steps.size(); ++i)
+  for (size_t i = 0; i < y->steps.size(); ++i) {
     if (y->steps[i].out_moved) writers[y->steps[i].out].push_back(int(i));
+    if (y->steps[i].sib_cols) writers[y->steps[i].sib_out].push_back(int(i));   // the merged launch is the sibling output's producer
+  }
   std::vector<std::vector<int>> memo(nt);
   std::vector<char> done(nt, 0);
   std::function<const std::vector<int>&(int)> producers = [&](int t) -> const std::vector<int>& {
@@ -875,6 +958,14 @@ int upload_consts_and_bind(tod_yolact* y, const ConstArena& arena) {
     a.h_mult = reinterpret_cast<const int32_t*>(arena.host.data() + st.mult_off);
     a.h_shift = reinterpret_cast<const int32_t*>(arena.host.data() + st.shift_off);
     a.fast_epilogue = y->opt.conv_impl == 2 ? 0 : 1;
+    if (st.sib_cols) {
+      a.out_oc = st.sib_host_oc;
+      a.x_cols = st.sib_cols;
+      a.x_out = reinterpret_cast<int8_t*>(st.sib_place.base);
+      a.x_out_tile_stride = st.sib_place.tile_stride;
+      a.x_out_zp = st.sib_zp;
+      a.x_lut = st.sib_lut_off >= 0 ? y->d_const + st.sib_lut_off : nullptr;
+    }
     ConvTcAdd fa{};
     if (st.fused_add) {
       const Place& pr = y->place[st.in1];
