@@ -75,6 +75,29 @@ def test_pdl_does_not_change_bytes(tod, models):
         assert np.array_equal(a["tile_classes"], rb["tile_classes"])
 
 
+def test_sibling_head_fusion_and_launch_sizing_do_not_change_bytes(tod, models, monkeypatch):
+    """The planner merges the box head of every pyramid level into the coefficient head's launch (58 instead of 63 tcgen05
+    launches); handles that share a GPU give each convolution CTA two tiles.  Neither changes a byte: all five outputs, the class
+    maps and the detections of the merged / throughput-sized plan against the separate / latency-sized one, odd tile count."""
+    full, _ = models
+    tiles = synth.rgb_tiles(7, seed=41)
+    monkeypatch.setenv("TOD_HEAD_MERGE", "0")
+    ya = tod.Yolact.init(full, max_tiles=7)
+    monkeypatch.delenv("TOD_HEAD_MERGE")
+    yb = tod.Yolact.init(full, max_tiles=7, batches_in_flight=3)
+    assert ya.stats()["tc_conv_layers"] == yb.stats()["tc_conv_layers"] + 5
+    a = ya.infer_tiles(tiles, detections=True)
+    for _ in range(2):
+        b = yb.infer_tiles(tiles, detections=True)
+        for k in range(5):
+            assert np.array_equal(a["outputs"][k], b["outputs"][k]), k
+        assert np.array_equal(a["tile_classes"], b["tile_classes"])
+        for da, db in zip(a["dets"], b["dets"]):
+            assert da["n"] == db["n"] and np.array_equal(da["prior"], db["prior"])
+            assert np.array_equal(da["score"].view(np.uint32), db["score"].view(np.uint32))
+            assert np.array_equal(da["box"].view(np.uint32), db["box"].view(np.uint32))
+
+
 @pytest.mark.parametrize("n,max_tiles", [(1, 1), (3, 3), (5, 7), (13, 16)])
 def test_tile_counts_cross_check(tod, models, n, max_tiles):
     """Odd and partial tile counts (patch groups with tail masking, CTA pairs with a dummy tile, flat GEMMs whose last
