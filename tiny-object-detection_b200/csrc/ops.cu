@@ -637,110 +637,6 @@ __global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const
   }
 }
 
-// ------------------------------------------------------------------ depthwise 3x3, burst form
-// The sliding kernel above keeps one input row (three 4-byte loads) in flight per thread and walks 7 - 16 rows: a chain of
-// 7 - 16 dependent memory round trips, ~1.4 - 2.4 TB/s whatever the layer (round-2 layer table: 10.5 us for the 9.6 MB of a
-// 14 x 14 x 384 layer, 29 us for the 51 MB of the 112 x 112 x 32 one).  Here a thread owns R consecutive output rows of its
-// (column, channel word) and issues ALL (R - 1) * STRIDE + 3 input rows before any arithmetic - one round trip per thread,
-// 15 - 18 independent loads in flight - and the parallelism comes from OH / R times more threads.  Rows shared between
-// vertically adjacent threads are re-read from L1 / L2 ((R + 2) / R input reads per byte).  Same arithmetic, same bytes.
-template <int STRIDE, bool SAT, bool RELU, int R>
-__global__ void __launch_bounds__(kDwThreads, 6) depthwise3x3_burst_kernel(const int8_t* __restrict__ in, int64_t in_ts,
-                                                                        const int8_t* __restrict__ w,
-                                                                        const int32_t* __restrict__ bias, int32_t in_zp,
-                                                                        ConvGeom g, Requant rq, int8_t* __restrict__ out,
-                                                                        int64_t out_ts) {
-  pdl_trigger();
-  constexpr int NR = (R - 1) * STRIDE + 3;
-  const int C = g.OC, CW = C >> 2;
-  const int j = blockIdx.x * kDwThreads + threadIdx.x;
-  if (j >= g.OW * CW) return;
-  const int ox = j / CW, c = (j - ox * CW) * 4;
-  auto transpose = [](unsigned a0, unsigned a1, unsigned a2, unsigned (&t)[4]) {
-    const unsigned lo = __byte_perm(a0, a1, 0x5140);
-    const unsigned hi = __byte_perm(a0, a1, 0x7362);
-    t[0] = __byte_perm(lo, a2, 0x4410);
-    t[1] = __byte_perm(lo, a2, 0x5532);
-    t[2] = __byte_perm(hi, a2, 0x6610);
-    t[3] = __byte_perm(hi, a2, 0x7732);
-  };
-  const unsigned zp4 = unsigned(in_zp & 0xFF) * 0x01010101u;
-  const int ix0 = ox * STRIDE - g.pad_left;
-  const bool vx0 = ix0 >= 0 && ix0 < g.IW, vx1 = ix0 + 1 >= 0 && ix0 + 1 < g.IW, vx2 = ix0 + 2 >= 0 && ix0 + 2 < g.IW;
-  const int oy0 = blockIdx.y * R;
-  const int iy0 = oy0 * STRIDE - g.pad_top;
-  const int64_t row_pitch = int64_t(g.IW) * C;
-  const int8_t* base = in + int64_t(blockIdx.z) * in_ts + int64_t(iy0) * row_pitch + int64_t(ix0) * C + c;
-  // filters and constants first (they do not depend on the previous kernel)
-  unsigned wv[3][3];
-#pragma unroll
-  for (int fy = 0; fy < 3; ++fy)
-#pragma unroll
-    for (int fx = 0; fx < 3; ++fx) wv[fy][fx] = unsigned(__ldg(reinterpret_cast<const int*>(w + int64_t(fy * 3 + fx) * C + c)));
-  int4 k[4];
-  int bs[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    k[q] = __ldg(rq.fast_tab + c + q);
-    bs[q] = bias ? __ldg(bias + c + q) : 0;
-  }
-  pdl_wait();
-  unsigned raw[NR][3];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int iy = iy0 + r;
-    const bool vy = iy >= 0 && iy < g.IH;
-    const int8_t* p = base + int64_t(r) * row_pitch;
-    raw[r][0] = raw[r][1] = raw[r][2] = zp4;
-    if (vy && vx0) raw[r][0] = *reinterpret_cast<const unsigned*>(p);
-    if (vy && vx1) raw[r][1] = *reinterpret_cast<const unsigned*>(p + C);
-    if (vy && vx2) raw[r][2] = *reinterpret_cast<const unsigned*>(p + 2 * C);
-  }
-  unsigned wt[3][4];
-  int wall[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int fy = 0; fy < 3; ++fy) {
-#pragma unroll
-    for (int fx = 0; fx < 3; ++fx)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) wall[q] += int(wv[fy][fx] << (24 - 8 * q)) >> 24;
-    transpose(wv[fy][0], wv[fy][1], wv[fy][2], wt[fy]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) wt[fy][q] &= 0x00FFFFFFu;
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) bs[q] -= in_zp * wall[q];
-  int8_t* op = out + int64_t(blockIdx.z) * out_ts + (int64_t(oy0) * g.OW + ox) * C + c;
-  const int64_t ostep = int64_t(g.OW) * C;
-  unsigned t[NR][4];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) transpose(raw[r][0], raw[r][1], raw[r][2], t[r]);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (oy0 + r >= g.OH) break;
-    int o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int a = __dp4a(int(t[r * STRIDE][q]), int(wt[0][q]), bs[q]);
-      a = __dp4a(int(t[r * STRIDE + 1][q]), int(wt[1][q]), a);
-      a = __dp4a(int(t[r * STRIDE + 2][q]), int(wt[2][q]), a);
-      if (RELU) o[q] = requant_relu(a, k[q].x, k[q].y, (int64_t(k[q].w) << 32) | int64_t(uint32_t(k[q].z)));
-      else o[q] = requant_tab(a, k[q].x, k[q].y, k[q].w);
-    }
-    unsigned packed;
-    if (SAT) {
-      unsigned hi;
-      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o[3]), "r"(o[2]), "r"(0u));
-      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(packed) : "r"(o[1]), "r"(o[0]), "r"(hi));
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = max(rq.act_min, min(rq.act_max, o[q]));
-      packed = (unsigned(o[0]) & 0xFFu) | ((unsigned(o[1]) & 0xFFu) << 8) | ((unsigned(o[2]) & 0xFFu) << 16) | (unsigned(o[3]) << 24);
-    }
-    *reinterpret_cast<unsigned*>(op + r * ostep) = packed;
-  }
-}
-
 // ------------------------------------------------------------------ depthwise 3x3, lean form (default)
 // ncu on the sliding kernel above (round 2, whole-step capture): 107 SASS instructions per output word of which ~32 are
 // the arithmetic (3 loads, 6 PRMT, 12 dp4a, 8 requantisation, 2 pack, 1 store); issue 57 - 67 %, ALU pipe 45 - 54 %,
@@ -1182,11 +1078,9 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
     const int words = g.OW * (g.OC / 4);
     const int gx = (words + kDwThreads - 1) / kDwThreads;
     const bool sat = rq.act_min == -128 && rq.act_max == 127;
-    // TOD_DW_IMPL: 0 (default) = lean kernel (sliding kernel where it does not apply), 2 = sliding kernel, 1 = burst kernel (all of
-    // a thread's input rows in flight at once; measured 2 % slower per step)
+    // TOD_DW_IMPL: 0 (default) = lean kernel (sliding kernel where it does not apply), 2 = sliding kernel.  (A burst variant - all
+    // of a thread's input rows in flight before any arithmetic - measured 2 % slower per step and was removed: DESIGN 5.2.)
     static const int dw_impl = std::getenv("TOD_DW_IMPL") ? std::atoi(std::getenv("TOD_DW_IMPL")) : 0;
-    static const int dw_r1 = std::getenv("TOD_DW_R1") ? std::atoi(std::getenv("TOD_DW_R1")) : 4;
-    static const int dw_r2 = std::getenv("TOD_DW_R2") ? std::atoi(std::getenv("TOD_DW_R2")) : 2;
     // lean kernel: ReLU-form table, at most one window column outside the image on either side, tile fits 32-bit word offsets
     const bool lean_ok = rq.relu_tab && g.IW >= 3 && g.pad_left <= 1 && (g.OW - 1) * g.stride_w - g.pad_left + 2 <= g.IW &&
                          int64_t(g.IH + 4) * g.IW * g.OC < (int64_t(1) << 31);
@@ -1214,24 +1108,6 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
       }
 #undef TOD_DWL_C
 #undef TOD_DWL
-      return;
-    }
-    if (dw_impl == 1) {
-      const int R = g.stride_h == 1 ? dw_r1 : dw_r2;
-      dim3 grid(gx, (g.OH + R - 1) / R, tiles);
-#define TOD_DWB(ST, SA, RE, RR) launch_k(depthwise3x3_burst_kernel<ST, SA, RE, RR>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts)
-#define TOD_DWB_R(ST, RR)                                                                   \
-  do {                                                                                      \
-    if (rq.relu_tab) { if (sat) TOD_DWB(ST, true, true, RR); else TOD_DWB(ST, false, true, RR); } \
-    else { if (sat) TOD_DWB(ST, true, false, RR); else TOD_DWB(ST, false, false, RR); }     \
-  } while (0)
-      if (g.stride_h == 1) {
-        if (R == 2) TOD_DWB_R(1, 2); else if (R == 3) TOD_DWB_R(1, 3); else TOD_DWB_R(1, 4);
-      } else {
-        if (R == 1) TOD_DWB_R(2, 1); else if (R == 3) TOD_DWB_R(2, 3); else TOD_DWB_R(2, 2);
-      }
-#undef TOD_DWB_R
-#undef TOD_DWB
       return;
     }
     // rows per block: long enough to amortise the two warm-up rows, short enough for >= ~4 CTAs per SM
