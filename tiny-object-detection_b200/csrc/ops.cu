@@ -398,6 +398,149 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_kernel(const int8_t* _
   }
 }
 
+// ------------------------------------------------------------------ stem, two output pixels per thread (default)
+// ncu on the kernel above: ~500 SASS instructions per (pixel, 16 channels) item for 144 dp4a - four 32-bit divisions to decode
+// the item, 36 weight LDS.128, 16 constant LDS.128, the input words and their funnel shifts.  Here a thread owns two horizontally
+// adjacent output pixels of one row (their windows share one of five input pixels: 15 contiguous bytes per filter row, and
+// 12 * pair is a whole number of words), so every weight / constant load feeds two outputs, and the item is decoded once per
+// thread: (pair, channel group) from the thread index, then kStemRows consecutive output rows by pointer increments.
+constexpr int kStemRows = 8;
+
+template <bool SAT, bool RELU>
+__global__ void __launch_bounds__(kStemThreads) stem3x3s2_pair_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+                                                                     const int8_t* __restrict__ w, const int32_t* __restrict__ bias,
+                                                                     int32_t in_zp, ConvGeom g, Requant rq, int8_t* __restrict__ out,
+                                                                     int64_t out_ts, int tiles) {
+  __shared__ int4 s_w[9 * 8 * 4];
+  __shared__ int s_bs[64];
+  __shared__ int4 s_k[64];
+  pdl_trigger();
+  const int OCg = g.OC;  // <= 64 (launcher checks)
+  int* s_wi = reinterpret_cast<int*>(s_w);   // s_wi[(fy*3 + k) * OC + oc] = weight bytes 4k .. 4k+3 of filter row fy (9 real bytes), 0-padded
+  for (int i = threadIdx.x; i < 9 * OCg; i += kStemThreads) {
+    const int oc = i % OCg, fk = i / OCg, fy = fk / 3, k = fk - fy * 3;
+    int word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = 4 * k + b;
+      if (j < 9) word |= (int(w[(int64_t(oc) * 9 + fy * 3 + j / 3) * 3 + j % 3]) & 0xFF) << (8 * b);
+    }
+    s_wi[i] = word;
+  }
+  for (int oc = threadIdx.x; oc < OCg; oc += kStemThreads) {
+    int sum = 0;
+    for (int j = 0; j < 27; ++j) sum += int(w[int64_t(oc) * 27 + j]);
+    s_bs[oc] = (bias ? bias[oc] : 0) - in_zp * sum;
+    s_k[oc] = rq.fast_tab[oc];
+  }
+  __syncthreads();
+  pdl_wait();
+  const int groups = OCg / kStemOct;
+  const int pairs = (g.OW + 1) >> 1;
+  const int ig = blockIdx.x * kStemThreads + threadIdx.x;
+  if (ig >= pairs * groups) return;
+  const int pr = ig / groups, grp = ig - pr * groups;
+  const int ox = 2 * pr, oc0 = grp * kStemOct;
+  const bool has_b = ox + 1 < g.OW;
+  const int ix0 = 2 * ox;                       // pad_left == 0; the pair's windows cover input columns ix0 .. ix0 + 4
+  const int valid_a = g.IW - ix0, valid_b = g.IW - ix0 - 2;  // pixels of each window inside the image (>= 3: all)
+  const int zp4 = (in_zp & 0xFF) * 0x01010101;
+  const int xr = g.in_xor * 0x01010101;         // folded uint8 -> int8 QUANTIZE (x ^ 0x80), 0 otherwise
+  const int rows_total = tiles * g.OH;
+  int row = blockIdx.y * kStemRows;
+  if (row >= rows_total) return;
+  int t = row / g.OH, oy = row - t * g.OH;
+  // bytes of pixels to the right of the image read as the zero point: keep the bytes of the first `valid` pixels of a window
+  auto clip = [&](int valid, int& x0, int& x1, int& x2) {
+    if (valid >= 3) return;
+    const int k0 = valid == 2 ? int(0xFFFFFFFFu) : (valid == 1 ? 0x00FFFFFF : 0);
+    const int k1 = valid == 2 ? 0x0000FFFF : 0;
+    x0 = (x0 & k0) | (zp4 & ~k0);
+    x1 = (x1 & k1) | (zp4 & ~k1);
+    x2 = zp4;
+  };
+  for (int rep = 0; rep < kStemRows && row < rows_total; ++rep, ++row) {
+    const int8_t* tin = in + int64_t(t) * in_ts;
+    int acc_a[kStemOct], acc_b[kStemOct];
+#pragma unroll
+    for (int j = 0; j < kStemOct; ++j) acc_a[j] = acc_b[j] = s_bs[oc0 + j];
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy) {
+      int a0 = zp4, a1 = zp4, a2 = zp4, b0 = zp4, b1 = zp4, b2 = zp4;
+      const int iy = 2 * oy + fy;               // pad_top == 0
+      if (iy < g.IH) {
+        const int64_t off = (int64_t(iy) * g.IW + ix0) * 3;          // even: 0 or 2 mod 4
+        const int* p = reinterpret_cast<const int*>(tin + (off & ~int64_t(3)));
+        const int sh = int(off & 3) * 8;
+        const int w0 = p[0] ^ xr, w1 = p[1] ^ xr, w2 = p[2] ^ xr, w3 = p[3] ^ xr, w4 = p[4] ^ xr;
+        const int c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh), c2 = __funnelshift_r(w2, w3, sh), c3 = __funnelshift_r(w3, w4, sh);
+        a0 = c0;                              // window A: bytes 0 .. 8 (the weight words are zero beyond byte 8)
+        a1 = c1;
+        a2 = c2;
+        b0 = __funnelshift_r(c1, c2, 16);     // window B: bytes 6 .. 14
+        b1 = __funnelshift_r(c2, c3, 16);
+        b2 = int(unsigned(c3) >> 16);
+        clip(valid_a, a0, a1, a2);
+        clip(valid_b, b0, b1, b2);
+      }
+      const int4* wr0 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 0) * OCg + oc0);
+      const int4* wr1 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 1) * OCg + oc0);
+      const int4* wr2 = reinterpret_cast<const int4*>(s_wi + (fy * 3 + 2) * OCg + oc0);
+#pragma unroll
+      for (int q = 0; q < kStemOct / 4; ++q) {
+        const int4 u0 = wr0[q], u1 = wr1[q], u2 = wr2[q];
+        acc_a[4 * q + 0] = __dp4a(a2, u2.x, __dp4a(a1, u1.x, __dp4a(a0, u0.x, acc_a[4 * q + 0])));
+        acc_a[4 * q + 1] = __dp4a(a2, u2.y, __dp4a(a1, u1.y, __dp4a(a0, u0.y, acc_a[4 * q + 1])));
+        acc_a[4 * q + 2] = __dp4a(a2, u2.z, __dp4a(a1, u1.z, __dp4a(a0, u0.z, acc_a[4 * q + 2])));
+        acc_a[4 * q + 3] = __dp4a(a2, u2.w, __dp4a(a1, u1.w, __dp4a(a0, u0.w, acc_a[4 * q + 3])));
+        acc_b[4 * q + 0] = __dp4a(b2, u2.x, __dp4a(b1, u1.x, __dp4a(b0, u0.x, acc_b[4 * q + 0])));
+        acc_b[4 * q + 1] = __dp4a(b2, u2.y, __dp4a(b1, u1.y, __dp4a(b0, u0.y, acc_b[4 * q + 1])));
+        acc_b[4 * q + 2] = __dp4a(b2, u2.z, __dp4a(b1, u1.z, __dp4a(b0, u0.z, acc_b[4 * q + 2])));
+        acc_b[4 * q + 3] = __dp4a(b2, u2.w, __dp4a(b1, u1.w, __dp4a(b0, u0.w, acc_b[4 * q + 3])));
+      }
+    }
+    unsigned pk_a[kStemOct / 4], pk_b[kStemOct / 4];
+#pragma unroll
+    for (int q = 0; q < kStemOct / 4; ++q) {
+      int oa[4], ob[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int4 k = s_k[oc0 + 4 * q + j];
+        if (RELU) {
+          const int64_t ad = (int64_t(k.w) << 32) | int64_t(uint32_t(k.z));
+          oa[j] = requant_relu(acc_a[4 * q + j], k.x, k.y, ad);
+          ob[j] = requant_relu(acc_b[4 * q + j], k.x, k.y, ad);
+        } else {
+          oa[j] = requant_tab(acc_a[4 * q + j], k.x, k.y, k.w);
+          ob[j] = requant_tab(acc_b[4 * q + j], k.x, k.y, k.w);
+        }
+      }
+      if (SAT) {
+        unsigned hi;
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(oa[3]), "r"(oa[2]), "r"(0u));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(pk_a[q]) : "r"(oa[1]), "r"(oa[0]), "r"(hi));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(ob[3]), "r"(ob[2]), "r"(0u));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(pk_b[q]) : "r"(ob[1]), "r"(ob[0]), "r"(hi));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          oa[j] = max(rq.act_min, min(rq.act_max, oa[j]));
+          ob[j] = max(rq.act_min, min(rq.act_max, ob[j]));
+        }
+        pk_a[q] = (unsigned(oa[0]) & 0xFFu) | ((unsigned(oa[1]) & 0xFFu) << 8) | ((unsigned(oa[2]) & 0xFFu) << 16) | (unsigned(oa[3]) << 24);
+        pk_b[q] = (unsigned(ob[0]) & 0xFFu) | ((unsigned(ob[1]) & 0xFFu) << 8) | ((unsigned(ob[2]) & 0xFFu) << 16) | (unsigned(ob[3]) << 24);
+      }
+    }
+    int8_t* op = out + int64_t(t) * out_ts + (int64_t(oy) * g.OW + ox) * g.OC + oc0;
+    *reinterpret_cast<uint4*>(op) = make_uint4(pk_a[0], pk_a[1], pk_a[2], pk_a[3]);
+    if (has_b) *reinterpret_cast<uint4*>(op + g.OC) = make_uint4(pk_b[0], pk_b[1], pk_b[2], pk_b[3]);
+    if (++oy == g.OH) {
+      oy = 0;
+      ++t;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ depthwise, register-resident filters
 // blockDim = (channel groups of 4, pixel lanes).  A thread keeps the 3x3 taps of its 4 channels (pre-masked so a
 // dp4a isolates one channel), their bias and requantisation constants in registers and walks over output pixels;
@@ -996,6 +1139,120 @@ __global__ void __launch_bounds__(256) resize16_kernel(const int8_t* __restrict_
   }
 }
 
+// 2 x 2 output pixels per thread.  With the 2x up-samplings of the FPN / protonet (half-pixel centres) the output rows 2k - 1 and 2k
+// interpolate between the same two input rows, and likewise the columns, so the four outputs of such a block share their four
+// corner loads and the byte interleave; only the dp2a against the two column weight pairs and the vertical blends are per output.
+// Blocks are anchored at odd coordinates (rows 2k - 1, 2k; the -1 / OH positions of the border blocks do not exist).  A block
+// whose rows or columns do not share their sources (other scales) computes its outputs one by one: same arithmetic, same bytes.
+__device__ __forceinline__ void resize16_one(const int8_t* __restrict__ tin, int IW, int C, int c, int y0, int y1, int wy1, int x0, int x1, int wx1,
+                                             int8_t* __restrict__ dst) {
+  const int wy0 = (1 << 10) - wy1, wx0 = (1 << 10) - wx1;
+  const unsigned wx = (unsigned(wx1) << 16) | (unsigned(wx0) & 0xFFFFu);
+  const uint4 p00 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0) * IW + x0) * C + c);
+  const uint4 p10 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1) * IW + x0) * C + c);
+  const uint4 p01 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0) * IW + x1) * C + c);
+  const uint4 p11 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1) * IW + x1) * C + c);
+  const unsigned ta[4] = {p00.x, p00.y, p00.z, p00.w}, td[4] = {p01.x, p01.y, p01.z, p01.w};
+  const unsigned tb[4] = {p10.x, p10.y, p10.z, p10.w}, te[4] = {p11.x, p11.y, p11.z, p11.w};
+  unsigned ow[4];
+#pragma unroll
+  for (int wd = 0; wd < 4; ++wd) {
+    int q[4];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const unsigned sel = hf ? 0x7362u : 0x5140u;
+      const unsigned ad = __byte_perm(ta[wd], td[wd], sel), be = __byte_perm(tb[wd], te[wd], sel);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ht = u ? __dp2a_hi(int(wx), int(ad), 0) : __dp2a_lo(int(wx), int(ad), 0);
+        const int hb = u ? __dp2a_hi(int(wx), int(be), 0) : __dp2a_lo(int(wx), int(be), 0);
+        const int o20 = wy0 * ht + wy1 * hb;
+        q[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+      }
+    }
+    ow[wd] = (unsigned(q[0]) & 0xFFu) | ((unsigned(q[1]) & 0xFFu) << 8) | ((unsigned(q[2]) & 0xFFu) << 16) | (unsigned(q[3]) << 24);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+__global__ void __launch_bounds__(256) resize16_quad_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
+                                                           int C, int8_t* __restrict__ out, int64_t out_ts, int OH, int OW,
+                                                           int hs, int ws, bool half_pixel) {
+  pdl_trigger();
+  pdl_wait();
+  const int t = blockIdx.y;
+  const int c16n = C >> 4;
+  const int bw = OW / 2 + 1, bh = OH / 2 + 1;        // blocks per row / column (anchored at -1: columns 2j - 1, 2j)
+  const int total = bh * bw * c16n;
+  const int8_t* tin = in + int64_t(t) * in_ts;
+  int8_t* tout = out + int64_t(t) * out_ts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (i % c16n) * 16;
+    const int bx = (i / c16n) % bw;
+    const int by = i / (c16n * bw);
+    const int ya = 2 * by - 1, yb = 2 * by, xa = 2 * bx - 1, xb = 2 * bx;
+    const bool va = ya >= 0, vb = yb < OH, ua = xa >= 0, ub = xb < OW;
+    int iy[2], y0[2], y1[2], ix[2], x0[2], x1[2];
+    resize_axis(va ? ya : yb, hs, IH, half_pixel, &iy[0], &y0[0], &y1[0]);
+    resize_axis(vb ? yb : ya, hs, IH, half_pixel, &iy[1], &y0[1], &y1[1]);
+    resize_axis(ua ? xa : xb, ws, IW, half_pixel, &ix[0], &x0[0], &x1[0]);
+    resize_axis(ub ? xb : xa, ws, IW, half_pixel, &ix[1], &x0[1], &x1[1]);
+    const int wy1[2] = {iy[0] - (1 << 10) * y0[0], iy[1] - (1 << 10) * y0[1]};
+    const int wx1[2] = {ix[0] - (1 << 10) * x0[0], ix[1] - (1 << 10) * x0[1]};
+    const bool shared = va && vb && ua && ub && y0[0] == y0[1] && y1[0] == y1[1] && x0[0] == x0[1] && x1[0] == x1[1];
+    if (!shared) {
+      if (va && ua) resize16_one(tin, IW, C, c, y0[0], y1[0], wy1[0], x0[0], x1[0], wx1[0], tout + (int64_t(ya) * OW + xa) * C + c);
+      if (va && ub) resize16_one(tin, IW, C, c, y0[0], y1[0], wy1[0], x0[1], x1[1], wx1[1], tout + (int64_t(ya) * OW + xb) * C + c);
+      if (vb && ua) resize16_one(tin, IW, C, c, y0[1], y1[1], wy1[1], x0[0], x1[0], wx1[0], tout + (int64_t(yb) * OW + xa) * C + c);
+      if (vb && ub) resize16_one(tin, IW, C, c, y0[1], y1[1], wy1[1], x0[1], x1[1], wx1[1], tout + (int64_t(yb) * OW + xb) * C + c);
+      continue;
+    }
+    const uint4 p00 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0[0]) * IW + x0[0]) * C + c);
+    const uint4 p10 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1[0]) * IW + x0[0]) * C + c);
+    const uint4 p01 = *reinterpret_cast<const uint4*>(tin + (int64_t(y0[0]) * IW + x1[0]) * C + c);
+    const uint4 p11 = *reinterpret_cast<const uint4*>(tin + (int64_t(y1[0]) * IW + x1[0]) * C + c);
+    const unsigned ta[4] = {p00.x, p00.y, p00.z, p00.w}, td[4] = {p01.x, p01.y, p01.z, p01.w};
+    const unsigned tb[4] = {p10.x, p10.y, p10.z, p10.w}, te[4] = {p11.x, p11.y, p11.z, p11.w};
+    const unsigned wxa = (unsigned(wx1[0]) << 16) | (unsigned((1 << 10) - wx1[0]) & 0xFFFFu);
+    const unsigned wxb = (unsigned(wx1[1]) << 16) | (unsigned((1 << 10) - wx1[1]) & 0xFFFFu);
+    const int wya0 = (1 << 10) - wy1[0], wya1 = wy1[0], wyb0 = (1 << 10) - wy1[1], wyb1 = wy1[1];
+    unsigned o_aa[4], o_ab[4], o_ba[4], o_bb[4];   // (row a/b, column a/b)
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      int qaa[4], qab[4], qba[4], qbb[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const unsigned sel = hf ? 0x7362u : 0x5140u;
+        const unsigned ad = __byte_perm(ta[wd], td[wd], sel), be = __byte_perm(tb[wd], te[wd], sel);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int hta = u ? __dp2a_hi(int(wxa), int(ad), 0) : __dp2a_lo(int(wxa), int(ad), 0);
+          const int hba = u ? __dp2a_hi(int(wxa), int(be), 0) : __dp2a_lo(int(wxa), int(be), 0);
+          const int htb = u ? __dp2a_hi(int(wxb), int(ad), 0) : __dp2a_lo(int(wxb), int(ad), 0);
+          const int hbb = u ? __dp2a_hi(int(wxb), int(be), 0) : __dp2a_lo(int(wxb), int(be), 0);
+          int o20 = wya0 * hta + wya1 * hba;
+          qaa[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+          o20 = wya0 * htb + wya1 * hbb;
+          qab[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+          o20 = wyb0 * hta + wyb1 * hba;
+          qba[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+          o20 = wyb0 * htb + wyb1 * hbb;
+          qbb[2 * hf + u] = (o20 + (o20 >> 31) + (1 << 19)) >> 20;
+        }
+      }
+      o_aa[wd] = (unsigned(qaa[0]) & 0xFFu) | ((unsigned(qaa[1]) & 0xFFu) << 8) | ((unsigned(qaa[2]) & 0xFFu) << 16) | (unsigned(qaa[3]) << 24);
+      o_ab[wd] = (unsigned(qab[0]) & 0xFFu) | ((unsigned(qab[1]) & 0xFFu) << 8) | ((unsigned(qab[2]) & 0xFFu) << 16) | (unsigned(qab[3]) << 24);
+      o_ba[wd] = (unsigned(qba[0]) & 0xFFu) | ((unsigned(qba[1]) & 0xFFu) << 8) | ((unsigned(qba[2]) & 0xFFu) << 16) | (unsigned(qba[3]) << 24);
+      o_bb[wd] = (unsigned(qbb[0]) & 0xFFu) | ((unsigned(qbb[1]) & 0xFFu) << 8) | ((unsigned(qbb[2]) & 0xFFu) << 16) | (unsigned(qbb[3]) << 24);
+    }
+    int8_t* d0 = tout + (int64_t(ya) * OW + xa) * C + c;
+    *reinterpret_cast<uint4*>(d0) = make_uint4(o_aa[0], o_aa[1], o_aa[2], o_aa[3]);
+    *reinterpret_cast<uint4*>(d0 + C) = make_uint4(o_ab[0], o_ab[1], o_ab[2], o_ab[3]);
+    *reinterpret_cast<uint4*>(d0 + int64_t(OW) * C) = make_uint4(o_ba[0], o_ba[1], o_ba[2], o_ba[3]);
+    *reinterpret_cast<uint4*>(d0 + int64_t(OW) * C + C) = make_uint4(o_bb[0], o_bb[1], o_bb[2], o_bb[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const uint8_t* __restrict__ in, int64_t in_ts,
                                                   uint8_t* __restrict__ out, int64_t out_ts, int64_t bytes, bool vec) {
   const int t = blockIdx.y;
@@ -1034,6 +1291,18 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
                         cudaStream_t s) {
   // the RGB stem: 3x3, stride 2, no top / left padding, 16-byte-aligned 16-channel output groups
   if (stem_kernel_eligible(g, rq, in, in_ts, out, out_ts) && int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct) < (int64_t(1) << 31)) {
+    static const int stem_impl = std::getenv("TOD_STEM_IMPL") ? std::atoi(std::getenv("TOD_STEM_IMPL")) : 0;  // 0 = two pixels per thread, 1 = one
+    if (stem_impl == 0 && int64_t(tiles) * g.OH <= 65535 * int64_t(kStemRows)) {
+      const int items = ((g.OW + 1) / 2) * (g.OC / kStemOct);
+      dim3 grid2(unsigned((items + kStemThreads - 1) / kStemThreads), unsigned((int64_t(tiles) * g.OH + kStemRows - 1) / kStemRows));
+      if (rq.act_min == -128 && rq.act_max == 127)
+        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<true, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
+                    : launch_k(stem3x3s2_pair_kernel<true, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+      else
+        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<false, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
+                    : launch_k(stem3x3s2_pair_kernel<false, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+      return;
+    }
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
     dim3 grid(unsigned((total + kStemThreads * kStemIters - 1) / (kStemThreads * kStemIters)));
     if (rq.act_min == -128 && rq.act_max == 127)
@@ -1175,6 +1444,12 @@ void launch_resize_bilinear(const int8_t* in, int64_t in_ts, int IH, int IW, int
   if (align_corners && OH > 1) hs = ((1 << 10) * (IH - 1) + (OH - 1) / 2) / (OH - 1);
   if (align_corners && OW > 1) ws = ((1 << 10) * (IW - 1) + (OW - 1) / 2) / (OW - 1);
   if (C % 16 == 0 && aligned16(in, in_ts) && aligned16(out, out_ts) && int64_t(OH) * OW * C < (int64_t(1) << 31)) {
+    static const int resize_impl = std::getenv("TOD_RESIZE_IMPL") ? std::atoi(std::getenv("TOD_RESIZE_IMPL")) : 0;  // 0 = 2 x 2 outputs per thread, 1 = one
+    if (resize_impl == 0 && OH % 2 == 0 && OW % 2 == 0 && OH >= 2 && OW >= 2) {
+      dim3 gridq(grid_for(int64_t(OH / 2 + 1) * (OW / 2 + 1) * (C / 16), 256, tiles), tiles);
+      launch_k(resize16_quad_kernel, gridq, dim3(256), 0, s, in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
+      return;
+    }
     dim3 grid16(grid_for(int64_t(OH) * OW * (C / 16), 256, tiles), tiles);
     launch_k(resize16_kernel, grid16, dim3(256), 0, s, in, in_ts, IH, IW, C, out, out_ts, OH, OW, hs, ws, half_pixel);
     return;
