@@ -379,6 +379,14 @@ struct IouTest {
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmall = 512;
 constexpr int kNmsRank = 256;   // lists up to this long are rank-sorted (needs top_k <= sort_cap / 2, checked per launch)
+constexpr int kNmsBins = 1024;  // score histogram of the longer lists: 4 bins per thread
+static_assert(kNmsBins == 4 * kNmsThreads, "one thread owns four histogram bins");
+
+// monotone bin of a candidate key's score (float bits in the high word): exponents 2^-5 .. 2^-1 with 7 mantissa bits each, clamped
+__device__ __forceinline__ int nms_bin(unsigned long long key) {
+  const int v = int(unsigned(key >> 48)) - (122 << 7);
+  return min(kNmsBins - 1, max(0, v));
+}
 
 // One (class, tile) list.  All threads of the CTA call it with the same arguments.
 //  * sort: lists of <= kNmsRank candidates are rank-sorted (keys are unique - the prior index is part of the key - so a
@@ -398,19 +406,78 @@ __device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers&
   const int m = min(n, c.top_k);
   const float4* boxes = reinterpret_cast<const float4*>(b.boxes) + int64_t(t) * c.P;
   for (int i = threadIdx.x; i < m; i += kNmsThreads) s_sup[i] = 0;
-  if (n <= kNmsRank && n <= sort_cap / 2) {
+  // Lists longer than the rank sort takes only need their top_k best keys: a 1024-bin histogram of the score (a monotone function
+  // of its float bits between 2^-5 and 1), a suffix scan for the bin the top_k-th best key falls in, and a compaction of the keys
+  // at or above that bin - usually a few more than top_k - which then take the rank sort below.  (The bitonic sort of all n keys
+  // remains for the lists whose cut bin is too crowded: 45 - 66 barrier-separated rounds over 512 - 2048 keys.)
+  int nn = n;
+  bool compacted = false;
+  if (n > kNmsRank && sort_cap / 2 >= kNmsRank) {
+    __shared__ int s_hist[kNmsBins];
+    __shared__ int s_warp[kNmsThreads / 32];
+    __shared__ int s_cut, s_cnt;
+    for (int i = threadIdx.x; i < kNmsBins; i += kNmsThreads) s_hist[i] = 0;
+    if (threadIdx.x == 0) {
+      s_cnt = 0;
+      s_cut = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) atomicAdd(&s_hist[nms_bin(src[i])], 1);
+    __syncthreads();
+    // suffix sums, 4 consecutive bins per thread, highest bins first (thread 0 owns the top four)
+    const int b0 = kNmsBins - 4 * (int(threadIdx.x) + 1);
+    const int h3 = s_hist[b0 + 3], h2 = s_hist[b0 + 2], h1 = s_hist[b0 + 1], h0 = s_hist[b0];
+    const int mine = h0 + h1 + h2 + h3;
+    int incl = mine;
+    const int ln = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (ln >= o) incl += v;
+    }
+    if (ln == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int above = incl - mine;
+    for (int wq = 0; wq < wid; ++wq) above += s_warp[wq];
+    if (above < m && above + mine >= m) {   // the m-th best key lies in one of my bins
+      int cut = b0 + 3, acc = above + h3;
+      if (acc < m) { cut = b0 + 2; acc += h2; }
+      if (acc < m) { cut = b0 + 1; acc += h1; }
+      if (acc < m) { cut = b0; }
+      s_cut = cut;
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+      const unsigned long long key = src[i];
+      if (nms_bin(key) >= cut) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        if (slot < kNmsRank) s_keys[slot] = key;
+      }
+    }
+    __syncthreads();
+    if (s_cnt <= kNmsRank) {   // uniform
+      nn = s_cnt;              // >= m by construction of the cut
+      compacted = true;
+    }
+  }
+  if (nn <= kNmsRank && nn <= sort_cap / 2) {
     unsigned long long key = 0ull;
     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (int(threadIdx.x) < n) {   // n <= kNmsRank == kNmsThreads: one candidate per thread
-      key = src[threadIdx.x];
-      s_keys[threadIdx.x] = key;
+    if (int(threadIdx.x) < nn) {   // nn <= kNmsRank == kNmsThreads: one candidate per thread
+      if (compacted) {
+        key = s_keys[threadIdx.x];
+      } else {
+        key = src[threadIdx.x];
+        s_keys[threadIdx.x] = key;
+      }
       bx = boxes[int(0xFFFFFFFFu - unsigned(key & 0xFFFFFFFFull))];
     }
     __syncthreads();
-    if (int(threadIdx.x) < n) {
+    if (int(threadIdx.x) < nn) {
       int rank = 0;
 #pragma unroll 8
-      for (int q = 0; q < n; ++q) rank += s_keys[q] > key ? 1 : 0;
+      for (int q = 0; q < nn; ++q) rank += s_keys[q] > key ? 1 : 0;
       if (rank < m) {
         s_keys[sort_cap / 2 + rank] = key;
         s_box[rank] = bx;
