@@ -655,15 +655,15 @@ def main():
                                          "d2h_bytes_per_step": int(pn * W4 * H4 * (4 + 52)),
                                          "call": "tod_pool_rgbd_batch: 192 host frames + depth per call, %d handles behind the C ABI; 4.3 MB of read-back per frame (PCIe-bound)" % pool_depth}
             # the reference's own call: Yolact::classify on 640x480 frames, in place, host buffer (yolact.rs:39)
-            cn = 96
+            cn = 32 * pool_depth   # one 32-frame chunk per handle and call: the warm-up call touches every handle's buffers
             cf = torch.from_numpy(np.tile(synth.rgb_frames(8, seed=5 + rank), (cn // 8, 1)).view(np.int32)).pin_memory()
 
             def classify_e2e():
                 tod_b200._lib.check(lib.tod_pool_classify_batch(pool._h, cf.data_ptr(), cn, 640, 480))
 
-            es = host_timed(classify_e2e, 3, warm=1)
+            es = host_timed(classify_e2e, 3, warm=2)
             line["classify_e2e"] = {"value": world * cn * 3 / es, "unit": "frames/s", "h2d_bytes_per_step": int(cn * 640 * 480 * 4), "d2h_bytes_per_step": int(cn * 640 * 480 * 4),
-                                    "call": "tod_pool_classify_batch: 96 frames of 640x480 u32 per call, classified in place (Yolact::classify for every frame), %d handles behind the C ABI" % pool_depth}
+                                    "call": "tod_pool_classify_batch: %d frames of 640x480 u32 per call, classified in place (Yolact::classify for every frame), %d handles behind the C ABI" % (cn, pool_depth)}
             # one synchronous caller, tiles: the pooled form of tod_yolact_infer_tiles_cells
             tn = 8 * n
             pt = torch.from_numpy(np.tile(synth.rgb_tiles(n, seed=2 + rank), (8, 1, 1, 1))).pin_memory()
