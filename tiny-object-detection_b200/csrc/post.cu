@@ -239,7 +239,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* k, int n) 
 // decode + softmax + per-class candidate lists.  One thread per prior; the class bytes of the CTA's
 // priors are staged through shared memory so the global read is coalesced.
 constexpr int kDecodeThreads = 128;
-__global__ void __launch_bounds__(kDecodeThreads) decode_kernel(DetectCfg c, DetectBuffers b, const uint8_t* __restrict__ cls,
+__global__ void __launch_bounds__(kDecodeThreads, 12) decode_kernel(DetectCfg c, DetectBuffers b, const uint8_t* __restrict__ cls,
                                                                int64_t cls_ts, const uint8_t* __restrict__ box, int64_t box_ts) {
   extern __shared__ uint8_t s_q[];  // [kDecodeThreads][C]
   __shared__ float s_exp[256];
