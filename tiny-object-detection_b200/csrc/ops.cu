@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(kDwThreads, 8) depthwise3x3_slide_kernel(const
 //     the loop counter only).
 // Bytes are identical to the sliding kernel (tests/test_gpu_graph.py, test_gpu_property.py run both against the oracle).
 template <int STRIDE, bool SAT, bool RELU, int CWT>
-__global__ void __launch_bounds__(kDwThreads, STRIDE == 1 ? 7 : 8) depthwise3x3_lean_kernel(const int8_t* __restrict__ in, int64_t in_ts,
+__global__ void __launch_bounds__(kDwThreads, 6) depthwise3x3_lean_kernel(const int8_t* __restrict__ in, int64_t in_ts,
                                                                       const int8_t* __restrict__ w,
                                                                       const int32_t* __restrict__ bias, int32_t in_zp,
                                                                       ConvGeom g, Requant rq, int8_t* __restrict__ out,
@@ -1175,7 +1175,7 @@ __device__ __forceinline__ void resize16_one(const int8_t* __restrict__ tin, int
   *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
-__global__ void __launch_bounds__(256) resize16_quad_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
+__global__ void __launch_bounds__(256, 4) resize16_quad_kernel(const int8_t* __restrict__ in, int64_t in_ts, int IH, int IW,
                                                            int C, int8_t* __restrict__ out, int64_t out_ts, int OH, int OW,
                                                            int hs, int ws, bool half_pixel) {
   pdl_trigger();
