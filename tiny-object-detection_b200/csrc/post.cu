@@ -542,7 +542,7 @@ __device__ __forceinline__ void nms_one(const DetectCfg& c, const DetectBuffers&
 
 // Fast-NMS, one CTA per (class, tile) whose list has at most n_hi candidates (8 KB of shared memory: the whole grid is
 // resident at once).  Longer lists belong to nms_long_kernel.
-__global__ void __launch_bounds__(kNmsThreads, 8) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_hi) {
+__global__ void __launch_bounds__(kNmsThreads, 6) nms_kernel(DetectCfg c, DetectBuffers b, int sort_cap, int n_hi) {
   extern __shared__ unsigned long long s_keys[];  // [sort_cap] then float4 boxes[top_k], float areas[top_k], int suppressed[top_k]
   const int k = blockIdx.x, t = blockIdx.y;
   const int n = b.cand_count[int64_t(t) * (c.C - 1) + k];
