@@ -1354,9 +1354,13 @@ void launch_depthwise(const int8_t* in, int64_t in_ts, const int8_t* w, const in
     const bool lean_ok = rq.relu_tab && g.IW >= 3 && g.pad_left <= 1 && (g.OW - 1) * g.stride_w - g.pad_left + 2 <= g.IW &&
                          int64_t(g.IH + 4) * g.IW * g.OC < (int64_t(1) << 31);
     if (dw_impl == 0 && lean_ok) {
+      // rows per thread: every run re-loads and re-transposes two halo rows, so runs are as long as keeps ~4 CTAs per SM in the
+      // grid (measured: 8 per SM / 16 rows -> 4 per SM / 28 rows = -2 % per step; longer runs or fewer CTAs no better)
+      static const int dw_min_ctas = std::getenv("TOD_DW_MINCTAS") ? std::atoi(std::getenv("TOD_DW_MINCTAS")) : 148 * 4;
+      static const int dw_max_rows = std::getenv("TOD_DW_MAXROWS") ? std::atoi(std::getenv("TOD_DW_MAXROWS")) : 28;
       int rpb = g.OH;
-      while (rpb > 4 && int64_t(gx) * ((g.OH + rpb - 1) / rpb) * tiles < 148 * 8) rpb = (rpb + 1) / 2;
-      rpb = std::min(rpb, 16);
+      while (rpb > 4 && int64_t(gx) * ((g.OH + rpb - 1) / rpb) * tiles < dw_min_ctas) rpb = (rpb + 1) / 2;
+      rpb = std::min(rpb, dw_max_rows);
       dim3 grid(gx, (g.OH + rpb - 1) / rpb, tiles);
       const int cw = g.OC / 4;
 #define TOD_DWL(ST, SA, CWT) launch_k(depthwise3x3_lean_kernel<ST, SA, true, CWT>, grid, dim3(kDwThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, rpb)
