@@ -410,7 +410,7 @@ template <bool SAT, bool RELU>
 __global__ void __launch_bounds__(kStemThreads) stem3x3s2_pair_kernel(const int8_t* __restrict__ in, int64_t in_ts,
                                                                      const int8_t* __restrict__ w, const int32_t* __restrict__ bias,
                                                                      int32_t in_zp, ConvGeom g, Requant rq, int8_t* __restrict__ out,
-                                                                     int64_t out_ts, int tiles) {
+                                                                     int64_t out_ts, int tiles, int rows_per_cta) {
   __shared__ int4 s_w[9 * 8 * 4];
   __shared__ int s_bs[64];
   __shared__ int4 s_k[64];
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_pair_kernel(const int8
   const int zp4 = (in_zp & 0xFF) * 0x01010101;
   const int xr = g.in_xor * 0x01010101;         // folded uint8 -> int8 QUANTIZE (x ^ 0x80), 0 otherwise
   const int rows_total = tiles * g.OH;
-  int row = blockIdx.y * kStemRows;
+  int row = blockIdx.y * rows_per_cta;
   if (row >= rows_total) return;
   int t = row / g.OH, oy = row - t * g.OH;
   // bytes of pixels to the right of the image read as the zero point: keep the bytes of the first `valid` pixels of a window
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kStemThreads) stem3x3s2_pair_kernel(const int8
     x1 = (x1 & k1) | (zp4 & ~k1);
     x2 = zp4;
   };
-  for (int rep = 0; rep < kStemRows && row < rows_total; ++rep, ++row) {
+  for (int rep = 0; rep < rows_per_cta && row < rows_total; ++rep, ++row) {
     const int8_t* tin = in + int64_t(t) * in_ts;
     int acc_a[kStemOct], acc_b[kStemOct];
 #pragma unroll
@@ -1292,15 +1292,16 @@ void launch_conv_direct(const int8_t* in, int64_t in_ts, const int8_t* w, const 
   // the RGB stem: 3x3, stride 2, no top / left padding, 16-byte-aligned 16-channel output groups
   if (stem_kernel_eligible(g, rq, in, in_ts, out, out_ts) && int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct) < (int64_t(1) << 31)) {
     static const int stem_impl = std::getenv("TOD_STEM_IMPL") ? std::atoi(std::getenv("TOD_STEM_IMPL")) : 0;  // 0 = two pixels per thread, 1 = one
-    if (stem_impl == 0 && int64_t(tiles) * g.OH <= 65535 * int64_t(kStemRows)) {
+    static const int stem_rows = std::getenv("TOD_STEM_ROWS") ? std::max(1, std::atoi(std::getenv("TOD_STEM_ROWS"))) : kStemRows;
+    if (stem_impl == 0 && int64_t(tiles) * g.OH <= 65535 * int64_t(stem_rows)) {
       const int items = ((g.OW + 1) / 2) * (g.OC / kStemOct);
-      dim3 grid2(unsigned((items + kStemThreads - 1) / kStemThreads), unsigned((int64_t(tiles) * g.OH + kStemRows - 1) / kStemRows));
+      dim3 grid2(unsigned((items + kStemThreads - 1) / kStemThreads), unsigned((int64_t(tiles) * g.OH + stem_rows - 1) / stem_rows));
       if (rq.act_min == -128 && rq.act_max == 127)
-        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<true, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
-                    : launch_k(stem3x3s2_pair_kernel<true, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<true, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles, stem_rows)
+                    : launch_k(stem3x3s2_pair_kernel<true, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles, stem_rows);
       else
-        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<false, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles)
-                    : launch_k(stem3x3s2_pair_kernel<false, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles);
+        rq.relu_tab ? launch_k(stem3x3s2_pair_kernel<false, true>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles, stem_rows)
+                    : launch_k(stem3x3s2_pair_kernel<false, false>, grid2, dim3(kStemThreads), 0, s, in, in_ts, w, bias, in_zp, g, rq, out, out_ts, tiles, stem_rows);
       return;
     }
     const int64_t total = int64_t(tiles) * g.OH * g.OW * (g.OC / kStemOct);
