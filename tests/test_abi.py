@@ -37,6 +37,13 @@ def test_abi_version_and_defaults(tod):
     lib.tod_yolact_default_options(C.byref(o))
     assert (o.top_k, o.max_dets, o.id_mode) == (200, 100, 0)
     assert abs(o.conf_thresh - 0.05) < 1e-7 and abs(o.nms_thresh - 0.5) < 1e-7
+    # the struct's last fields: a layout drift between include/tod.h and the ctypes mirror would land elsewhere
+    assert (o.use_cuda_graph, o.conv_impl, o.fusion, o.use_pdl, o.batches_in_flight) == (1, 0, 1, 1, 1)
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "tod.h")).read()
+    body = re.search(r"typedef struct tod_yolact_options \{(.*?)\} tod_yolact_options;", hdr, re.S).group(1)
+    fields = re.findall(r"^\s*(?:int32_t|float)\s+(\w+);", body, re.M)
+    assert fields == [f[0] for f in YolactOptions._fields_]
 
 
 def test_model_inspect_matches_reference_op_log(tod, models):
