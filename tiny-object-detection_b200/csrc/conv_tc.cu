@@ -3,7 +3,8 @@
 // Replaces the CONV_2D kernels TFLite runs inside interpreter.invoke() (/root/reference/src/yolact.rs:163)
 // for stride-1 1x1 / 3x3 layers with Cin % 16 == 0 — >97 % of the graph's multiply-accumulates.
 //
-// Kernel anatomy (persistent, one CTA per SM, 8 warps):
+// Kernel anatomy (persistent, at most one CTA per SM - the launch asks for the CTAs that keep every round of tiles full, see
+// conv_tc_launch - 12 warps):
 //   warp 0   TMA producer   per (filter tap, K chunk): one 4-D activation box [BK ch x pw x ph x pn] fetched at the
 //                           tap's shifted coordinates (out-of-image elements are zero-filled by the TMA unit = SAME
 //                           padding) and one 3-D weight box [BK x 1 tap x BN], both 32/64/128B-swizzled, K-major
