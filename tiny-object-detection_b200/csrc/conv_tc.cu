@@ -650,6 +650,12 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (p.b_res && threadIdx.x == 0) {
+    // resident weights (every tile of this CTA multiplies by the same N tile): the whole matrix once, and - weights being
+    // constants - ahead of the wait for the previous kernel, so the load runs under its tail
+    mbar_expect_tx(&ctl->b_full, uint32_t(p.kchunks * p.BN * p.BK));
+    for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
+  }
   pdl_wait();  // everything above touched constants only; activations (and our output buffer) are safe from here on
 
   if (p.a_cp && (warp == 0 || warp == 2 || warp == 3)) {
@@ -663,10 +669,6 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
     if (pt == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     int stage = 0;
     uint32_t phase = 0;
-    if (p.b_res && pt == 0) {  // the whole weight matrix once: every tile of this CTA multiplies by the same N tile
-      mbar_expect_tx(&ctl->b_full, uint32_t(p.kchunks * p.BN * p.BK));
-      for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
-    }
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       if (p.late_trig && pt == 0 && work + int(gridDim.x) >= total_work) pdl_trigger();
       const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
@@ -709,10 +711,6 @@ __device__ __forceinline__ void conv_tc_fast_body(const CUtensorMap& map_a, cons
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      if (p.b_res) {
-        mbar_expect_tx(&ctl->b_full, uint32_t(p.kchunks * p.BN * p.BK));
-        for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(smem_b + size_t(kc) * p.b_stage, &map_b, &ctl->b_full, kc * p.BK, 0, 0);
-      }
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         if (p.late_trig && work + int(gridDim.x) >= total_work) pdl_trigger();
         const WorkItem w = decode_work(work, p.n_tiles, tiles_x, p.tiles_y);
